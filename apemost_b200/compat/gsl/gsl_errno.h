@@ -1,0 +1,5 @@
+/* gsl_errno.h -- part of the minimal GSL-compatible header set; see gsl_compat.h */
+#ifndef APM_COMPAT_GSL_ERRNO_H_
+#define APM_COMPAT_GSL_ERRNO_H_
+#include "gsl_compat.h"
+#endif

@@ -1,0 +1,5 @@
+/* gsl_sf.h -- part of the minimal GSL-compatible header set; see gsl_compat.h */
+#ifndef APM_COMPAT_GSL_SF_H_
+#define APM_COMPAT_GSL_SF_H_
+#include "gsl_compat.h"
+#endif
