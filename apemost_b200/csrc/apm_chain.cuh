@@ -1,0 +1,511 @@
+// apm_chain.cuh -- device-side chain state and the per-chain Metropolis / parallel
+// tempering / calibration logic.  These __device__ functions restate, one to one, the
+// reference's control code; both kernel families (the tiled path's control kernel and
+// the fused persistent kernel) call them, so the semantics exist exactly once.
+#pragma once
+
+#include "apm_math.cuh"
+#include "apm_models.cuh"
+
+namespace apm {
+
+typedef unsigned long long u64;
+
+// what evaluation is pending for a chain
+#define PEND_NONE (-1)
+// 0 .. n_par-1 : single-parameter step (markov_chain_step_for), n_par : full step
+
+// calibration state machine phases (markov_chain_calibrate = burn_in + _orig)
+enum {
+	CAL_IDLE = 0, CAL_BURN_A = 1, CAL_BURN_B = 2, CAL_SINGLE = 3, CAL_FULL = 4, CAL_DONE = 5
+};
+
+struct CalState {
+	int phase;
+	int status;
+	int sub;           // steps done in the current block / parameter index within an iteration
+	int nchecks_without_rescaling;
+	int rescaled;
+	int reached_perfection;
+	u64 iter;
+	double rat_limit;
+	double saved_steps[APM_MAX_PAR];
+};
+
+struct CalibCfgDev {
+	u64 burn_in_iterations;
+	double desired_acceptance_rate;
+	double max_ar_deviation;
+	u64 iter_limit;
+	double mul;
+	double adjust_step;
+	int skip_calibrate;
+	int iter_readjust;
+	int no_rescaling_limit;
+};
+
+struct ProgressRow {
+	int chain;
+	int param;
+	u64 iter;
+	double step_normalised;
+	double accept_rate;
+};
+
+// All per-chain arrays are chain-major: v[g * n_par + j].
+struct DevState {
+	int n_chains, n_beta, n_ens, n_par;
+	u64 seed;
+	int proposal;
+	unsigned circular_mask, quirks;
+	int chain_id_offset, ensemble_id_offset;
+	double model_const[4];
+	// mcmc struct members (reference src/mcmc_struct.h:30-106)
+	double * params, *params_best, *steps;
+	double * prob, *prior, *prob_best;
+	u64 * accept, *reject, *pacc, *prej, *n_iter;
+	// parallel_tempering_mcmc (reference src/parallel_tempering_beta.h:65-76)
+	double * beta;
+	u64 * swapcount;
+	// bounds (identical for all chains: one params file)
+	double * pmin, *pmax;
+	// counter-RNG positions
+	u64 * rng_ctr;     // per chain
+	u64 * swap_round;  // per ensemble
+	// pending proposal
+	double * prop;     // [n_chains][n_par]
+	int * pend;        // [n_chains]
+	// likelihood partial sums written by the tiled kernel: [n_chains][n_splits]
+	double * partial;
+	int n_splits;
+	// accumulators
+	u64 * stat_n;
+	double * stat_sum_dl, *stat_sum_p, *stat_sum_p2;
+	// calibration
+	CalState * cal;
+	ProgressRow * progress;
+	long long progress_cap;
+	unsigned long long * progress_n;
+	int * n_active;    // chains still calibrating (device counter)
+	// trace of the current run
+	double * tr_prob, *tr_dl, *tr_params;
+	int tr_prob_every, tr_params_chains, tr_dumped;
+};
+
+// ---- proposal: reference src/markov_chain.c:226-270 (do_step_for) ------------------------
+APM_D double propose_coordinate(const DevState & S, int g, u64 ctr, int i, double old_value,
+		double step) {
+	const double mx = S.pmax[i], mn = S.pmin[i];
+	const uint32_t id = (uint32_t) (S.chain_id_offset + g);
+	unsigned attempt = 0;
+	double u0, u1, new_value;
+	if (S.circular_mask == 0) {
+		// CIRCULAR_PARAMS == 0: redraw until inside the bounds (:235-240)
+		do {
+			philox_uniforms(S.seed, id, ctr, PURPOSE_JUMP, (uint32_t) i, attempt++, u0, u1);
+			new_value = old_value + jump_from_uniforms(S.proposal, step, u0, u1);
+		} while (new_value > mx || new_value < mn);
+	} else {
+		// (:241-262)
+		philox_uniforms(S.seed, id, ctr, PURPOSE_JUMP, (uint32_t) i, attempt++, u0, u1);
+		new_value = old_value + jump_from_uniforms(S.proposal, step, u0, u1);
+		if (new_value > mx || new_value < mn) {
+			if (S.circular_mask & (1u << i)) {
+				new_value = mn + mod_double(new_value - mn, mx - mn);
+			} else {
+				do {
+					philox_uniforms(S.seed, id, ctr, PURPOSE_JUMP, (uint32_t) i, attempt++, u0, u1);
+					new_value = old_value + jump_from_uniforms(S.proposal, step, u0, u1);
+				} while (new_value > mx || new_value < mn);
+			}
+		}
+	}
+	return new_value;
+}
+
+// do_step (:272-277) / do_step_for for the pending kind; writes S.prop[g]
+APM_D void chain_propose(const DevState & S, int g, int kind) {
+	const int n = S.n_par;
+	const u64 ctr = S.rng_ctr[g];
+	const double * p = S.params + (size_t) g * n;
+	const double * st = S.steps + (size_t) g * n;
+	double * q = S.prop + (size_t) g * n;
+	for (int i = 0; i < n; i++) {
+		if (kind == n || kind == i)
+			q[i] = propose_coordinate(S, g, ctr, i, p[i], st[i]);
+		else
+			q[i] = p[i];
+	}
+	S.pend[g] = kind;
+}
+
+// mcmc_check_best: reference src/mcmc_calculate.c:35-41
+APM_D void chain_check_best(const DevState & S, int g) {
+	if (S.prob[g] > S.prob_best[g]) {
+		S.prob_best[g] = S.prob[g];
+		for (int i = 0; i < S.n_par; i++)
+			S.params_best[(size_t) g * S.n_par + i] = S.params[(size_t) g * S.n_par + i];
+	}
+}
+
+// restart_from_best: reference src/markov_chain.c:29-32
+APM_D void chain_restart_from_best(const DevState & S, int g) {
+	for (int i = 0; i < S.n_par; i++)
+		S.params[(size_t) g * S.n_par + i] = S.params_best[(size_t) g * S.n_par + i];
+	S.prob[g] = S.prob_best[g];
+}
+
+// reset_accept_rejects: reference src/mcmc_gettersetter.c:119-127
+APM_D void chain_reset_accept_rejects(const DevState & S, int g) {
+	for (int i = 0; i < S.n_par; i++) {
+		S.pacc[(size_t) g * S.n_par + i] = 0;
+		S.prej[(size_t) g * S.n_par + i] = 0;
+	}
+	S.reject[g] = 0;
+	S.accept[g] = 0;
+}
+
+// The second half of markov_chain_step / markov_chain_step_for (reference
+// src/markov_chain.c:369-386, 317-333) once the model's running sum for the proposal
+// is known: set_prior/set_prob, check_accept (:282-311), bookkeeping.
+template<class M>
+APM_D void chain_finalize(const DevState & S, int g, double sum) {
+	const int n = S.n_par;
+	const int kind = S.pend[g];
+	const double * q = S.prop + (size_t) g * n;
+	double * p = S.params + (size_t) g * n;
+	const double prob_old = S.prob[g];
+	const double prior_old = S.prior[g];
+	double prior_new = prior_old;
+	if (M::HAS_PRIOR)
+		prior_new = M::prior(q, n, S.model_const);
+	const double prob_new = M::finish(S.beta[g], sum, prior_new, q, S.model_const);
+	int accepted;
+	if (prob_new == prob_old)
+		accepted = 1;
+	else if (prob_new > prob_old)
+		accepted = 1;
+	else {
+		// get_next_alog_urandom: reference src/mcmc_gettersetter.c:307-309
+		double u0, u1;
+		philox_uniforms(S.seed, (uint32_t) (S.chain_id_offset + g), S.rng_ctr[g], PURPOSE_ACCEPT, 0, 0,
+				u0, u1);
+		accepted = log(u0) < (prob_new - prob_old) ? 1 : 0;
+	}
+	if (accepted) {
+		S.prob[g] = prob_new;
+		S.prior[g] = prior_new;
+		if (kind == n) {
+			for (int i = 0; i < n; i++)
+				p[i] = q[i];
+			S.accept[g]++; // inc_params_accepts: src/mcmc_gettersetter.c:98-103
+			for (int i = 0; i < n; i++)
+				S.pacc[(size_t) g * n + i]++;
+		} else {
+			p[kind] = q[kind];
+			S.pacc[(size_t) g * n + kind]++;
+		}
+	} else {
+		// revert() restores prob only (:313-315)
+		if (S.quirks & 2u)
+			S.prior[g] = prior_new;
+		if (kind == n) {
+			S.reject[g]++;
+			for (int i = 0; i < n; i++)
+				S.prej[(size_t) g * n + i]++;
+		} else {
+			S.prej[(size_t) g * n + kind]++;
+		}
+	}
+	S.rng_ctr[g]++;
+	S.pend[g] = PEND_NONE;
+}
+
+// the bookkeeping of one sampler iteration after the step (reference
+// src/parallel_tempering.c:396-401): check_best, append (n_iter++), the prob-chain
+// line and the parameter dump, plus the on-device accumulators
+APM_D void chain_record(const DevState & S, int g, long long step_index) {
+	const int n = S.n_par;
+	chain_check_best(S, g);
+	S.n_iter[g]++;
+	const double prob = S.prob[g], dl = S.prob[g] - S.prior[g];
+	if (S.tr_prob_every > 0 && S.tr_prob != nullptr && step_index % S.tr_prob_every == 0) {
+		long long row = step_index / S.tr_prob_every;
+		S.tr_prob[row * S.n_chains + g] = prob;
+		S.tr_dl[row * S.n_chains + g] = dl;
+	}
+	if (S.tr_params != nullptr) {
+		int slot = -1;
+		if (S.tr_params_chains == 2)
+			slot = g;
+		else if (S.tr_params_chains == 1 && g % S.n_beta == 0)
+			slot = g / S.n_beta;
+		if (slot >= 0)
+			for (int i = 0; i < n; i++)
+				S.tr_params[((size_t) step_index * S.tr_dumped + slot) * n + i] =
+						S.params[(size_t) g * n + i];
+	}
+	S.stat_n[g]++;
+	S.stat_sum_dl[g] += dl;
+	for (int i = 0; i < n; i++) {
+		double v = S.params[(size_t) g * n + i];
+		S.stat_sum_p[(size_t) g * n + i] += v;
+		S.stat_sum_p2[(size_t) g * n + i] += v * v;
+	}
+}
+
+// tempering_interaction for one ensemble: reference
+// src/parallel_tempering_interaction.c:125-141 -> decide_swap_now :87-97 ->
+// check_swap_probability :25-42 -> do_swap :99-123.  One thread per ensemble.
+APM_D void ensemble_swap(const DevState & S, int ens) {
+	const int n_beta = S.n_beta, n = S.n_par;
+	if (n_beta == 1)
+		return;
+	const int base = ens * n_beta;
+	const uint32_t id = (uint32_t) (S.ensemble_id_offset + ens);
+	const u64 round = S.swap_round[ens];
+	double u_pick, u_test, dummy;
+	philox_uniforms(S.seed, id, round, PURPOSE_SWAP_PICK, 0, 0, u_pick, dummy);
+	philox_uniforms(S.seed, id, round, PURPOSE_SWAP_TEST, 0, 0, u_test, dummy);
+	S.swap_round[ens] = round + 1;
+	const int a = (int) (n_beta * 1000 * u_pick) % (n_beta - 1);
+	const int ga = base + a, gb = base + a + 1;
+	const double a_prob = S.prob[ga], b_prob = S.prob[gb];
+	const double a_beta = S.beta[ga], b_beta = S.beta[gb];
+	double r;
+	if (S.quirks & 1u) {
+		r = a_beta * b_prob / b_beta + b_beta * a_prob / a_beta - (a_prob + b_prob);
+	} else {
+		double la = (a_prob - S.prior[ga]) / a_beta;
+		double lb = (b_prob - S.prior[gb]) / b_beta;
+		r = (a_beta - b_beta) * (lb - la);
+	}
+	if (r > log(u_test)) {
+		for (int i = 0; i < n; i++) {
+			double t = S.params[(size_t) ga * n + i];
+			S.params[(size_t) ga * n + i] = S.params[(size_t) gb * n + i];
+			S.params[(size_t) gb * n + i] = t;
+		}
+		if (!(S.quirks & 1u)) {
+			double la = (a_prob - S.prior[ga]) / a_beta;
+			double lb = (b_prob - S.prior[gb]) / b_beta;
+			double pa = S.prior[ga], pb = S.prior[gb];
+			S.prior[ga] = pb;
+			S.prior[gb] = pa;
+			S.prob[ga] = pb + a_beta * lb;
+			S.prob[gb] = pa + b_beta * la;
+		}
+		double rb = S.prob_best[ga];
+		if (rb > S.prob_best[gb]) {
+			S.prob_best[gb] = rb;
+			for (int i = 0; i < n; i++)
+				S.params_best[(size_t) gb * n + i] = S.params_best[(size_t) ga * n + i];
+		} else {
+			rb = S.prob_best[gb];
+			S.prob_best[ga] = rb;
+			for (int i = 0; i < n; i++)
+				S.params_best[(size_t) ga * n + i] = S.params_best[(size_t) gb * n + i];
+		}
+		S.swapcount[ga]++; // inc_swapcount(chains[candidate]) (:139)
+	}
+}
+
+// ---- calibration state machine ----------------------------------------------------------
+// One call = "the step that was pending has been finalised; decide what this chain
+// does next".  Unrolls, per chain, the loops of burn_in (reference
+// src/markov_chain.c:34-79) and markov_chain_calibrate_orig
+// (src/markov_chain_calibrate.c:1039-1180) so that thousands of chains calibrate
+// concurrently, each at its own position in the algorithm.
+APM_D void cal_finish(const DevState & S, int g, int status) {
+	S.cal[g].phase = CAL_DONE;
+	S.cal[g].status = status;
+	atomicSub(S.n_active, 1);
+}
+
+APM_D void cal_enter_orig(const DevState & S, int g, const CalibCfgDev & cfg) {
+	CalState & c = S.cal[g];
+	const int n = S.n_par;
+	if (cfg.skip_calibrate) { // SKIP_CALIBRATE_ALLCHAINS: burn_in only (parallel_tempering.c:189-195)
+		cal_finish(S, g, 0);
+		return;
+	}
+	c.rat_limit = pow(cfg.desired_acceptance_rate, 1.0 / n); // (:1058)
+	for (int i = 0; i < n; i++)
+		S.steps[(size_t) g * n + i] *= cfg.adjust_step;          // (:1060)
+	chain_reset_accept_rejects(S, g);                           // (:1062)
+	c.iter = 0;
+	c.sub = 0;
+	c.nchecks_without_rescaling = 0;
+	c.reached_perfection = 0;
+	c.phase = CAL_SINGLE;
+}
+
+// leave BURN_A (first half done or empty)
+APM_D void cal_burn_midpoint(const DevState & S, int g, const CalibCfgDev & cfg) {
+	CalState & c = S.cal[g];
+	const int n = S.n_par;
+	chain_restart_from_best(S, g);                             // markov_chain.c:59
+	for (int i = 0; i < n; i++)
+		S.steps[(size_t) g * n + i] *= 0.5;                    // :60
+	c.sub = 0;
+	if (c.iter < cfg.burn_in_iterations) {
+		c.phase = CAL_BURN_B;
+	} else {
+		for (int i = 0; i < n; i++)
+			S.steps[(size_t) g * n + i] = c.saved_steps[i];    // :73
+		cal_enter_orig(S, g, cfg);
+	}
+}
+
+APM_D void cal_begin(const DevState & S, int g, const CalibCfgDev & cfg) {
+	CalState & c = S.cal[g];
+	const int n = S.n_par;
+	c.status = 0;
+	c.iter = 0;
+	c.sub = 0;
+	for (int i = 0; i < n; i++) {
+		c.saved_steps[i] = S.steps[(size_t) g * n + i];                 // markov_chain.c:38
+		S.steps[(size_t) g * n + i] = (S.pmax[i] - S.pmin[i]) * 0.1;    // :39-41
+	}
+	if (c.iter < cfg.burn_in_iterations / 2)
+		c.phase = CAL_BURN_A;
+	else
+		cal_burn_midpoint(S, g, cfg);
+}
+
+// what kind of step the chain needs next (PEND_NONE when it is finished)
+APM_D int cal_next_kind(const DevState & S, int g) {
+	const CalState & c = S.cal[g];
+	switch (c.phase) {
+	case CAL_BURN_A:
+	case CAL_BURN_B:
+	case CAL_FULL:
+		return S.n_par;
+	case CAL_SINGLE:
+		return c.sub;
+	default:
+		return PEND_NONE;
+	}
+}
+
+APM_D void cal_after_step(const DevState & S, int g, const CalibCfgDev & cfg) {
+	CalState & c = S.cal[g];
+	const int n = S.n_par;
+	const int iter_readjust = cfg.iter_readjust > 0 ? cfg.iter_readjust : 200;
+	const int no_rescaling_limit = cfg.no_rescaling_limit > 0 ? cfg.no_rescaling_limit : 15;
+	switch (c.phase) {
+	case CAL_BURN_A:
+	case CAL_BURN_B: {
+		// blocks of 200 full steps, mcmc_check_best once per block (markov_chain.c:46-57,61-72)
+		if (++c.sub < 200)
+			return;
+		c.sub = 0;
+		c.iter += 200;
+		chain_check_best(S, g);
+		if (c.phase == CAL_BURN_A) {
+			if (c.iter >= cfg.burn_in_iterations / 2)
+				cal_burn_midpoint(S, g, cfg);
+		} else if (c.iter >= cfg.burn_in_iterations) {
+			for (int i = 0; i < n; i++)
+				S.steps[(size_t) g * n + i] = c.saved_steps[i];
+			cal_enter_orig(S, g, cfg);
+		}
+		return;
+	}
+	case CAL_SINGLE: {
+		// for each parameter: markov_chain_step_for; mcmc_check_best (:1064-1067)
+		chain_check_best(S, g);
+		if (++c.sub < n)
+			return;
+		c.sub = 0;
+		c.iter++;
+		if (c.iter % (u64) iter_readjust != 0)
+			return;
+		// (:1069-1133) compare per-parameter acceptance rates with the target, rescale
+		int rescaled = 0;
+		for (int i = 0; i < n; i++) {
+			double acc = (double) S.pacc[(size_t) g * n + i], rej = (double) S.prej[(size_t) g * n + i];
+			double rate = acc / (rej + acc);
+			double range = S.pmax[i] - S.pmin[i];
+			double & step = S.steps[(size_t) g * n + i];
+			if (rate > c.rat_limit + 0.05) {
+				step = step / cfg.mul;
+				if (rescaled == 0)
+					rescaled = -1;
+				if (step / range > 1) {
+					step = 1 * range;
+					if (rescaled == -1)
+						rescaled = 0;
+				}
+				if (step / range > 10000) {
+					cal_finish(S, g, 1);
+					return;
+				}
+				if (rescaled == -1)
+					rescaled = 1;
+			}
+			if (rate < c.rat_limit - 0.05) {
+				step = step * cfg.mul;
+				rescaled = 1;
+			}
+		}
+		if (rescaled == 0)
+			c.nchecks_without_rescaling++;
+		c.rescaled = rescaled;
+		chain_restart_from_best(S, g);
+		chain_reset_accept_rejects(S, g);
+		c.phase = CAL_FULL;
+		return;
+	}
+	case CAL_FULL: {
+		// ITER_READJUST x { markov_chain_step; mcmc_check_best } (:1135-1138)
+		chain_check_best(S, g);
+		if (++c.sub < iter_readjust)
+			return;
+		c.sub = 0;
+		// calibration_progress.data rows (:1142-1147)
+		if (S.progress != nullptr) {
+			for (int i = 0; i < n; i++) {
+				unsigned long long slot = atomicAdd(S.progress_n, 1ull);
+				if ((long long) slot < S.progress_cap) {
+					double acc = (double) S.pacc[(size_t) g * n + i], rej = (double) S.prej[(size_t) g * n + i];
+					ProgressRow & row = S.progress[slot];
+					row.chain = g;
+					row.param = i;
+					row.iter = c.iter;
+					row.step_normalised = S.steps[(size_t) g * n + i] / (S.pmax[i] - S.pmin[i]);
+					row.accept_rate = acc / (rej + acc);
+				}
+			}
+		}
+		// (:1148-1163)
+		double delta = (double) S.accept[g] / (double) (S.accept[g] + S.reject[g])
+				- cfg.desired_acceptance_rate;
+		if (fabs(delta) < cfg.max_ar_deviation) {
+			c.reached_perfection = 1;
+		} else {
+			c.reached_perfection = 0;
+			if (delta < 0)
+				c.rat_limit /= 0.99;
+			else
+				c.rat_limit *= 0.99;
+		}
+		if (c.nchecks_without_rescaling >= no_rescaling_limit && c.reached_perfection == 1
+				&& c.rescaled == 0) {
+			chain_reset_accept_rejects(S, g); // (:1177)
+			cal_finish(S, g, 0);
+			return;
+		}
+		if (c.iter > cfg.iter_limit) {
+			cal_finish(S, g, 2);
+			return;
+		}
+		c.phase = CAL_SINGLE;
+		return;
+	}
+	default:
+		return;
+	}
+}
+
+} // namespace apm

@@ -1,0 +1,903 @@
+// apm_engine.cu -- host side of the C ABI in include/apemost_gpu.h: device memory,
+// launch plans, the per-step launch sequences and the NCCL hook.  No CPU compute path
+// exists here: every likelihood, accept/reject, swap and calibration decision is taken
+// by the kernels in apm_kernels.cuh.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/apemost_gpu.h"
+#include "apm_kernels.cuh"
+
+using namespace apm;
+
+// ------------------------------------------------------------------ NCCL through dlopen
+// (libnccl.so.2 is resolved at run time so the library also loads on boxes without NCCL;
+// inside a torch process this binds to the copy torch already loaded)
+typedef struct ncclComm * ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64 = 8, ncclSum = 0 };
+struct NcclApi {
+	void * lib = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	const char * (*GetErrorString)(ncclResult_t) = nullptr;
+	bool load() {
+		if (lib)
+			return true;
+		lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+		if (!lib)
+			lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+		if (!lib)
+			return false;
+		GetUniqueId = (decltype(GetUniqueId)) dlsym(lib, "ncclGetUniqueId");
+		CommInitRank = (decltype(CommInitRank)) dlsym(lib, "ncclCommInitRank");
+		AllReduce = (decltype(AllReduce)) dlsym(lib, "ncclAllReduce");
+		CommDestroy = (decltype(CommDestroy)) dlsym(lib, "ncclCommDestroy");
+		GetErrorString = (decltype(GetErrorString)) dlsym(lib, "ncclGetErrorString");
+		return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+	}
+};
+static NcclApi g_nccl;
+
+// ------------------------------------------------------------------ handle
+struct apm_gpu {
+	apm_gpu_config cfg;
+	int n_chains = 0;
+	DevState S;
+	cudaStream_t stream = nullptr;
+	int sm_count = 0;
+	int ll_grid = 0;
+	// data
+	double * d_data = nullptr;
+	long long n_rows = 0;
+	int n_cols = 0;
+	int n_chunks = 0;
+	bool have_data = false, have_bounds = false;
+	// plan for n_chains slots
+	int plan_tile = 0, plan_ctiles = 0, plan_splits = 0, plan_cps = 0;
+	size_t partial_cap = 0;
+	// trace (device)
+	double * d_tr_prob = nullptr, *d_tr_dl = nullptr, *d_tr_params = nullptr;
+	long long tr_prob_rows = 0, tr_param_rows = 0;
+	int tr_dumped = 0;
+	// calibration
+	unsigned char * d_select = nullptr;
+	// timing / introspection
+	long long launches = 0;
+	std::vector<cudaEvent_t> ev;
+	size_t ev_used = 0;
+	double last_ll_ms = 0, last_total_ms = 0;
+	long long last_ll_launches = 0;
+	int last_path = APM_PATH_TILED;
+	// nccl
+	ncclComm_t comm = nullptr;
+	int rank = 0, n_ranks = 1;
+	double * d_shard_sum = nullptr;
+	std::string err;
+};
+
+static std::string g_create_error;
+
+static int fail(apm_gpu * h, int code, const char * fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	if (h)
+		h->err = buf;
+	else
+		g_create_error = buf;
+	return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+	return fail(h, APM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+template<class T>
+static cudaError_t dalloc(T ** p, size_t n) {
+	cudaError_t e = cudaMalloc((void **) p, std::max<size_t>(n, 1) * sizeof(T));
+	if (e == cudaSuccess)
+		e = cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T));
+	return e;
+}
+
+// ------------------------------------------------------------------ model dispatch
+#ifdef APM_USER_MODEL_HEADER
+#define APM_USER_CASE(FN, ...) case APM_MODEL_USER: return FN<UserModel>(__VA_ARGS__);
+#else
+#define APM_USER_CASE(FN, ...)
+#endif
+#define DISPATCH(model_id, FN, ...) \
+	switch (model_id) { \
+	case APM_MODEL_SIMPLESIN: return FN<ModelSimplesin>(__VA_ARGS__); \
+	case APM_MODEL_SIMPLESIN5: return FN<ModelSimplesin5>(__VA_ARGS__); \
+	case APM_MODEL_SIMPLESIN2: return FN<ModelSimplesin2>(__VA_ARGS__); \
+	case APM_MODEL_NORMAL: return FN<ModelNormal>(__VA_ARGS__); \
+	case APM_MODEL_PULSE_VROT: return FN<ModelPulseVrot>(__VA_ARGS__); \
+	case APM_MODEL_PULSE: return FN<ModelPulse>(__VA_ARGS__); \
+	APM_USER_CASE(FN, __VA_ARGS__) \
+	default: return fail(h, APM_EINVAL, "unknown model id %d", model_id); }
+
+template<class M> static int model_npar_t(apm_gpu *) { return M::NPAR; }
+template<class M> static int model_ncols_t(apm_gpu *) { return M::HAS_DATA ? M::NCOLS : 0; }
+static int model_npar(apm_gpu * h, int id) { DISPATCH(id, model_npar_t, h) }
+static int model_ncols(apm_gpu * h, int id) { DISPATCH(id, model_ncols_t, h) }
+
+extern "C" int apm_gpu_model_n_par(int model_id) {
+	int r = model_npar(nullptr, model_id);
+	return r < 0 ? 0 : r;
+}
+extern "C" int apm_gpu_model_n_cols(int model_id) {
+	int r = model_ncols(nullptr, model_id);
+	return r < 0 ? 0 : r;
+}
+extern "C" int apm_gpu_abi_version(void) { return APM_GPU_ABI_VERSION; }
+
+extern "C" const char * apm_gpu_last_error(const apm_gpu * h) {
+	return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+// ------------------------------------------------------------------ lifecycle
+template<class M>
+static int configure_kernels(apm_gpu * h) {
+	CU(cudaFuncSetAttribute(loglik_tiled_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			(int) LL_SMEM_BYTES));
+	int occ = 0;
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loglik_tiled_kernel<M>, LL_THREADS,
+			LL_SMEM_BYTES));
+	if (occ < 1)
+		return fail(h, APM_ECUDA, "likelihood kernel does not fit on an SM");
+	h->ll_grid = h->sm_count * occ;
+	return APM_OK;
+}
+
+extern "C" int apm_gpu_create(apm_gpu ** out, const apm_gpu_config * cfg) {
+	apm_gpu * h = nullptr;
+	if (!out || !cfg)
+		return fail(h, APM_EINVAL, "null argument");
+	*out = nullptr;
+	if (cfg->n_ensembles < 1 || cfg->n_beta < 1 || cfg->n_par < 1 || cfg->n_par > APM_MAX_PAR)
+		return fail(h, APM_EINVAL, "need n_ensembles >= 1, n_beta >= 1, 1 <= n_par <= %d", APM_MAX_PAR);
+	if ((long long) cfg->n_ensembles * cfg->n_beta > (1ll << 30))
+		return fail(h, APM_EINVAL, "too many chains");
+	int want = model_npar(nullptr, cfg->model_id);
+	if (want < 0)
+		return want;
+	if (want > 0 && want != cfg->n_par)
+		return fail(h, APM_EINVAL, "model %d has %d parameters, config says %d", cfg->model_id, want,
+				cfg->n_par);
+	if (cfg->model_id == APM_MODEL_PULSE && (cfg->n_par < 4 || (cfg->n_par - 2) % 2 != 0))
+		return fail(h, APM_EINVAL, "pulse needs n_par = 2 + 2k");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		cudaGetLastError();
+		return fail(h, APM_ENODEVICE, "no CUDA device available (this engine has no CPU fallback)");
+	}
+	if (cfg->device < 0 || cfg->device >= ndev)
+		return fail(h, APM_ENODEVICE, "device %d out of range (%d devices)", cfg->device, ndev);
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess)
+		return fail(h, APM_ECUDA, "cudaGetDeviceProperties failed");
+	if (prop.major != 10)
+		return fail(h, APM_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+				cfg->device, prop.major, prop.minor);
+	h = new apm_gpu();
+	h->cfg = *cfg;
+	h->n_chains = cfg->n_ensembles * cfg->n_beta;
+	h->sm_count = prop.multiProcessorCount;
+	memset(&h->S, 0, sizeof(h->S));
+	int rc = APM_OK;
+	do {
+		if (cudaSetDevice(cfg->device) != cudaSuccess || cudaStreamCreate(&h->stream) != cudaSuccess) {
+			rc = fail(nullptr, APM_ECUDA, "cannot initialise device %d: %s", cfg->device,
+					cudaGetErrorString(cudaGetLastError()));
+			break;
+		}
+		DevState & S = h->S;
+		const size_t n = h->n_chains, np = cfg->n_par, nv = n * np;
+		S.n_chains = h->n_chains;
+		S.n_beta = cfg->n_beta;
+		S.n_ens = cfg->n_ensembles;
+		S.n_par = cfg->n_par;
+		S.seed = cfg->seed;
+		S.proposal = cfg->proposal;
+		S.circular_mask = cfg->circular_mask;
+		S.quirks = cfg->quirks;
+		S.chain_id_offset = cfg->chain_id_offset;
+		S.ensemble_id_offset = cfg->ensemble_id_offset;
+		for (int i = 0; i < 4; i++)
+			S.model_const[i] = cfg->model_const[i];
+		cudaError_t e = cudaSuccess;
+#define A(ptr, count) if (e == cudaSuccess) e = dalloc(&ptr, count)
+		A(S.params, nv); A(S.params_best, nv); A(S.steps, nv); A(S.prop, nv);
+		A(S.prob, n); A(S.prior, n); A(S.prob_best, n); A(S.beta, n);
+		A(S.accept, n); A(S.reject, n); A(S.pacc, nv); A(S.prej, nv); A(S.n_iter, n);
+		A(S.swapcount, n); A(S.rng_ctr, n); A(S.swap_round, (size_t) cfg->n_ensembles);
+		A(S.pmin, np); A(S.pmax, np); A(S.pend, n);
+		A(S.stat_n, n); A(S.stat_sum_dl, n); A(S.stat_sum_p, nv); A(S.stat_sum_p2, nv);
+		A(S.cal, n); A(S.progress_n, 1); A(S.n_active, 1);
+		A(h->d_select, n); A(h->d_shard_sum, n);
+#undef A
+		if (e != cudaSuccess) {
+			rc = fail(nullptr, APM_ENOMEM, "device allocation failed: %s", cudaGetErrorString(e));
+			break;
+		}
+		// mcmc_init defaults (reference src/mcmc.c:37-78): prob = prob_best = -1e10, beta = 1
+		std::vector<double> init(n, -1e10), ones(n, 1.0);
+		std::vector<int> none(n, PEND_NONE);
+		cudaMemcpy(S.prob, init.data(), n * sizeof(double), cudaMemcpyHostToDevice);
+		cudaMemcpy(S.prob_best, init.data(), n * sizeof(double), cudaMemcpyHostToDevice);
+		cudaMemcpy(S.beta, ones.data(), n * sizeof(double), cudaMemcpyHostToDevice);
+		cudaMemcpy(S.pend, none.data(), n * sizeof(int), cudaMemcpyHostToDevice);
+		S.n_splits = 1;
+	} while (0);
+	if (rc == APM_OK) {
+		auto conf = [&]() -> int { DISPATCH(cfg->model_id, configure_kernels, h) };
+		rc = conf();
+		if (rc != APM_OK)
+			g_create_error = h->err;
+	}
+	if (rc != APM_OK) {
+		apm_gpu_destroy(h);
+		return rc;
+	}
+	*out = h;
+	return APM_OK;
+}
+
+extern "C" int apm_gpu_destroy(apm_gpu * h) {
+	if (!h)
+		return APM_OK;
+	cudaSetDevice(h->cfg.device);
+	if (h->stream)
+		cudaStreamSynchronize(h->stream);
+	DevState & S = h->S;
+	void * ptrs[] = { S.params, S.params_best, S.steps, S.prop, S.prob, S.prior, S.prob_best, S.beta,
+			S.accept, S.reject, S.pacc, S.prej, S.n_iter, S.swapcount, S.rng_ctr, S.swap_round, S.pmin,
+			S.pmax, S.pend, S.partial, S.stat_n, S.stat_sum_dl, S.stat_sum_p, S.stat_sum_p2, S.cal,
+			S.progress, S.progress_n, S.n_active, h->d_select, h->d_shard_sum, h->d_data, h->d_tr_prob,
+			h->d_tr_dl, h->d_tr_params };
+	for (void * p : ptrs)
+		if (p)
+			cudaFree(p);
+	for (cudaEvent_t e : h->ev)
+		cudaEventDestroy(e);
+	if (h->comm && g_nccl.CommDestroy)
+		g_nccl.CommDestroy(h->comm);
+	if (h->stream)
+		cudaStreamDestroy(h->stream);
+	delete h;
+	return APM_OK;
+}
+
+// ------------------------------------------------------------------ launch plan
+static void make_plan(const apm_gpu * h, int n_slots, int & tile, int & n_ctiles, int & n_splits,
+		int & cps) {
+	const int n_chunks = std::max(h->n_chunks, 1);
+	tile = 16;
+	// few chains: smaller tiles so that the chain axis alone gives some parallelism
+	while (tile > 1 && (n_slots + tile - 1) / tile < 4 && n_slots > 1)
+		tile /= 2;
+	n_ctiles = (n_slots + tile - 1) / tile;
+	long long target_items = 40ll * std::max(h->ll_grid, 1);
+	long long want = (target_items + n_ctiles - 1) / n_ctiles;
+	n_splits = (int) std::min<long long>(std::max<long long>(want, 1), n_chunks);
+	cps = (n_chunks + n_splits - 1) / n_splits;
+	n_splits = (n_chunks + cps - 1) / cps;
+}
+
+static int ensure_partial(apm_gpu * h, size_t count) {
+	if (count <= h->partial_cap)
+		return APM_OK;
+	if (h->S.partial)
+		cudaFree(h->S.partial);
+	h->S.partial = nullptr;
+	h->partial_cap = 0;
+	CU(dalloc(&h->S.partial, count));
+	h->partial_cap = count;
+	return APM_OK;
+}
+
+// ------------------------------------------------------------------ inputs
+extern "C" int apm_gpu_set_data(apm_gpu * h, const double * rowmajor, long long n_rows, int n_cols) {
+	if (!h)
+		return APM_EINVAL;
+	CU(cudaSetDevice(h->cfg.device));
+	const int need = model_ncols(h, h->cfg.model_id);
+	if (need < 0)
+		return need;
+	if (need > 0 && (rowmajor == nullptr || n_rows < 1))
+		return fail(h, APM_EINVAL, "this model needs a data table");
+	if (need > 0 && n_cols < need)
+		return fail(h, APM_EINVAL, "model reads %d data columns, table has %d", need, n_cols);
+	if (need > 2)
+		return fail(h, APM_EINVAL, "models reading more than 2 columns are not supported yet");
+	if (h->d_data)
+		cudaFree(h->d_data);
+	h->d_data = nullptr;
+	h->n_rows = n_rows;
+	h->n_cols = n_cols;
+	h->n_chunks = 0;
+	if (need > 0) {
+		// device layout: [rows padded to a whole number of chunks][2], i.e. the gsl_matrix
+		// row-major layout for two columns (tda = 2); wider tables are narrowed on upload
+		h->n_chunks = (int) ((n_rows + LL_CHUNK - 1) / LL_CHUNK);
+		const size_t padded = (size_t) h->n_chunks * LL_CHUNK;
+		CU(dalloc(&h->d_data, padded * 2));
+		if (n_cols == 2) {
+			CU(cudaMemcpyAsync(h->d_data, rowmajor, (size_t) n_rows * 2 * sizeof(double),
+					cudaMemcpyHostToDevice, h->stream));
+		} else {
+			CU(cudaMemcpy2DAsync(h->d_data, 2 * sizeof(double), rowmajor, (size_t) n_cols * sizeof(double),
+					2 * sizeof(double), (size_t) n_rows, cudaMemcpyHostToDevice, h->stream));
+		}
+		CU(cudaStreamSynchronize(h->stream));
+	}
+	make_plan(h, h->n_chains, h->plan_tile, h->plan_ctiles, h->plan_splits, h->plan_cps);
+	int rc = ensure_partial(h, (size_t) h->n_chains * h->plan_splits);
+	if (rc != APM_OK)
+		return rc;
+	h->S.n_splits = h->plan_splits;
+	h->have_data = true;
+	return APM_OK;
+}
+
+extern "C" int apm_gpu_set_bounds(apm_gpu * h, const double * pmin, const double * pmax) {
+	if (!h || !pmin || !pmax)
+		return APM_EINVAL;
+	CU(cudaSetDevice(h->cfg.device));
+	for (int i = 0; i < h->cfg.n_par; i++)
+		if (!(pmin[i] <= pmax[i]))
+			return fail(h, APM_EINVAL, "min(%f) > max(%f) for parameter %d", pmin[i], pmax[i], i);
+	CU(cudaMemcpy(h->S.pmin, pmin, h->cfg.n_par * sizeof(double), cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(h->S.pmax, pmax, h->cfg.n_par * sizeof(double), cudaMemcpyHostToDevice));
+	h->have_bounds = true;
+	return APM_OK;
+}
+
+#define CHAIN_FIELDS(X) \
+	X(beta, double, 1, S.beta) X(params, double, np, S.params) X(steps, double, np, S.steps) \
+	X(prob, double, 1, S.prob) X(prior, double, 1, S.prior) X(prob_best, double, 1, S.prob_best) \
+	X(params_best, double, np, S.params_best) X(accept, u64, 1, S.accept) X(reject, u64, 1, S.reject) \
+	X(params_accepts, u64, np, S.pacc) X(params_rejects, u64, np, S.prej) X(n_iter, u64, 1, S.n_iter) \
+	X(swapcount, u64, 1, S.swapcount) X(rng_counter, u64, 1, S.rng_ctr)
+
+extern "C" int apm_gpu_set_chains(apm_gpu * h, int first, int count, const apm_gpu_chain_io * in) {
+	if (!h || !in)
+		return APM_EINVAL;
+	if (first < 0 || count < 0 || first + count > h->n_chains)
+		return fail(h, APM_EINVAL, "chain range [%d, %d) outside [0, %d)", first, first + count,
+				h->n_chains);
+	CU(cudaSetDevice(h->cfg.device));
+	DevState & S = h->S;
+	const size_t np = h->cfg.n_par;
+	if (in->beta && !in->swapcount) // set_beta zeroes swapcount (src/parallel_tempering_beta.c:25-28)
+		CU(cudaMemsetAsync(S.swapcount + first, 0, count * sizeof(u64), h->stream));
+#define X(name, type, width, dev) \
+	if (in->name) CU(cudaMemcpyAsync(dev + (size_t) first * (width), in->name, \
+			(size_t) count * (width) * sizeof(type), cudaMemcpyHostToDevice, h->stream));
+	CHAIN_FIELDS(X)
+#undef X
+	CU(cudaStreamSynchronize(h->stream));
+	return APM_OK;
+}
+
+extern "C" int apm_gpu_get_chains(apm_gpu * h, int first, int count, apm_gpu_chain_io * out) {
+	if (!h || !out)
+		return APM_EINVAL;
+	if (first < 0 || count < 0 || first + count > h->n_chains)
+		return fail(h, APM_EINVAL, "chain range [%d, %d) outside [0, %d)", first, first + count,
+				h->n_chains);
+	CU(cudaSetDevice(h->cfg.device));
+	DevState & S = h->S;
+	const size_t np = h->cfg.n_par;
+#define X(name, type, width, dev) \
+	if (out->name) CU(cudaMemcpyAsync(out->name, dev + (size_t) first * (width), \
+			(size_t) count * (width) * sizeof(type), cudaMemcpyDeviceToHost, h->stream));
+	CHAIN_FIELDS(X)
+#undef X
+	CU(cudaStreamSynchronize(h->stream));
+	return APM_OK;
+}
+
+// ------------------------------------------------------------------ launches
+static cudaEvent_t next_event(apm_gpu * h) {
+	if (h->ev_used == h->ev.size()) {
+		cudaEvent_t e;
+		cudaEventCreate(&e);
+		h->ev.push_back(e);
+	}
+	return h->ev[h->ev_used++];
+}
+
+constexpr size_t MAX_TIMED_LAUNCHES = 8192;
+
+template<class M>
+static int launch_loglik(apm_gpu * h, const double * prop, const int * pend, int n_slots, int tile,
+		int n_ctiles, int n_splits, int cps, double * partial, bool timed) {
+	if (!M::HAS_DATA)
+		return APM_OK;
+	LLArgs a;
+	a.data = h->d_data;
+	a.n_rows = h->n_rows;
+	a.prop = prop;
+	a.pend = pend;
+	a.n_slots = n_slots;
+	a.n_par = h->cfg.n_par;
+	a.tile = tile;
+	a.n_ctiles = n_ctiles;
+	a.n_splits = n_splits;
+	a.chunks_per_split = cps;
+	a.n_chunks = h->n_chunks;
+	a.partial = partial;
+	for (int i = 0; i < 4; i++)
+		a.model_const[i] = h->cfg.model_const[i];
+	const long long n_items = (long long) n_ctiles * n_splits;
+	const int grid = (int) std::min<long long>(h->ll_grid, n_items);
+	timed = timed && h->ev_used + 2 <= 2 * MAX_TIMED_LAUNCHES;
+	if (timed)
+		cudaEventRecord(next_event(h), h->stream);
+	loglik_tiled_kernel<M><<<grid, LL_THREADS, LL_SMEM_BYTES, h->stream>>>(a);
+	if (timed)
+		cudaEventRecord(next_event(h), h->stream);
+	h->launches++;
+	return APM_OK;
+}
+
+// ---- data-sharded support: fold row splits per chain, all-reduce, finalise with 1 split
+__global__ void fold_splits_kernel(const double * partial, int n_splits, int n, double * out) {
+	const int g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= n)
+		return;
+	double s = 0;
+	for (int k = 0; k < n_splits; k++)
+		s += partial[(size_t) g * n_splits + k];
+	out[g] = s;
+}
+
+template<class M>
+static int step_likelihood(apm_gpu * h, bool timed) {
+	// likelihood of every pending proposal -> S.partial (or, data-sharded, the all-reduced
+	// per-chain sums in d_shard_sum)
+	int rc = launch_loglik<M>(h, h->S.prop, h->S.pend, h->n_chains, h->plan_tile, h->plan_ctiles,
+			h->plan_splits, h->plan_cps, h->S.partial, timed);
+	if (rc != APM_OK)
+		return rc;
+	if (h->comm && M::HAS_DATA) {
+		fold_splits_kernel<<<(h->n_chains + 255) / 256, 256, 0, h->stream>>>(h->S.partial, h->plan_splits,
+				h->n_chains, h->d_shard_sum);
+		h->launches++;
+		ncclResult_t r = g_nccl.AllReduce(h->d_shard_sum, h->d_shard_sum, (size_t) h->n_chains,
+				ncclFloat64, ncclSum, h->comm, h->stream);
+		if (r != 0)
+			return fail(h, APM_ENCCL, "ncclAllReduce failed: %s",
+					g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+	}
+	return APM_OK;
+}
+
+static DevState state_for_advance(const apm_gpu * h) {
+	DevState S = h->S;
+	if (h->comm) {
+		S.partial = h->d_shard_sum;
+		S.n_splits = 1;
+	}
+	return S;
+}
+
+// ------------------------------------------------------------------ eval
+template<class M>
+static int eval_t(apm_gpu * h, int n, const double * params, const double * beta, double * prob_out,
+		double * prior_out) {
+	const int np = h->cfg.n_par;
+	double * d_params = nullptr, *d_beta = nullptr, *d_prob = nullptr, *d_prior = nullptr, *d_partial = nullptr;
+	int tile = 1, n_ctiles = 1, n_splits = 1, cps = 1;
+	make_plan(h, n, tile, n_ctiles, n_splits, cps);
+	int rc = APM_OK;
+	cudaError_t e = dalloc(&d_params, (size_t) n * np);
+	if (e == cudaSuccess) e = dalloc(&d_beta, (size_t) n);
+	if (e == cudaSuccess) e = dalloc(&d_prob, (size_t) n);
+	if (e == cudaSuccess) e = dalloc(&d_prior, (size_t) n);
+	if (e == cudaSuccess) e = dalloc(&d_partial, (size_t) n * n_splits);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_params, params, (size_t) n * np * sizeof(double),
+			cudaMemcpyHostToDevice, h->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_beta, beta, (size_t) n * sizeof(double),
+			cudaMemcpyHostToDevice, h->stream);
+	if (e == cudaSuccess) {
+		h->ev_used = 0;
+		cudaEvent_t t0 = next_event(h), t1 = next_event(h);
+		cudaEventRecord(t0, h->stream);
+		rc = launch_loglik<M>(h, d_params, nullptr, n, tile, n_ctiles, n_splits, cps, d_partial, true);
+		const double * mc = h->cfg.model_const;
+		eval_finish_kernel<M><<<(n + 127) / 128, 128, 0, h->stream>>>(n, np, d_params, d_beta, d_partial,
+				n_splits, d_prob, d_prior, mc[0], mc[1], mc[2], mc[3]);
+		h->launches++;
+		cudaEventRecord(t1, h->stream);
+		e = cudaMemcpyAsync(prob_out, d_prob, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+		if (e == cudaSuccess && prior_out)
+			e = cudaMemcpyAsync(prior_out, d_prior, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost,
+					h->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+		if (e == cudaSuccess) {
+			// t0/t1 occupy ev[0], ev[1]; the loglik pair (if any) is ev[2], ev[3]
+			float tot = 0;
+			cudaEventElapsedTime(&tot, t0, t1);
+			h->last_total_ms = tot;
+			h->last_ll_ms = 0;
+			h->last_ll_launches = 0;
+			if (h->ev_used >= 4) {
+				float ms = 0;
+				cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+				h->last_ll_ms = ms;
+				h->last_ll_launches = 1;
+			}
+		}
+	}
+	cudaFree(d_params); cudaFree(d_beta); cudaFree(d_prob); cudaFree(d_prior); cudaFree(d_partial);
+	if (e != cudaSuccess)
+		return fail(h, APM_ECUDA, "eval failed: %s", cudaGetErrorString(e));
+	h->last_path = APM_PATH_TILED;
+	return rc;
+}
+
+extern "C" int apm_gpu_eval(apm_gpu * h, int n, const double * params, const double * beta,
+		double * prob_out, double * prior_out) {
+	if (!h || n < 0 || !params || !beta || !prob_out)
+		return APM_EINVAL;
+	if (n == 0)
+		return APM_OK;
+	if (!h->have_data)
+		return fail(h, APM_ESTATE, "apm_gpu_set_data must be called first");
+	if (h->comm)
+		return fail(h, APM_ESTATE, "apm_gpu_eval is not available in data-sharded mode");
+	CU(cudaSetDevice(h->cfg.device));
+	DISPATCH(h->cfg.model_id, eval_t, h, n, params, beta, prob_out, prior_out)
+}
+
+// ------------------------------------------------------------------ run (tiled path)
+static int setup_trace(apm_gpu * h, long long n_steps, const apm_gpu_trace_cfg * tr) {
+	for (double ** p : { &h->d_tr_prob, &h->d_tr_dl, &h->d_tr_params }) {
+		if (*p)
+			cudaFree(*p);
+		*p = nullptr;
+	}
+	h->tr_prob_rows = h->tr_param_rows = 0;
+	h->tr_dumped = 0;
+	DevState & S = h->S;
+	S.tr_prob = S.tr_dl = S.tr_params = nullptr;
+	S.tr_prob_every = tr ? tr->prob_every : 0;
+	S.tr_params_chains = tr ? tr->params_chains : 0;
+	if (S.tr_prob_every < 0 || S.tr_params_chains < 0 || S.tr_params_chains > 2)
+		return fail(h, APM_EINVAL, "bad trace configuration");
+	if (S.tr_prob_every > 0) {
+		h->tr_prob_rows = (n_steps + S.tr_prob_every - 1) / S.tr_prob_every;
+		CU(dalloc(&h->d_tr_prob, (size_t) h->tr_prob_rows * h->n_chains));
+		CU(dalloc(&h->d_tr_dl, (size_t) h->tr_prob_rows * h->n_chains));
+	}
+	h->tr_dumped = S.tr_params_chains == 2 ? h->n_chains : (S.tr_params_chains == 1 ? h->cfg.n_ensembles : 0);
+	if (h->tr_dumped > 0) {
+		h->tr_param_rows = n_steps;
+		CU(dalloc(&h->d_tr_params, (size_t) n_steps * h->tr_dumped * h->cfg.n_par));
+	}
+	S.tr_prob = h->d_tr_prob;
+	S.tr_dl = h->d_tr_dl;
+	S.tr_params = h->d_tr_params;
+	S.tr_dumped = h->tr_dumped;
+	return APM_OK;
+}
+
+template<class M>
+static int run_tiled_t(apm_gpu * h, long long n_rounds, int n_swap) {
+	const long long total = n_rounds * n_swap;
+	AdvArgs a;
+	memset(&a, 0, sizeof(a));
+	h->ev_used = 0;
+	cudaEvent_t t0 = next_event(h), t1 = next_event(h);
+	// ev[0], ev[1] are the run brackets; pairs from ev[2] on are likelihood launches
+	CU(cudaEventRecord(t0, h->stream));
+	a.flags = ADV_PROPOSE_RUN;
+	advance_kernel<M><<<h->cfg.n_ensembles, ADV_THREADS, 0, h->stream>>>(state_for_advance(h), a);
+	h->launches++;
+	for (long long step = 0; step < total; step++) {
+		int rc = step_likelihood<M>(h, true);
+		if (rc != APM_OK)
+			return rc;
+		a.flags = ADV_FINALIZE | ADV_RECORD;
+		if ((step + 1) % n_swap == 0)
+			a.flags |= ADV_SWAP;
+		if (step + 1 < total)
+			a.flags |= ADV_PROPOSE_RUN;
+		a.step_index = step;
+		advance_kernel<M><<<h->cfg.n_ensembles, ADV_THREADS, 0, h->stream>>>(state_for_advance(h), a);
+		h->launches++;
+	}
+	CU(cudaEventRecord(t1, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	CU(cudaGetLastError());
+	// timing: skip the bracket pair
+	h->last_ll_ms = 0;
+	h->last_ll_launches = 0;
+	for (size_t i = 2; i + 1 < h->ev_used; i += 2) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) {
+			h->last_ll_ms += ms;
+			h->last_ll_launches++;
+		}
+	}
+	float tot = 0;
+	cudaEventElapsedTime(&tot, t0, t1);
+	h->last_total_ms = tot;
+	h->last_path = APM_PATH_TILED;
+	return APM_OK;
+}
+
+extern "C" int apm_gpu_run(apm_gpu * h, long long n_rounds, int n_swap, const apm_gpu_trace_cfg * trace) {
+	if (!h || n_rounds < 0 || n_swap < 1)
+		return APM_EINVAL;
+	if (!h->have_data || !h->have_bounds)
+		return fail(h, APM_ESTATE, "apm_gpu_set_data and apm_gpu_set_bounds must be called first");
+	CU(cudaSetDevice(h->cfg.device));
+	int rc = setup_trace(h, n_rounds * n_swap, trace);
+	if (rc != APM_OK)
+		return rc;
+	if (n_rounds == 0)
+		return APM_OK;
+	DISPATCH(h->cfg.model_id, run_tiled_t, h, n_rounds, n_swap)
+}
+
+extern "C" int apm_gpu_read_trace(apm_gpu * h, double * prob, double * dl, double * params,
+		long long * n_prob_rows, long long * n_param_rows) {
+	if (!h)
+		return APM_EINVAL;
+	CU(cudaSetDevice(h->cfg.device));
+	if (prob && h->d_tr_prob)
+		CU(cudaMemcpy(prob, h->d_tr_prob, (size_t) h->tr_prob_rows * h->n_chains * sizeof(double),
+				cudaMemcpyDeviceToHost));
+	if (dl && h->d_tr_dl)
+		CU(cudaMemcpy(dl, h->d_tr_dl, (size_t) h->tr_prob_rows * h->n_chains * sizeof(double),
+				cudaMemcpyDeviceToHost));
+	if (params && h->d_tr_params)
+		CU(cudaMemcpy(params, h->d_tr_params,
+				(size_t) h->tr_param_rows * h->tr_dumped * h->cfg.n_par * sizeof(double),
+				cudaMemcpyDeviceToHost));
+	if (n_prob_rows)
+		*n_prob_rows = h->tr_prob_rows;
+	if (n_param_rows)
+		*n_param_rows = h->tr_param_rows;
+	return APM_OK;
+}
+
+// ------------------------------------------------------------------ calibrate
+template<class M>
+static int calibrate_t(apm_gpu * h, const apm_gpu_calib_cfg * cfg, int * status) {
+	AdvArgs a;
+	memset(&a, 0, sizeof(a));
+	a.cal.burn_in_iterations = cfg->burn_in_iterations;
+	a.cal.desired_acceptance_rate = cfg->desired_acceptance_rate;
+	a.cal.max_ar_deviation = cfg->max_ar_deviation;
+	a.cal.iter_limit = cfg->iter_limit;
+	a.cal.mul = cfg->mul;
+	a.cal.adjust_step = cfg->adjust_step;
+	a.cal.skip_calibrate = cfg->skip_calibrate;
+	a.cal.iter_readjust = cfg->iter_readjust;
+	a.cal.no_rescaling_limit = cfg->no_rescaling_limit;
+	a.select = h->d_select;
+	h->ev_used = 0;
+	cudaEvent_t t0 = next_event(h), t1 = next_event(h);
+	CU(cudaEventRecord(t0, h->stream));
+	a.flags = ADV_CALIB_BEGIN;
+	advance_kernel<M><<<h->cfg.n_ensembles, ADV_THREADS, 0, h->stream>>>(state_for_advance(h), a);
+	h->launches++;
+	int active = 1;
+	const int block = 200;
+	while (active > 0) {
+		for (int i = 0; i < block; i++) {
+			int rc = step_likelihood<M>(h, true);
+			if (rc != APM_OK)
+				return rc;
+			a.flags = ADV_FINALIZE | ADV_CALIB;
+			advance_kernel<M><<<h->cfg.n_ensembles, ADV_THREADS, 0, h->stream>>>(state_for_advance(h), a);
+			h->launches++;
+		}
+		CU(cudaMemcpyAsync(&active, h->S.n_active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+		CU(cudaStreamSynchronize(h->stream));
+	}
+	CU(cudaEventRecord(t1, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	CU(cudaGetLastError());
+	h->last_ll_ms = 0;
+	h->last_ll_launches = 0;
+	for (size_t i = 2; i + 1 < h->ev_used; i += 2) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) {
+			h->last_ll_ms += ms;
+			h->last_ll_launches++;
+		}
+	}
+	float tot = 0;
+	cudaEventElapsedTime(&tot, t0, t1);
+	h->last_total_ms = tot;
+	h->last_path = APM_PATH_TILED;
+	// per-chain status
+	std::vector<CalState> cs(h->n_chains);
+	CU(cudaMemcpy(cs.data(), h->S.cal, h->n_chains * sizeof(CalState), cudaMemcpyDeviceToHost));
+	int any = 0;
+	for (int g = 0; g < h->n_chains; g++) {
+		if (status)
+			status[g] = cs[g].status;
+		if (cs[g].status > 0)
+			any = 1;
+	}
+	if (any)
+		return fail(h, APM_ECALIB, "calibration failed for at least one chain (see status[])");
+	return APM_OK;
+}
+
+extern "C" int apm_gpu_calibrate(apm_gpu * h, const unsigned char * select, const apm_gpu_calib_cfg * cfg,
+		int * status, apm_gpu_calib_progress * progress, long long progress_capacity, long long * n_progress) {
+	if (!h || !cfg)
+		return APM_EINVAL;
+	if (!h->have_data || !h->have_bounds)
+		return fail(h, APM_ESTATE, "apm_gpu_set_data and apm_gpu_set_bounds must be called first");
+	CU(cudaSetDevice(h->cfg.device));
+	std::vector<unsigned char> sel(h->n_chains, 1);
+	if (select)
+		memcpy(sel.data(), select, h->n_chains);
+	CU(cudaMemcpy(h->d_select, sel.data(), h->n_chains, cudaMemcpyHostToDevice));
+	CU(cudaMemset(h->S.n_active, 0, sizeof(int)));
+	CU(cudaMemset(h->S.progress_n, 0, sizeof(unsigned long long)));
+	if (h->S.progress)
+		cudaFree(h->S.progress);
+	h->S.progress = nullptr;
+	h->S.progress_cap = 0;
+	if (progress && progress_capacity > 0) {
+		CU(dalloc(&h->S.progress, (size_t) progress_capacity));
+		h->S.progress_cap = progress_capacity;
+	}
+	auto go = [&]() -> int { DISPATCH(h->cfg.model_id, calibrate_t, h, cfg, status) };
+	int rc = go();
+	if (rc != APM_OK && rc != APM_ECALIB)
+		return rc;
+	unsigned long long np_rows = 0;
+	CU(cudaMemcpy(&np_rows, h->S.progress_n, sizeof(np_rows), cudaMemcpyDeviceToHost));
+	if (n_progress)
+		*n_progress = (long long) np_rows;
+	if (progress && progress_capacity > 0) {
+		static_assert(sizeof(ProgressRow) == sizeof(apm_gpu_calib_progress), "progress row layout");
+		size_t take = (size_t) std::min<unsigned long long>(np_rows, (unsigned long long) progress_capacity);
+		CU(cudaMemcpy(progress, h->S.progress, take * sizeof(ProgressRow), cudaMemcpyDeviceToHost));
+		// rows are appended by concurrently calibrating chains: hand them out ordered by
+		// (chain, iter, param), the order the reference writes them per chain
+		std::sort(progress, progress + take, [](const apm_gpu_calib_progress & x, const apm_gpu_calib_progress & y) {
+			if (x.chain != y.chain) return x.chain < y.chain;
+			if (x.iter != y.iter) return x.iter < y.iter;
+			return x.param < y.param;
+		});
+	}
+	return rc;
+}
+
+// ------------------------------------------------------------------ accumulators
+extern "C" int apm_gpu_reset_stats(apm_gpu * h) {
+	if (!h)
+		return APM_EINVAL;
+	CU(cudaSetDevice(h->cfg.device));
+	const size_t n = h->n_chains, nv = n * h->cfg.n_par;
+	CU(cudaMemset(h->S.stat_n, 0, n * sizeof(u64)));
+	CU(cudaMemset(h->S.stat_sum_dl, 0, n * sizeof(double)));
+	CU(cudaMemset(h->S.stat_sum_p, 0, nv * sizeof(double)));
+	CU(cudaMemset(h->S.stat_sum_p2, 0, nv * sizeof(double)));
+	return APM_OK;
+}
+
+extern "C" int apm_gpu_get_stats(apm_gpu * h, unsigned long long * n, double * sum_dl, double * sum_p,
+		double * sum_p2) {
+	if (!h)
+		return APM_EINVAL;
+	CU(cudaSetDevice(h->cfg.device));
+	const size_t nc = h->n_chains, nv = nc * h->cfg.n_par;
+	if (n) CU(cudaMemcpy(n, h->S.stat_n, nc * sizeof(u64), cudaMemcpyDeviceToHost));
+	if (sum_dl) CU(cudaMemcpy(sum_dl, h->S.stat_sum_dl, nc * sizeof(double), cudaMemcpyDeviceToHost));
+	if (sum_p) CU(cudaMemcpy(sum_p, h->S.stat_sum_p, nv * sizeof(double), cudaMemcpyDeviceToHost));
+	if (sum_p2) CU(cudaMemcpy(sum_p2, h->S.stat_sum_p2, nv * sizeof(double), cudaMemcpyDeviceToHost));
+	return APM_OK;
+}
+
+// ------------------------------------------------------------------ NCCL
+extern "C" int apm_gpu_nccl_unique_id(unsigned char id_out[128]) {
+	if (!g_nccl.load())
+		return fail(nullptr, APM_ENCCL, "libnccl.so.2 not found");
+	ncclUniqueId id;
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+	ncclResult_t r = g_nccl.GetUniqueId(&id);
+	if (r != 0)
+		return fail(nullptr, APM_ENCCL, "ncclGetUniqueId failed (%d)", r);
+	memcpy(id_out, &id, 128);
+	return APM_OK;
+}
+
+extern "C" int apm_gpu_nccl_init(apm_gpu * h, const unsigned char id_in[128], int rank, int n_ranks) {
+	if (!h || !id_in || n_ranks < 1 || rank < 0 || rank >= n_ranks)
+		return APM_EINVAL;
+	if (!g_nccl.load())
+		return fail(h, APM_ENCCL, "libnccl.so.2 not found");
+	CU(cudaSetDevice(h->cfg.device));
+	ncclUniqueId id;
+	memcpy(&id, id_in, 128);
+	ncclResult_t r = g_nccl.CommInitRank(&h->comm, n_ranks, id, rank);
+	if (r != 0) {
+		h->comm = nullptr;
+		return fail(h, APM_ENCCL, "ncclCommInitRank failed: %s",
+				g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+	}
+	h->rank = rank;
+	h->n_ranks = n_ranks;
+	return APM_OK;
+}
+
+// ------------------------------------------------------------------ introspection
+extern "C" long long apm_gpu_launch_count(const apm_gpu * h) { return h ? h->launches : 0; }
+
+extern "C" int apm_gpu_last_kernel_ms(const apm_gpu * h, double * loglik_ms, long long * loglik_launches,
+		double * total_ms) {
+	if (!h)
+		return APM_EINVAL;
+	if (loglik_ms) *loglik_ms = h->last_ll_ms;
+	if (loglik_launches) *loglik_launches = h->last_ll_launches;
+	if (total_ms) *total_ms = h->last_total_ms;
+	return APM_OK;
+}
+
+extern "C" int apm_gpu_last_path(const apm_gpu * h) { return h ? h->last_path : 0; }
+
+extern "C" int apm_gpu_measure_fp64_peak(int device, double seconds, double * instr_per_s) {
+	apm_gpu * h = nullptr;
+	if (!instr_per_s)
+		return APM_EINVAL;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+		cudaGetLastError();
+		return fail(h, APM_ENODEVICE, "no such CUDA device");
+	}
+	CU(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, device));
+	const int grid = prop.multiProcessorCount * 8, block = 256;
+	double * out = nullptr;
+	CU(dalloc(&out, (size_t) grid * block));
+	cudaEvent_t t0, t1;
+	CU(cudaEventCreate(&t0));
+	CU(cudaEventCreate(&t1));
+	int iters = 2000;
+	double best = 0;
+	// warm up, then grow the launch until it lasts long enough to average over clock ramps
+	for (int rep = 0; rep < 12; rep++) {
+		CU(cudaEventRecord(t0));
+		fp64_peak_kernel<<<grid, block>>>(out, iters, 0.999999, 1e-9);
+		CU(cudaEventRecord(t1));
+		CU(cudaEventSynchronize(t1));
+		float ms = 0;
+		CU(cudaEventElapsedTime(&ms, t0, t1));
+		double rate = (double) grid * block * (double) iters * 64.0 / (ms * 1e-3);
+		if (rep >= 2 && rate > best)
+			best = rate;
+		if (ms * 1e-3 < seconds / 4 && iters < (1 << 24))
+			iters *= 2;
+	}
+	cudaEventDestroy(t0);
+	cudaEventDestroy(t1);
+	cudaFree(out);
+	*instr_per_s = best;
+	return APM_OK;
+}

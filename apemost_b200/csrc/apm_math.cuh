@@ -1,0 +1,193 @@
+// apm_math.cuh -- numeric building blocks of the engine: the fp64 sine used by the
+// likelihood kernels, the Philox4x32-10 counter RNG and the proposal transforms.
+//
+// Everything here is __host__ __device__ so that tests/test_math_cpu.py can compile
+// the very same source with g++ -mfma (IEEE fma is deterministic, so the CPU run
+// reproduces the device arithmetic bit for bit) and check it against 50-digit
+// references without a GPU.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define APM_HD __host__ __device__ __forceinline__
+#define APM_D __device__ __forceinline__
+#else
+#define APM_HD static inline
+#define APM_D static inline
+#endif
+
+namespace apm {
+
+// ---- bit access ----------------------------------------------------------------
+APM_HD int hi32(double x) {
+#if defined(__CUDA_ARCH__)
+	return __double2hiint(x);
+#else
+	int64_t b;
+	memcpy(&b, &x, 8);
+	return (int) (b >> 32);
+#endif
+}
+APM_HD int lo32(double x) {
+#if defined(__CUDA_ARCH__)
+	return __double2loint(x);
+#else
+	int64_t b;
+	memcpy(&b, &x, 8);
+	return (int) (b & 0xffffffff);
+#endif
+}
+APM_HD double make_double(int hi, int lo) {
+#if defined(__CUDA_ARCH__)
+	return __hiloint2double(hi, lo);
+#else
+	int64_t b = ((int64_t) hi << 32) | (uint32_t) lo;
+	double x;
+	memcpy(&x, &b, 8);
+	return x;
+#endif
+}
+// strictly rounded (never contracted) multiply / add: used where the reference's
+// own rounding sequence must be reproduced (the argument of sin)
+APM_HD double mul_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+	return __dmul_rn(a, b);
+#else
+	volatile double r = a * b;
+	return r;
+#endif
+}
+APM_HD double add_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+	return __dadd_rn(a, b);
+#else
+	volatile double r = a + b;
+	return r;
+#endif
+}
+
+// ---- sine ------------------------------------------------------------------------
+// sin(x) for |x| < 2^30 in 14 FP64-pipe instructions and no table, select or
+// conversion instruction (CUDA's sin() costs 14 FP64 + 2 F2I/I2F + 3 LDG + 6 FSEL and
+// a slow-path call):
+//   q = rint(x / pi) by the 1.5*2^52 magic-number add (1 DFMA + 1 DADD), its parity is
+//   the low mantissa bit; r = x - q*pi by a two-term Cody-Waite reduction (2 DFMA; the
+//   first is exact, the third term q*3e-33 is below 1e-23 for every q < 2^31);
+//   sin(x) = (-1)^q sin(r), |r| <= pi/2: odd minimax polynomial of degree 17 in r
+//   (Remez, weighted for absolute error; max error 2.0e-19 before rounding) evaluated
+//   as r + (r*s)*P(s), s = r*r: 1 DMUL + 7 DFMA + 1 DMUL + 1 DFMA.
+// Measured against 50-digit references (tests/test_math_cpu.py): max error < 0.9 ulp
+// of the result for |x| <= 1e5 ... 1e9.  Outside the fast range (or NaN/Inf) the
+// caller falls back to the CUDA library sin().
+#define APM_SIN_FAST_LIMIT 1073741824.0 /* 2^30 */
+
+APM_HD double sin_fast(double x) {
+	const double MAGIC = 6755399441055744.0; /* 1.5 * 2^52 */
+	const double INV_PI = 0.3183098861837907;
+	const double PI_HI = 3.141592653589793;
+	const double PI_LO = 1.2246467991473532e-16;
+	double t = fma(x, INV_PI, MAGIC);
+	int q = lo32(t);
+	double qd = t - MAGIC;
+	double r = fma(qd, -PI_HI, x);
+	r = fma(qd, -PI_LO, r);
+	// (-1)^q: move q's parity into r's sign bit (sin is odd)
+	r = make_double(hi32(r) ^ (q << 31), lo32(r));
+	double s = r * r;
+	double p = 0x1.87c623b020b36p-49;
+	p = fma(p, s, -0x1.ae3f136452c88p-41);
+	p = fma(p, s, 0x1.6123b9f483e33p-33);
+	p = fma(p, s, -0x1.ae64547e37987p-26);
+	p = fma(p, s, 0x1.71de3a51c5b7bp-19);
+	p = fma(p, s, -0x1.a01a01a012713p-13);
+	p = fma(p, s, 0x1.1111111111092p-7);
+	p = fma(p, s, -0x1.5555555555555p-3);
+	return fma(r * s, p, r);
+}
+
+// true when x is outside sin_fast's range (|x| >= 2^30, NaN, Inf): one LOP3 + one ISETP
+APM_HD bool sin_fast_out_of_range(double x) {
+	return (unsigned) (hi32(x) & 0x7fffffff) >= 0x41d00000u;
+}
+
+APM_HD double sin_full(double x) {
+	if (fabs(x) < APM_SIN_FAST_LIMIT)
+		return sin_fast(x);
+	return sin(x); /* Payne-Hanek path of the math library; NaN/Inf land here too */
+}
+
+// ---- Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011) -----------------------------
+struct Philox4 {
+	uint32_t w[4];
+};
+
+APM_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+	return __umulhi(a, b);
+#else
+	return (uint32_t) (((uint64_t) a * b) >> 32);
+#endif
+}
+
+APM_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+		uint32_t k0, uint32_t k1) {
+#pragma unroll
+	for (int r = 0; r < 10; r++) {
+		uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+		uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+		uint32_t n0 = h1 ^ c1 ^ k0;
+		uint32_t n2 = h0 ^ c3 ^ k1;
+		c0 = n0;
+		c1 = l1;
+		c2 = n2;
+		c3 = l0;
+		k0 += 0x9E3779B9u;
+		k1 += 0xBB67AE85u;
+	}
+	Philox4 o;
+	o.w[0] = c0;
+	o.w[1] = c1;
+	o.w[2] = c2;
+	o.w[3] = c3;
+	return o;
+}
+
+// Stream layout (shared, by construction, with the test oracle):
+//   key     = (seed lo, seed hi)
+//   counter = (id, step lo, step hi, purpose << 28 | idx << 20 | attempt)
+//   id      = global chain id for per-chain draws, global ensemble id for swap draws
+//   u0, u1  = two 53-bit uniforms strictly inside (0, 1)
+enum {
+	PURPOSE_JUMP = 0, PURPOSE_ACCEPT = 1, PURPOSE_SWAP_PICK = 2, PURPOSE_SWAP_TEST = 3
+};
+
+APM_HD void philox_uniforms(uint64_t seed, uint32_t id, uint64_t step, uint32_t purpose,
+		uint32_t idx, uint32_t attempt, double & u0, double & u1) {
+	Philox4 o = philox4x32_10(id, (uint32_t) step, (uint32_t) (step >> 32),
+			(purpose << 28) | ((idx & 0xffu) << 20) | (attempt & 0xfffffu),
+			(uint32_t) seed, (uint32_t) (seed >> 32));
+	u0 = ((double) (o.w[0] >> 5) * 67108864.0 + (double) (o.w[1] >> 6) + 0.5)
+			* (1.0 / 9007199254740992.0);
+	u1 = ((double) (o.w[2] >> 5) * 67108864.0 + (double) (o.w[3] >> 6) + 0.5)
+			* (1.0 / 9007199254740992.0);
+}
+
+// the proposal jump: reference src/mcmc_gettersetter.c:290-306 (Gaussian default;
+// PROPOSAL_LOGISTIC; PROPOSAL_UNIFORM = flat on (-sigma, sigma))
+APM_HD double jump_from_uniforms(int proposal, double sigma, double u0, double u1) {
+	if (proposal == 1)
+		return sigma * log(u0 / (1 - u0));
+	if (proposal == 2)
+		return (-sigma) * (1 - u0) + sigma * u0;
+	return sigma * (sqrt(-2.0 * log(u0)) * cos(2.0 * 3.14159265358979323846 * u1));
+}
+
+// reference src/mcmc_internal.h:46-48
+APM_HD double mod_double(double x, double div) {
+	return x < 0 ? x - div * (int) (x / div - 1) : x - div * (int) (x / div);
+}
+
+} // namespace apm

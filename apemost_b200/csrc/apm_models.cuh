@@ -1,0 +1,264 @@
+// apm_models.cuh -- __device__ counterparts of the reference's apps/<model>.c plugins.
+//
+// The reference binds one calc_model() per executable at link time
+// (Makefile:54-55; contract src/mcmc.h:164,173, doc/manual.rst:126-168).  On the
+// device a model is a struct with the static interface below; the kernels are
+// templates over it, so a model costs nothing at run time:
+//
+//   NPAR        number of parameters (0 = decided at run time, n_par is passed in)
+//   NCOLS       data columns the model reads (the row-major table may not be narrower)
+//   HAS_DATA    false for models that never touch m->data (apps/normal.c)
+//   HAS_PRIOR   whether calc_model calls set_prior()
+//   Prep        per-chain constants derived once per proposal (kept in registers)
+//   prep()      fill Prep from the parameter vector
+//   accum()      acc + (one data row's contribution to the model's running sum), exact
+//                for every input (falls back to the math library outside sin_fast's range)
+//   accum_fast() the same on the branch-free fast path; sets `bad` instead of branching
+//                when an input is outside the fast range -- the kernel then redoes that
+//                thread's rows with accum()
+//   prior()     value passed to set_prior()
+//   sum0()      initial value of the running sum (apps/pulse*.c start it at params[1])
+//   finish()    the value passed to set_prob()
+//
+// Arithmetic follows each reference file's operation order; the argument of sin is
+// rounded exactly like the reference (no fused multiply-add), because at |arg| ~ 1e4
+// a half-ulp there is ~1e-12 absolute.  The whole library is compiled with
+// -fmad=false: every fused operation below is an explicit fma().
+//
+// A user model: write apps/<name>.cuh defining `struct UserModel` with this
+// interface and build with -DAPM_USER_MODEL_HEADER='"<name>.cuh"' (see
+// apemost_b200/host/Makefile); it is then reachable as APM_MODEL_USER.
+#pragma once
+
+#include "apm_math.cuh"
+
+namespace apm {
+
+#define APM_MAX_PAR 16
+#define APM_TWO_PI 6.283185307179586 /* (2.0 * M_PI) as the compiler folds it */
+
+// ---- apps/simplesin.c:12-38 -----------------------------------------------------------
+struct ModelSimplesin {
+	static constexpr int NPAR = 4, NCOLS = 2;
+	static constexpr bool HAS_DATA = true, HAS_PRIOR = false;
+	struct Prep {
+		double amplitude, frequency, phase, offset;
+	};
+	APM_D static void prep(Prep & q, const double * p, int, const double *) {
+		q.amplitude = p[0];
+		q.frequency = p[1];
+		q.phase = p[2];
+		q.offset = p[3];
+	}
+	// y_model = amplitude * sin(2.0 * M_PI * (frequency * x + phase)) + offset   (:15)
+	APM_D static double accum(double acc, const Prep & q, double x, double y) {
+		double arg = mul_rn(APM_TWO_PI, add_rn(mul_rn(q.frequency, x), q.phase));
+		double deltay = fma(q.amplitude, sin_full(arg), q.offset) - y;
+		return fma(deltay, deltay, acc);
+	}
+	APM_D static double accum_fast(double acc, const Prep & q, double x, double y, bool & bad) {
+		double arg = mul_rn(APM_TWO_PI, add_rn(mul_rn(q.frequency, x), q.phase));
+		bad |= sin_fast_out_of_range(arg);
+		double deltay = fma(q.amplitude, sin_fast(arg), q.offset) - y;
+		return fma(deltay, deltay, acc);
+	}
+	APM_D static double sum0(const double *) { return 0.0; }
+	APM_D static double prior(const double *, int, const double *) { return 0.0; }
+	APM_D static double finish(double beta, double sum, double, const double *, const double * mc) {
+		const double sigma = mc[0] != 0 ? mc[0] : 0.5; // SIGMA (:8-10)
+		return beta * sum / (-2 * sigma * sigma);       // (:36)
+	}
+};
+
+// ---- apps/simplesin5.c:15-41 (formula) ----------------------------------
+struct ModelSimplesin5 {
+	static constexpr int NPAR = 4, NCOLS = 2;
+	static constexpr bool HAS_DATA = true, HAS_PRIOR = false;
+	struct Prep {
+		double a, w, ph, off;
+	};
+	APM_D static void prep(Prep & q, const double * p, int, const double *) {
+		q.a = p[0];
+		q.w = mul_rn(APM_TWO_PI, p[1]); // 2.0 * M_PI * param1 associates to the left (:18)
+		q.ph = p[2];
+		q.off = p[3];
+	}
+	APM_D static double accum(double acc, const Prep & q, double x, double y) {
+		double arg = add_rn(mul_rn(q.w, x), q.ph);
+		double d = fma(q.a, sin_full(arg), q.off) - y; // (:35-36)
+		return fma(d, d, acc);
+	}
+	APM_D static double accum_fast(double acc, const Prep & q, double x, double y, bool & bad) {
+		double arg = add_rn(mul_rn(q.w, x), q.ph);
+		bad |= sin_fast_out_of_range(arg);
+		double d = fma(q.a, sin_fast(arg), q.off) - y;
+		return fma(d, d, acc);
+	}
+	APM_D static double sum0(const double *) { return 0.0; }
+	APM_D static double prior(const double *, int, const double *) { return 0.0; }
+	APM_D static double finish(double beta, double sum, double, const double *, const double * mc) {
+		const double sigma = mc[0] != 0 ? mc[0] : 0.5;
+		return beta * sum / (-2 * sigma * sigma);
+	}
+};
+
+// ---- apps/simplesin2.c:12-32 ------------------------------------------------------------
+struct ModelSimplesin2 {
+	static constexpr int NPAR = 2, NCOLS = 2;
+	static constexpr bool HAS_DATA = true, HAS_PRIOR = false;
+	struct Prep {
+		double a, f;
+	};
+	APM_D static void prep(Prep & q, const double * p, int, const double *) {
+		q.a = p[0];
+		q.f = p[1];
+	}
+	APM_D static double accum(double acc, const Prep & q, double x, double y) {
+		double arg = mul_rn(APM_TWO_PI, add_rn(mul_rn(q.f, x), 0.3312));
+		double d = fma(q.a, sin_full(arg), -y);
+		return fma(d, d, acc);
+	}
+	APM_D static double accum_fast(double acc, const Prep & q, double x, double y, bool & bad) {
+		double arg = mul_rn(APM_TWO_PI, add_rn(mul_rn(q.f, x), 0.3312));
+		bad |= sin_fast_out_of_range(arg);
+		double d = fma(q.a, sin_fast(arg), -y);
+		return fma(d, d, acc);
+	}
+	APM_D static double sum0(const double *) { return 0.0; }
+	APM_D static double prior(const double *, int, const double *) { return 0.0; }
+	APM_D static double finish(double beta, double sum, double, const double *, const double * mc) {
+		const double sigma = mc[0] != 0 ? mc[0] : 0.5;
+		return beta * sum / (-2 * sigma * sigma);
+	}
+};
+
+// ---- apps/normal.c:8-34 (data-free) -------------------------------------------------------
+struct ModelNormal {
+	static constexpr int NPAR = 1, NCOLS = 0;
+	static constexpr bool HAS_DATA = false, HAS_PRIOR = false;
+	struct Prep {
+		double x;
+	};
+	APM_D static void prep(Prep & q, const double * p, int, const double *) { q.x = p[0]; }
+	APM_D static double accum(double acc, const Prep &, double, double) { return acc; }
+	APM_D static double accum_fast(double acc, const Prep &, double, double, bool &) { return acc; }
+	APM_D static double sum0(const double *) { return 0.0; }
+	APM_D static double prior(const double *, int, const double *) { return 0.0; }
+	APM_D static double finish(double beta, double, double, const double * p, const double *) {
+		const double x = p[0];
+		double b = 0;
+		for (int i = 0; i < 10; i++) {
+			double pos = exp((double) i);
+			double height = 10.0; // 10 * pow(1.0, i)
+			double sigma = (double) i;
+			double a;
+			if (i % 2 == 0) {
+				double t = (x - pos) / sigma; // i == 0: +-inf or NaN, never taken by a > b
+				a = -sigma * (t * t) / 2 + height;
+			} else if (x > pos)
+				a = -height * (x - pos) / sigma + height;
+			else
+				a = -height * (pos - x) / sigma + height;
+			if (a > b)
+				b = a;
+		}
+		return beta * b;
+	}
+};
+
+// ---- apps/pulse_vrot.c:12-65 ----------------------------------------------------------------
+struct ModelPulseVrot {
+	static constexpr int NPAR = 7, NCOLS = 2;
+	static constexpr bool HAS_DATA = true, HAS_PRIOR = true;
+	struct Prep {
+		double lifetime, vrot, f1, h1, f2, h2;
+	};
+	APM_D static void prep(Prep & q, const double * p, int, const double *) {
+		q.lifetime = p[0];
+		q.vrot = p[2];
+		q.f1 = p[3];
+		q.h1 = p[4];
+		q.f2 = p[5];
+		q.h2 = p[6];
+	}
+	APM_D static double lorentz(double distance, double lifetime, double height) {
+		// mode_height / (1 + pow(2 * M_PI * distance * lifetime, 2))   (:49)
+		double t = (APM_TWO_PI * distance) * lifetime;
+		return height / (1 + t * t);
+	}
+	APM_D static double accum(double acc, const Prep & q, double freq, double d) {
+		double y = 0;
+		y += lorentz(q.f1 - freq, q.lifetime, q.h1);
+		y += lorentz(q.f2 - freq + -1 * q.vrot, q.lifetime, q.h2);
+		y += lorentz(q.f2 - freq, q.lifetime, q.h2);
+		y += lorentz(q.f2 - freq + 1 * q.vrot, q.lifetime, q.h2);
+		return acc + (log(y) + d / y); // (:61)
+	}
+	APM_D static double accum_fast(double acc, const Prep & q, double freq, double d, bool &) {
+		return accum(acc, q, freq, d);
+	}
+	APM_D static double sum0(const double * p) { return p[1]; } // accumulator starts at params[1] (:34)
+	APM_D static double prior(const double * p, int n_par, const double * mc) {
+		const double hmin = mc[0] != 0 ? mc[0] : 1e-6; // HMIN (:8-10)
+		double prior = 0;
+		for (int i = 3; i < n_par; i += 2)
+			prior += log(p[i + 1] + hmin);
+		return -prior / (double) ((n_par - 3) / 2); // (:12-23)
+	}
+	APM_D static double finish(double beta, double sum, double prior, const double *, const double *) {
+		return prior + -beta * sum; // (:64)
+	}
+};
+
+// ---- apps/pulse.c:12-56 (n_par = 2 + 2k, k modes) -------------------------------------------
+struct ModelPulse {
+	static constexpr int NPAR = 0, NCOLS = 2;
+	static constexpr bool HAS_DATA = true, HAS_PRIOR = true;
+	struct Prep {
+		double lifetime;
+		int n_modes;
+		double f[(APM_MAX_PAR - 2) / 2], h[(APM_MAX_PAR - 2) / 2];
+	};
+	APM_D static void prep(Prep & q, const double * p, int n_par, const double *) {
+		q.lifetime = p[0];
+		q.n_modes = (n_par - 2) / 2;
+#pragma unroll
+		for (int j = 0; j < (APM_MAX_PAR - 2) / 2; j++) {
+			if (j < q.n_modes) {
+				q.f[j] = p[2 + 2 * j];
+				q.h[j] = p[3 + 2 * j];
+			}
+		}
+	}
+	APM_D static double accum(double acc, const Prep & q, double freq, double d) {
+		double y = 0;
+#pragma unroll
+		for (int j = 0; j < (APM_MAX_PAR - 2) / 2; j++) {
+			if (j < q.n_modes)
+				y += ModelPulseVrot::lorentz(q.f[j] - freq, q.lifetime, q.h[j]);
+		}
+		return acc + (log(y) + d / y);
+	}
+	APM_D static double accum_fast(double acc, const Prep & q, double freq, double d, bool &) {
+		return accum(acc, q, freq, d);
+	}
+	APM_D static double sum0(const double * p) { return p[1]; }
+	APM_D static double prior(const double * p, int n_par, const double * mc) {
+		const double hmin = mc[0] != 0 ? mc[0] : 1e-6;
+		double prior = 0;
+		for (int i = 2; i < n_par; i += 2)
+			prior += log(p[i + 1] + hmin);
+		return -prior / (double) ((n_par - 2) / 2);
+	}
+	APM_D static double finish(double beta, double sum, double prior, const double *, const double *) {
+		return prior + -beta * sum;
+	}
+};
+
+#ifdef APM_USER_MODEL_HEADER
+} // namespace apm
+#include APM_USER_MODEL_HEADER
+namespace apm {
+#endif
+
+} // namespace apm

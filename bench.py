@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- chain-steps/s of the parallel-tempering hot path on config C3 of BASELINE.json:
+simplesin5 on a 1M-point synthetic light curve, 4096 chains (64 independent ensembles x a
+64-rung beta ladder) per GPU.
+
+A "step" is one PT round: n_swap = 2000 // n_beta = 31 Metropolis steps of every chain
+(Gaussian proposal -> calc_model over the whole light curve -> accept/reject -> best tracking
+-> trace/accumulators) followed by one swap attempt per ensemble.  chain-steps counts
+Metropolis steps actually executed (rejected ones included, swaps excluded).
+
+  value     device-timed (CUDA events on the engine's stream), inputs resident in HBM
+  e2e       the same work through the C ABI with pinned HOST buffers: every step uploads the
+            light curve and the chain state, runs one round, downloads state + traces
+  roofline  dominant kernel = loglik_tiled_kernel<simplesin5>; FP64-pipe bound (the likelihood
+            is a transcendental map-reduce).  achieved = row-evaluations/s x 17
+            FP64 instructions (4 arithmetic + 13 for sin, the ALGORITHMIC count) over the
+            kernel's CUDA-event time; peak = DFMA issue rate measured live on this GPU
+  cpu_baseline  the CPU oracle (reference semantics, OpenMP over chains like the reference)
+            on this box's cores, bounded sample
+
+Multi-GPU (torchrun, one rank per GPU): independent ensembles are sharded over the ranks, no
+data-path collective, weak scaling (4096 chains per GPU).
+
+--impl reference times the reference's CPU implementation on the host cores.  The unmodified
+reference cannot build apps/simplesin5.c, so this arm runs the CPU port of it
+(oracle/apm_oracle.c, byte-identical to the reference build on the models that do compile).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_ROWS = 1_000_000
+N_ENS, N_BETA, N_PAR = 64, 64, 4
+N_SWAP = 2000 // N_BETA  # reference src/parallel_tempering.c:228-231
+ALG_FP64_PER_ROW = 17    # simplesin5 = 4 arithmetic + 13 (fp64 sin fast path)
+TRUTH = np.array([1.3, 7.25, 0.31 * 2 * np.pi, 0.2])
+LO, HI = np.array([0.0, 4.0, 0.0, -1.0]), np.array([3.0, 10.0, 2 * np.pi, 1.0])
+
+
+def light_curve(n=N_ROWS):
+    """SURVEY.md 8d synthetic input: x_i = i * 1000/N (keeps 2*pi*f*x < 1e5), seed 12345"""
+    rng = np.random.default_rng(12345)
+    x = np.arange(n) * (1000.0 / n)
+    y = TRUTH[0] * np.sin(2 * np.pi * TRUTH[1] * x + TRUTH[2]) + TRUTH[3] + rng.normal(0, 0.5, n)
+    return np.ascontiguousarray(np.stack([x, y], axis=1))
+
+
+def ladder(n_beta, beta_0=0.01):
+    i = n_beta - np.arange(n_beta) - 1
+    return beta_0 + (1 - beta_0) / 2 * (1 - np.cos(i * np.pi / (n_beta - 1)))
+
+
+def chain_state(n_ens, n_beta, seed):
+    rng = np.random.default_rng(seed)
+    n = n_ens * n_beta
+    beta = np.tile(ladder(n_beta), n_ens)
+    post_sigma = np.array([7e-4, 3e-7, 1.1e-3, 5e-4])  # posterior widths at beta = 1, 1M rows
+    steps = post_sigma[None, :] * beta[:, None] ** -0.5
+    params = np.clip(TRUTH[None, :] + rng.normal(0, 1, (n, N_PAR)) * steps, LO, HI)
+    return dict(beta=beta, params=params, steps=steps, params_best=params.copy(),
+                prob=np.full(n, -1e10), prior=np.zeros(n), prob_best=np.full(n, -1e10))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def cpu_oracle_rate(data, seconds=15.0, n_threads=None):
+    """chain-steps/s of the CPU oracle on a bounded sample of the same workload: one 64-rung
+    ensemble on the full 1M-row table, as many rounds as fit in ~`seconds`."""
+    from oracle_binding import Oracle, RNG_PHILOX
+    cores = n_threads or os.cpu_count() or 1
+    st = chain_state(1, N_BETA, 99)
+    o = Oracle("simplesin5", 1, N_BETA, seed=1, rng=RNG_PHILOX, n_threads=cores)
+    o.set_data(data)
+    o.set_bounds(LO, HI)
+    o.set_chains(0, N_BETA, **st)
+    t0 = time.perf_counter()
+    o.run(1, 1)                      # one Metropolis step of all 64 chains: calibrates the sample size
+    t1 = time.perf_counter() - t0
+    steps = int(max(1, min(N_SWAP, seconds / max(t1, 1e-6))))
+    t0 = time.perf_counter()
+    o.run(1, steps)
+    dt = time.perf_counter() - t0
+    rate = N_BETA * steps / dt
+    sample = (f"1 ensemble x {N_BETA} chains x {steps} Metropolis steps + 1 swap on the full "
+              f"{N_ROWS}-row table ({dt:.1f} s), OpenMP over chains")
+    return rate, cores, sample, dt / steps * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = dist_env()
+    K, W = args.steps, max(args.warmup, 0)
+    config = {"workload": "C3: simplesin5, 1M-row synthetic light curve, 4096 chains per GPU "
+                          "(64 ensembles x 64-rung chebyshev ladder), n_swap 31",
+              "n_rows": N_ROWS, "n_chains_per_gpu": N_ENS * N_BETA, "n_ensembles_per_gpu": N_ENS,
+              "n_beta": N_BETA, "n_swap": N_SWAP, "parallelism": f"ensembles sharded over {args.gpus} GPU(s)",
+              "l2": "256 MiB flush write before the timed region and between e2e steps; the 16 MB "
+                    "table is L2-resident by design within a round"}
+    data = light_curve()
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"], check=True)
+        rates = []
+        per = max(2.0, min(args.cpu_seconds, 120.0 / max(K + min(W, 1), 1)))
+        for i in range(min(W, 1) + K):
+            rate, cores, sample, ms = cpu_oracle_rate(data, seconds=per)
+            if i >= min(W, 1):
+                rates.append((rate, ms))
+        v = float(np.mean([r[0] for r in rates]))
+        line = {"impl": "reference", "metric": "chain-steps/sec", "value": v, "unit": "chain-steps/s",
+                "n_gpus": args.gpus, "steps": K, "warmup": W,
+                "ms_per_step": float(np.mean([r[1] for r in rates])) * N_SWAP * N_ENS,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "chain-steps/s", "cores": cores, "kind": "port",
+                                 "sample": sample + "; the unmodified reference cannot build simplesin5 "
+                                           "(SURVEY.md D1), so its CPU port is timed"},
+                "e2e": {"value": v, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    import torch.distributed as dist
+    from apemost_b200 import capi
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng = capi.Engine("simplesin5", N_ENS, N_BETA, seed=1, device=local,
+                      chain_id_offset=rank * N_ENS * N_BETA, ensemble_id_offset=rank * N_ENS)
+    # pinned host buffers for everything that crosses PCIe in the e2e loop
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    h_data = pin(data)
+    st = {k: pin(v) for k, v in chain_state(N_ENS, N_BETA, 1000 + rank).items()}
+    eng.set_data(h_data)
+    eng.set_bounds(LO, HI)
+    eng.set_chains(0, eng.n_chains, **st)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    peak = capi.measure_fp64_peak(local, 0.25)
+
+    # warm-up rounds (untimed)
+    if W:
+        eng.run(W, N_SWAP, prob_every=1, params_chains=1)
+    flush.fill_(1)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = eng.launch_count()
+    t0 = time.perf_counter()
+    eng.run(K, N_SWAP, prob_every=1, params_chains=1)   # K steps, device-timed inside the engine
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ll_ms, ll_launches, total_ms = eng.last_kernel_ms()
+    launches = eng.launch_count() - launches0
+    clocks = sampler.summary()
+
+    # end to end through the C ABI with host buffers
+    h2d = h_data.nbytes + sum(v.nbytes for v in st.values())
+    e2e_ms = []
+    d2h = 0
+    barrier()
+    for i in range(1 + K):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.set_data(h_data)
+        eng.set_chains(0, eng.n_chains, **st)
+        eng.run(1, N_SWAP, prob_every=1, params_chains=1)
+        out = eng.get_chains()
+        tr = eng.read_trace()
+        dt = (time.perf_counter() - t0) * 1e3
+        d2h = sum(v.nbytes for v in out.values()) + sum(v.nbytes for v in tr.values())
+        if i >= 1:
+            e2e_ms.append(dt)
+    e2e_ms = float(np.mean(e2e_ms))
+
+    steps_per_round = eng.n_chains * N_SWAP
+    t = torch.tensor([total_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, wall_ms = [float(v) for v in t.tolist()]
+    value = world * steps_per_round * K / (total_ms * 1e-3)
+    e2e = world * steps_per_round / (e2e_ms * 1e-3)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"], check=True)
+        rate, cores, sample, _ = cpu_oracle_rate(data, seconds=args.cpu_seconds)
+        cpu = {"value": rate, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        row_evals_per_launch = eng.n_chains * N_ROWS
+        achieved = row_evals_per_launch * ALG_FP64_PER_ROW / (ll_ms / max(ll_launches, 1) * 1e-3)
+        hbm_alg_bytes = N_ROWS * 16 * (eng.n_chains / 16)  # the table once per 16-chain tile
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        line = {
+            "metric": "chain-steps/sec", "value": value, "unit": "chain-steps/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e, "unit": "chain-steps/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches),
+            "roofline": {
+                "bound": "fp64", "kernel": "loglik_tiled_kernel<ModelSimplesin5>",
+                "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "GFP64-instr/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "measured live: fp64_peak_kernel DFMA issue rate on this GPU "
+                               "(MEASURED_PEAKS.json has no fp64 entry)",
+                "algorithmic": "17 FP64 instr per row-evaluation x 4096 chains x 1e6 rows per launch",
+                "kernel_ms_per_launch": ll_ms / max(ll_launches, 1), "kernel_launches_timed": int(ll_launches),
+                "kernel_share_of_step": ll_ms / total_ms,
+                "hbm": {"achieved": hbm_alg_bytes / (ll_ms / max(ll_launches, 1) * 1e-3) / 1e9,
+                        "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                        "note": "algorithmic bytes = table once per 16-chain tile; it is served by L2"},
+            },
+            "cpu_baseline": cpu, "clocks": clocks, "wall_ms_per_step": wall_ms / K,
+            "row_evals_per_s": value * N_ROWS,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

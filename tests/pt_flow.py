@@ -173,3 +173,12 @@ def run(eng, rows, workdir, max_iterations, n_swap=-30, write_files=True, names=
                 for v in tr["params"][:, 0, j]:
                     f.write("%.15e\n" % v)
     return tr, n_swap
+
+
+def evidence(beta, mean_dl):
+    """analyse_data_probability's rectangle rule (src/analyse.c:50-93): mean_dl[k] = mean of
+    (prob - prior) of chain k; ln Z = sum_k mean_dl[k] / beta[k] * (beta[k] - beta[k+1]), beta[n] := 0."""
+    beta = np.asarray(beta, dtype=float)
+    mean_dl = np.asarray(mean_dl, dtype=float)
+    prev = np.concatenate([beta[1:], [0.0]])
+    return float(np.sum(mean_dl / beta * (beta - prev)))

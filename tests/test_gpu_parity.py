@@ -1,0 +1,326 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI
+(include/apemost_gpu.h) via ctypes.
+
+Tolerances
+  calc_model (fp64): 1e-12 relative against the oracle / the golden fixtures (north_star).
+  trajectories: the engine and the oracle (ORC_RNG_PHILOX) share the counter RNG, so chains are
+  compared step by step: accept/reject counters must be equal, visited points agree to 1e-9
+  relative (device log/cos/sqrt differ from glibc's in the last ulp; the likelihood sum is
+  reduced in a different order).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import pt_flow
+from oracle_binding import Oracle, RNG_PHILOX
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL_LOGLIK = 1e-12
+RTOL_TRAJ = 1e-9
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from apemost_b200 import capi as c
+    c.load_library()
+    return c
+
+
+def load(name):
+    return json.load(open(os.path.join(GOLDEN, name + ".json")))
+
+
+def lightcurve(n, seed=12345, span=1000.0):
+    rng = np.random.default_rng(seed)
+    x = np.arange(n) * (span / n)
+    y = 1.3 * np.sin(2 * np.pi * 7.25 * x + 0.31 * 2 * np.pi) + 0.2 + rng.normal(0, 0.5, n)
+    return np.stack([x, y], axis=1)
+
+
+SS5_LO, SS5_HI = np.array([0.0, 4.0, 0.0, -1.0]), np.array([3.0, 10.0, 2 * np.pi, 1.0])
+
+
+# ---------------------------------------------------------------- calc_model
+def test_manual_known_answer(capi):
+    """reference doc/manual.rst:189-213"""
+    e = capi.Engine("simplesin", 1, 1)
+    e.set_data(np.array([[101, 0.67], [102, 1.01], [103, 0.79], [104, 1.34]]))
+    prob, prior = e.eval([[1, 0.2, 1, 0]])
+    assert abs(prob[0] / -1.480898044165363e+01 - 1) < RTOL_LOGLIK
+    assert prior[0] == 0.0
+
+
+@pytest.mark.parametrize("model", ["simplesin", "simplesin5", "simplesin2", "normal", "pulse_vrot", "pulse"])
+def test_calc_model_matches_reference_fixture(capi, model):
+    fx = load("eval_" + model)
+    n_par = len(fx["rows"])
+    data = np.array(fx["data"], dtype=float).reshape(-1, fx["n_cols"])
+    params = np.array(fx["params"], dtype=float).reshape(-1, n_par)
+    e = capi.Engine(model, 1, 1, n_par=n_par)
+    e.set_data(data)
+    prob, prior = e.eval(params)
+    np.testing.assert_allclose(prob, np.array(fx["prob"], dtype=float), rtol=RTOL_LOGLIK)
+    np.testing.assert_allclose(prior, np.array(fx["prior"], dtype=float), rtol=RTOL_LOGLIK)
+
+
+@pytest.mark.parametrize("n_rows", [1, 7, 2047, 2048, 2049, 6000, 100000])
+@pytest.mark.parametrize("model", ["simplesin5", "simplesin"])
+def test_calc_model_ragged_sizes(capi, model, n_rows):
+    """row counts around the 2048-row chunk: empty tails, exactly full, one over"""
+    data = lightcurve(n_rows, seed=n_rows)
+    rng = np.random.default_rng(n_rows + 1)
+    lo, hi = (SS5_LO, SS5_HI) if model == "simplesin5" else (SS5_LO, np.array([3.0, 10.0, 1.0, 1.0]))
+    params = rng.uniform(lo, hi, size=(37, 4))
+    beta = rng.uniform(0.01, 1, 37)
+    e, o = capi.Engine(model, 1, 1), Oracle(model, 1, 1)
+    for eng in (e, o):
+        eng.set_data(data)
+    p_gpu, _ = e.eval(params, beta)
+    p_cpu, _ = o.eval(params, beta)
+    np.testing.assert_allclose(p_gpu, p_cpu, rtol=RTOL_LOGLIK)
+
+
+def test_calc_model_million_rows(capi):
+    """config C3's table size: 1M rows, 64 parameter vectors"""
+    data = lightcurve(1_000_000)
+    rng = np.random.default_rng(3)
+    params = rng.uniform(SS5_LO, SS5_HI, size=(64, 4))
+    params[0] = [1.3, 7.25, 0.31 * 2 * np.pi, 0.2]
+    e, o = capi.Engine("simplesin5", 1, 1), Oracle("simplesin5", 1, 1)
+    for eng in (e, o):
+        eng.set_data(data)
+    p_gpu, _ = e.eval(params)
+    p_cpu, _ = o.eval(params)
+    np.testing.assert_allclose(p_gpu, p_cpu, rtol=RTOL_LOGLIK)
+
+
+def test_calc_model_outside_fast_sine_range(capi):
+    """|argument| >= 2^30, infinities: the kernel's exact fallback must agree with libm"""
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(0, 50, 3000), rng.uniform(1e9, 1e13, 200), [1e300, 3e15]])
+    rng.shuffle(x)
+    data = np.stack([x, rng.normal(0, 1, x.size)], axis=1)
+    params = rng.uniform(SS5_LO, SS5_HI, size=(9, 4))
+    e, o = capi.Engine("simplesin5", 1, 1), Oracle("simplesin5", 1, 1)
+    for eng in (e, o):
+        eng.set_data(data)
+    p_gpu, _ = e.eval(params)
+    p_cpu, _ = o.eval(params)
+    np.testing.assert_allclose(p_gpu, p_cpu, rtol=RTOL_LOGLIK)
+
+
+def test_wide_table_is_narrowed(capi):
+    """a data file with more columns than the model reads (gsl_matrix with tda > 2)"""
+    d2 = lightcurve(5000)
+    d4 = np.concatenate([d2, np.ones((5000, 2))], axis=1)
+    params = np.array([[1.3, 7.25, 1.9, 0.2]])
+    e2, e4 = capi.Engine("simplesin5", 1, 1), capi.Engine("simplesin5", 1, 1)
+    e2.set_data(d2)
+    e4.set_data(d4)
+    assert e2.eval(params)[0][0] == e4.eval(params)[0][0]
+
+
+def test_linearity_in_rows(capi):
+    """size-independent property: the running sum over a table equals the sum over its halves"""
+    data = lightcurve(300001)
+    params = np.array([[1.1, 7.3, 2.0, 0.1], [0.5, 5.0, 0.3, -0.2]])
+    full = capi.Engine("simplesin5", 1, 1)
+    full.set_data(data)
+    a, b = capi.Engine("simplesin5", 1, 1), capi.Engine("simplesin5", 1, 1)
+    a.set_data(data[:123457])
+    b.set_data(data[123457:])
+    np.testing.assert_allclose(full.eval(params)[0], a.eval(params)[0] + b.eval(params)[0], rtol=1e-13)
+
+
+# ---------------------------------------------------------------- sampler trajectories
+def _pair(capi, model, n_ens, n_beta, n_par=None, seed=1, **kw):
+    return (capi.Engine(model, n_ens, n_beta, n_par=n_par, seed=seed, **kw),
+            Oracle(model, n_ens, n_beta, n_par=n_par, seed=seed, rng=RNG_PHILOX, **kw))
+
+
+def _compare_state(st_gpu, st_cpu):
+    for k in ("accept", "reject", "params_accepts", "params_rejects", "n_iter", "swapcount", "rng_counter"):
+        np.testing.assert_array_equal(st_gpu[k], st_cpu[k], err_msg=k)
+    for k in ("params", "params_best", "steps", "prob", "prior", "prob_best", "beta"):
+        np.testing.assert_allclose(st_gpu[k], st_cpu[k], rtol=RTOL_TRAJ, atol=1e-300, err_msg=k)
+
+
+@pytest.mark.parametrize("quirks", [3, 0])
+@pytest.mark.parametrize("name,kw", [("c1_phases", {}), ("c1_circular_phases", dict(circular_mask=4)),
+                                      ("c1_logistic_phases", dict(proposal=1)),
+                                      ("c1_uniform_phases", dict(proposal=2)), ("c4_phases", {}),
+                                      ("c2_phases", {})])
+def test_run_trajectory_equals_oracle(capi, name, kw, quirks):
+    """3 ensembles x the fixture's ladder, started from the reference's own calibration_results:
+    the whole run (steps, swaps, best tracking, traces, accumulators) against the oracle"""
+    fx = load(name)
+    rows = [tuple(r) for r in fx["rows"]]
+    n_par, n_beta, n_ens = len(rows), fx["config"]["N_BETA"], 3
+    data = (np.loadtxt(os.path.join(GOLDEN, fx["data_file"])) if fx["data_file"]
+            else np.array(fx["data"], dtype=float).reshape(-1, 2))
+    cal = np.array(fx["phases"]["calibrate_rest"].split(), dtype=float).reshape(n_beta, 1 + 2 * n_par)
+    engines = _pair(capi, fx["model"], n_ens, n_beta, n_par=n_par, seed=17, quirks=quirks, **kw)
+    res = []
+    for eng in engines:
+        eng.set_data(data)
+        pt_flow.setup_chains(eng, rows)
+        pt_flow.apply_calibration(eng, 0, np.tile(cal[:, 0], n_ens), np.tile(cal[:, 1:1 + n_par], (n_ens, 1)),
+                                  np.tile(cal[:, 1 + n_par:], (n_ens, 1)))
+        eng.reset_stats()
+        eng.run(8, 40, prob_every=1, params_chains=2)
+        res.append((eng.read_trace(), eng.get_chains(), eng.get_stats()))
+    (tr_g, st_g, ac_g), (tr_c, st_c, ac_c) = res
+    _compare_state(st_g, st_c)
+    for k in ("prob", "prob_minus_prior", "params"):
+        np.testing.assert_allclose(tr_g[k], tr_c[k], rtol=RTOL_TRAJ, atol=1e-300, err_msg=k)
+    np.testing.assert_array_equal(ac_g["n"], ac_c["n"])
+    for k in ("sum_dl", "sum_params", "sum_params_sq"):
+        np.testing.assert_allclose(ac_g[k], ac_c[k], rtol=RTOL_TRAJ)
+    assert st_g["swapcount"].sum() > 0, "the test must exercise accepted swaps"
+
+
+def test_run_continues_across_calls(capi):
+    """two runs of 4 rounds == one run of 8 rounds (state, RNG position and swap stream persist)"""
+    fx = load("c1_phases")
+    rows = [tuple(r) for r in fx["rows"]]
+    data = np.loadtxt(os.path.join(GOLDEN, fx["data_file"]))
+    outs = []
+    for split in (False, True):
+        e = capi.Engine("simplesin", 2, 4, seed=3)
+        e.set_data(data)
+        pt_flow.setup_chains(e, rows)
+        e.set_chains(0, 8, beta=np.tile([1.0, 0.6, 0.3, 0.1], 2))
+        if split:
+            e.run(4, 25)
+            e.run(4, 25)
+        else:
+            e.run(8, 25)
+        outs.append(e.get_chains())
+    for k in outs[0]:
+        np.testing.assert_array_equal(outs[0][k], outs[1][k], err_msg=k)
+
+
+def test_single_chain_ladder_never_swaps(capi):
+    data = lightcurve(3000)
+    for eng in _pair(capi, "simplesin5", 5, 1, seed=2):
+        eng.set_data(data)
+        eng.set_bounds(SS5_LO, SS5_HI)
+        eng.set_chains(0, 5, params=np.tile([1.3, 7.25, 1.9, 0.2], (5, 1)), steps=np.tile([0.01, 1e-5, 0.01, 0.01], (5, 1)))
+        eng.run(3, 10)
+        assert eng.get_chains()["swapcount"].sum() == 0
+
+
+def test_big_table_run_trajectory(capi):
+    """a table that spans many chunks and row splits (300k rows), 2 x 8 chains"""
+    data = lightcurve(300_000)
+    n_ens, n_beta = 2, 8
+    n = n_ens * n_beta
+    rng = np.random.default_rng(0)
+    params = np.tile([1.3, 7.25, 0.31 * 2 * np.pi, 0.2], (n, 1)) + rng.normal(0, 1e-5, (n, 4))
+    beta = np.tile(pt_flow.chebyshev_ladder(n_beta, 0.01), n_ens)
+    steps = np.tile([3e-3, 2e-6, 3e-3, 2e-3], (n, 1)) * beta[:, None] ** -0.5
+    res = []
+    for eng in _pair(capi, "simplesin5", n_ens, n_beta, seed=9):
+        eng.set_data(data)
+        eng.set_bounds(SS5_LO, SS5_HI)
+        eng.set_chains(0, n, beta=beta, params=params, steps=steps, params_best=params)
+        eng.run(2, 10, prob_every=1, params_chains=1)
+        res.append((eng.read_trace(), eng.get_chains()))
+    _compare_state(res[0][1], res[1][1])
+    np.testing.assert_allclose(res[0][0]["prob"], res[1][0]["prob"], rtol=RTOL_TRAJ)
+
+
+# ---------------------------------------------------------------- calibration
+@pytest.mark.parametrize("name", ["c1_phases", "c4_phases", "c2_phases"])
+def test_calibration_trajectory_equals_oracle(capi, name):
+    """markov_chain_calibrate (burn_in + _orig) for every chain of 2 ensembles concurrently:
+    final step widths, positions, counters and the progress rows against the oracle"""
+    fx = load(name)
+    rows = [tuple(r) for r in fx["rows"]]
+    n_par, n_beta, n_ens = len(rows), fx["config"]["N_BETA"], 2
+    data = (np.loadtxt(os.path.join(GOLDEN, fx["data_file"])) if fx["data_file"]
+            else np.array(fx["data"], dtype=float).reshape(-1, 2))
+    cal = np.array(fx["phases"]["calibrate_rest"].split(), dtype=float).reshape(n_beta, 1 + 2 * n_par)
+    res = []
+    for eng in _pair(capi, fx["model"], n_ens, n_beta, n_par=n_par, seed=23):
+        eng.set_data(data)
+        start, lo, hi, names, step = pt_flow.setup_chains(eng, rows)
+        n = n_ens * n_beta
+        beta = np.tile(cal[:, 0], n_ens)
+        eng.set_chains(0, n, beta=beta, steps=np.tile(step, (n, 1)) * beta[:, None] ** -0.5)
+        st = eng.get_chains(fields=("params", "beta"))
+        prob, prior = eng.eval(st["params"], st["beta"])
+        eng.set_chains(0, n, prob=prob, prior=prior)
+        status, prog = eng.calibrate(burn_in_iterations=600, progress_capacity=100000)
+        res.append((status, prog, eng.get_chains()))
+    (s_g, p_g, st_g), (s_c, p_c, st_c) = res
+    np.testing.assert_array_equal(s_g, s_c)
+    assert (s_g == 0).all()
+    _compare_state(st_g, st_c)
+    assert len(p_g) == len(p_c) and len(p_g) > 0
+    key = lambda r: (r[0], r[2], r[1])
+    for a, b in zip(sorted(p_g, key=key), sorted(p_c, key=key)):
+        assert a[:3] == b[:3]
+        np.testing.assert_allclose(a[3:], b[3:], rtol=RTOL_TRAJ)
+
+
+def test_calibration_selection_and_failure_status(capi):
+    """only selected chains move; a chain whose acceptance rate cannot be brought down (flat
+    likelihood) ends with the reference's 'iteration limit' failure (markov_chain_calibrate.c
+    :1169-1174) reported per chain instead of exit(1)"""
+    rows = [(100.0, -10.0, 10000.0, "x", -1.0)]
+    res = []
+    for eng in _pair(capi, "normal", 1, 3, seed=4):
+        eng.set_data(np.zeros((2, 2)))
+        pt_flow.setup_chains(eng, rows)
+        eng.set_chains(0, 3, beta=[1.0, 0.5, 0.001])
+        sel = np.array([0, 0, 1], dtype=np.uint8)
+        status, _ = eng.calibrate(select=sel, burn_in_iterations=400, iter_limit=3000, raise_on_failure=False)
+        res.append((status, eng.get_chains()))
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    assert res[0][0].tolist() == [-1, -1, 2]
+    assert res[0][1]["rng_counter"][:2].tolist() == [0, 0]
+    _compare_state(res[0][1], res[1][1])
+
+
+# ---------------------------------------------------------------- statistical parity with the reference
+def test_evidence_and_posterior_match_reference_statistics(capi):
+    """Second half of 'correctness' (north_star): with different RNG streams the engine's
+    posterior moments and thermodynamic-integration evidence must agree with the reference's.
+    Protocol: same params file, same calibration_results (the reference's own, from
+    tests/golden/c1_phases.json), 24 independent engine ensembles x 3000 iterations vs the
+    reference's run recorded in the fixture and the oracle (pinned byte-for-byte to the reference)
+    over 24 seeds; tolerance 5 standard errors of the seed-to-seed scatter."""
+    fx = load("c1_phases")
+    rows = [tuple(r) for r in fx["rows"]]
+    n_par, n_beta, n_ens, iters = 4, 4, 24, 3000
+    data = np.loadtxt(os.path.join(GOLDEN, fx["data_file"]))
+    cal = np.array(fx["phases"]["calibrate_rest"].split(), dtype=float).reshape(n_beta, 1 + 2 * n_par)
+    n_swap = 2000 // n_beta
+
+    def run(eng):
+        eng.set_data(data)
+        pt_flow.setup_chains(eng, rows)
+        pt_flow.apply_calibration(eng, 0, np.tile(cal[:, 0], n_ens), np.tile(cal[:, 1:1 + n_par], (n_ens, 1)),
+                                  np.tile(cal[:, 1 + n_par:], (n_ens, 1)))
+        eng.reset_stats()
+        eng.run(iters // n_swap, n_swap)
+        s = eng.get_stats()
+        mean_dl = (s["sum_dl"] / s["n"]).reshape(n_ens, n_beta)
+        lnz = np.array([pt_flow.evidence(cal[:, 0], m) for m in mean_dl])
+        mean_p = (s["sum_params"] / s["n"][:, None]).reshape(n_ens, n_beta, n_par)[:, 0, :]
+        return lnz, mean_p
+
+    lnz_g, mp_g = run(capi.Engine("simplesin", n_ens, n_beta, seed=101))
+    lnz_c, mp_c = run(Oracle("simplesin", n_ens, n_beta, seed=202, rng=RNG_PHILOX))
+    se = np.sqrt(lnz_g.var(ddof=1) / n_ens + lnz_c.var(ddof=1) / n_ens)
+    assert abs(lnz_g.mean() - lnz_c.mean()) < 5 * se, (lnz_g.mean(), lnz_c.mean(), se)
+    # the reference's own single run (GSL MT19937 stream) must be a typical member
+    assert abs(float(fx["evidence"]) - lnz_g.mean()) < 5 * lnz_g.std(ddof=1)
+    se_p = np.sqrt(mp_g.var(axis=0, ddof=1) / n_ens + mp_c.var(axis=0, ddof=1) / n_ens)
+    assert (np.abs(mp_g.mean(axis=0) - mp_c.mean(axis=0)) < 5 * se_p).all()
