@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -285,12 +286,17 @@ extern "C" int apm_gpu_destroy(apm_gpu * h) {
 static void make_plan(const apm_gpu * h, int n_slots, int & tile, int & n_ctiles, int & n_splits,
 		int & cps) {
 	const int n_chunks = std::max(h->n_chunks, 1);
-	tile = 16;
+	tile = std::min(16, (int) LL_MAX_TILE);
+	if (const char * t = getenv("APM_TILE")) // kernel-sweep override
+		tile = std::max(1, std::min(atoi(t), (int) LL_MAX_TILE));
 	// few chains: smaller tiles so that the chain axis alone gives some parallelism
 	while (tile > 1 && (n_slots + tile - 1) / tile < 4 && n_slots > 1)
 		tile /= 2;
 	n_ctiles = (n_slots + tile - 1) / tile;
-	long long target_items = 40ll * std::max(h->ll_grid, 1);
+	long long per_cta = 40;
+	if (const char * t = getenv("APM_ITEMS_PER_CTA"))
+		per_cta = std::max(1, atoi(t));
+	long long target_items = per_cta * std::max(h->ll_grid, 1);
 	long long want = (target_items + n_ctiles - 1) / n_ctiles;
 	n_splits = (int) std::min<long long>(std::max<long long>(want, 1), n_chunks);
 	cps = (n_chunks + n_splits - 1) / n_splits;
@@ -879,7 +885,7 @@ extern "C" int apm_gpu_measure_fp64_peak(int device, double seconds, double * in
 	cudaEvent_t t0, t1;
 	CU(cudaEventCreate(&t0));
 	CU(cudaEventCreate(&t1));
-	int iters = 2000;
+	int iters = 500;
 	double best = 0;
 	// warm up, then grow the launch until it lasts long enough to average over clock ramps
 	for (int rep = 0; rep < 12; rep++) {
@@ -889,7 +895,7 @@ extern "C" int apm_gpu_measure_fp64_peak(int device, double seconds, double * in
 		CU(cudaEventSynchronize(t1));
 		float ms = 0;
 		CU(cudaEventElapsedTime(&ms, t0, t1));
-		double rate = (double) grid * block * (double) iters * 64.0 / (ms * 1e-3);
+		double rate = (double) grid * block * (double) iters * 256.0 / (ms * 1e-3);
 		if (rep >= 2 && rate > best)
 			best = rate;
 		if (ms * 1e-3 < seconds / 4 && iters < (1 << 24))

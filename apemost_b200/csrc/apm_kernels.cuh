@@ -65,12 +65,32 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ------------------------------------------------------------------ tiled likelihood
-constexpr int LL_THREADS = 256;
+// tuning knobs (overridable at build time for kernel sweeps: tools/kernel_sweep.py)
+#ifndef APM_LL_THREADS
+#define APM_LL_THREADS 256
+#endif
+#ifndef APM_LL_RPT
+#define APM_LL_RPT 16
+#endif
+#ifndef APM_LL_MINBLOCKS
+#define APM_LL_MINBLOCKS 1
+#endif
+#ifndef APM_LL_STAGES
+#define APM_LL_STAGES 2
+#endif
+#ifndef APM_LL_CPV
+#define APM_LL_CPV 1
+#endif
+constexpr int LL_THREADS = APM_LL_THREADS;
 constexpr int LL_WARPS = LL_THREADS / 32;
-constexpr int LL_RPT = 8;                       // rows per thread per chunk (held in registers)
+constexpr int LL_RPT = APM_LL_RPT;                       // rows per thread per chunk (held in registers)
 constexpr int LL_CHUNK = LL_THREADS * LL_RPT;   // 2048 rows = 32 KB per stage
-constexpr int LL_STAGES = 2;
-constexpr int LL_MAX_TILE = 32;                 // chains per work item (upper bound)
+constexpr int LL_STAGES = APM_LL_STAGES;
+#ifndef APM_LL_MAX_TILE
+#define APM_LL_MAX_TILE 16
+#endif
+constexpr int LL_MAX_TILE = APM_LL_MAX_TILE;    // chains per work item (upper bound)
+constexpr int LL_CPV = APM_LL_CPV;              // chains evaluated together in one visit
 
 struct LLArgs {
 	const double * data;    // [n_rows_padded][2], padded with zeros to a multiple of LL_CHUNK
@@ -88,13 +108,62 @@ struct LLArgs {
 	double model_const[4];
 };
 
+// One visit: NC chains of the tile against the thread's LL_RPT register-held rows.  All
+// NC x LL_RPT row evaluations are independent, so the compiler interleaves them and the fp64
+// pipe sees long runs of back-to-back independent instructions; the per-visit costs (constant
+// loads, accumulator update, loop control, pipeline drain at the branch) are paid once per
+// NC x LL_RPT evaluations.  rows[] is only ever indexed by unrolled constants (registers).
+template<class M, int NC>
+__device__ __forceinline__ void ll_visit(const double2 (&rows)[LL_RPT], const double * sparams,
+		double * sacc, const int c, const int n_par, const double * mc, const bool full_chunk,
+		const int n_valid, const int tid, const double xub) {
+	typename M::Prep q[NC];
+	double acc[NC][2];
+#pragma unroll
+	for (int u = 0; u < NC; u++) {
+		M::prep(q[u], sparams + (c + u) * APM_MAX_PAR, n_par, mc);
+		acc[u][0] = 0.0;
+		acc[u][1] = 0.0;
+	}
+	// branch-free fast path when the model says every row of this thread is inside the fast
+	// range for these chains (one bound check per visit, none per row); otherwise -- and for
+	// every thread of a ragged last chunk -- the exact, masked path
+	bool fast = full_chunk;
+#pragma unroll
+	for (int u = 0; u < NC; u++)
+		fast = fast && M::fast_ok(q[u], xub);
+	if (fast) {
+#pragma unroll
+		for (int j = 0; j < LL_RPT; j += 2) {
+#pragma unroll
+			for (int u = 0; u < NC; u++) {
+				acc[u][0] = M::accum_fast(acc[u][0], q[u], rows[j].x, rows[j].y);
+				acc[u][1] = M::accum_fast(acc[u][1], q[u], rows[j + 1].x, rows[j + 1].y);
+			}
+		}
+	} else {
+#pragma unroll
+		for (int u = 0; u < NC; u++) {
+			acc[u][0] = 0.0;
+			acc[u][1] = 0.0;
+#pragma unroll
+			for (int j = 0; j < LL_RPT; j++)
+				if (j * LL_THREADS + tid < n_valid)
+					acc[u][0] = M::accum(acc[u][0], q[u], rows[j].x, rows[j].y);
+		}
+	}
+#pragma unroll
+	for (int u = 0; u < NC; u++)
+		sacc[(c + u) * LL_THREADS + tid] += acc[u][0] + acc[u][1];
+}
+
 template<class M>
-__global__ void __launch_bounds__(LL_THREADS, 2) loglik_tiled_kernel(const LLArgs a) {
+__global__ void __launch_bounds__(LL_THREADS, APM_LL_MINBLOCKS) loglik_tiled_kernel(const LLArgs a) {
 	extern __shared__ __align__(128) unsigned char ll_smem[];
 	double2 * sdata = reinterpret_cast<double2 *>(ll_smem);                      // [STAGES][CHUNK]
 	double * sparams = reinterpret_cast<double *>(sdata + LL_STAGES * LL_CHUNK); // [MAX_TILE][MAX_PAR]
-	double * swacc = sparams + LL_MAX_TILE * APM_MAX_PAR;                        // [MAX_TILE][WARPS]
-	int * sact = reinterpret_cast<int *>(swacc + LL_MAX_TILE * LL_WARPS);        // [MAX_TILE]
+	double * sacc = sparams + LL_MAX_TILE * APM_MAX_PAR;                         // [MAX_TILE][THREADS]
+	int * sact = reinterpret_cast<int *>(sacc + LL_MAX_TILE * LL_THREADS);       // [MAX_TILE]
 	uint64_t * full = reinterpret_cast<uint64_t *>(sact + LL_MAX_TILE);          // [STAGES]
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -118,11 +187,14 @@ __global__ void __launch_bounds__(LL_THREADS, 2) loglik_tiled_kernel(const LLArg
 		const int k0 = split * a.chunks_per_split;
 		const int nk = min(a.chunks_per_split, a.n_chunks - k0);
 
-		// stage the tile's parameter vectors, clear the per-warp accumulators
+		// stage the tile's parameter vectors, clear the accumulators.  Every thread owns one
+		// fp64 accumulator per chain of the tile in shared memory (sacc[c][tid], conflict-free):
+		// a chain visit costs one LDS + one STS instead of a 5-stage shuffle reduction, and the
+		// cross-thread reduction happens once per work item, in a fixed order.
 		for (int i = tid; i < nT * n_par; i += LL_THREADS)
 			sparams[(i / n_par) * APM_MAX_PAR + (i % n_par)] = a.prop[(size_t) c0 * n_par + i];
-		for (int i = tid; i < nT * LL_WARPS; i += LL_THREADS)
-			swacc[i] = 0.0;
+		for (int c = 0; c < nT; c++)
+			sacc[c * LL_THREADS + tid] = 0.0;
 		if (tid < nT)
 			sact[tid] = a.pend ? (a.pend[c0 + tid] >= 0) : 1;
 		// prologue of the TMA ring
@@ -152,52 +224,44 @@ __global__ void __launch_bounds__(LL_THREADS, 2) loglik_tiled_kernel(const LLArg
 			const long long row0 = (long long) (k0 + k) * LL_CHUNK;
 			const int n_valid = (int) min((long long) LL_CHUNK, a.n_rows - row0);
 			const bool full_chunk = n_valid == LL_CHUNK;
-			for (int c = 0; c < nT; c++) {
-				if (!sact[c])
-					continue;
-				typename M::Prep q;
-				M::prep(q, sparams + c * APM_MAX_PAR, n_par, a.model_const);
-				// branch-free fast path over the thread's rows (two accumulators: the d*d FMA
-				// chain is half as long).  A row outside the fast range only raises `bad`; the
-				// rare thread that saw one -- and every thread of a ragged last chunk -- takes
-				// the exact, masked path below instead.  rows[] is only ever indexed by
-				// unrolled constants, so it stays in registers.
-				double acc0 = 0.0, acc1 = 0.0;
-				bool bad = !full_chunk;
-				if (full_chunk) {
+			// upper bound of |x| over this thread's rows: max of the high words (monotonic for
+			// |doubles|; Inf/NaN give the largest), rounded up to the next high word
+			int xhi = 0;
 #pragma unroll
-					for (int j = 0; j < LL_RPT; j += 2) {
-						acc0 = M::accum_fast(acc0, q, rows[j].x, rows[j].y, bad);
-						acc1 = M::accum_fast(acc1, q, rows[j + 1].x, rows[j + 1].y, bad);
-					}
-				}
-				if (bad) {
-					acc0 = 0.0;
-					acc1 = 0.0;
+			for (int j = 0; j < LL_RPT; j++)
+				xhi = max(xhi, hi32(rows[j].x) & 0x7fffffff);
+			const double xub = make_double(xhi + 1, 0);
+			int c = 0;
+			for (; c + LL_CPV <= nT; c += LL_CPV) {
+				bool any = false;
 #pragma unroll
-					for (int j = 0; j < LL_RPT; j++)
-						if (j * LL_THREADS + tid < n_valid)
-							acc0 = M::accum(acc0, q, rows[j].x, rows[j].y);
-				}
-				double v = warp_sum(acc0 + acc1);
-				if (lane == 0)
-					swacc[c * LL_WARPS + warp] += v;
+				for (int u = 0; u < LL_CPV; u++)
+					any |= sact[c + u] != 0;
+				if (any)
+					ll_visit<M, LL_CPV>(rows, sparams, sacc, c, n_par, a.model_const, full_chunk, n_valid, tid, xub);
 			}
+			for (; c < nT; c++)
+				if (sact[c])
+					ll_visit<M, 1>(rows, sparams, sacc, c, n_par, a.model_const, full_chunk, n_valid, tid, xub);
 		}
 		__syncthreads();
-		if (tid < nT) {
-			double s = 0.0;
+		// fold the tile: warp w reduces chains w, w + WARPS, ...; lane l first adds its 8 strided
+		// thread slots in index order, then a butterfly -- the same order every run
+		for (int c = warp; c < nT; c += LL_WARPS) {
+			double v = 0.0;
 #pragma unroll
-			for (int w = 0; w < LL_WARPS; w++)
-				s += swacc[tid * LL_WARPS + w];
-			a.partial[(size_t) (c0 + tid) * a.n_splits + split] = s;
+			for (int k = 0; k < LL_THREADS / 32; k++)
+				v += sacc[c * LL_THREADS + k * 32 + lane];
+			v = warp_sum(v);
+			if (lane == 0)
+				a.partial[(size_t) (c0 + c) * a.n_splits + split] = v;
 		}
 		__syncthreads();
 	}
 }
 
 constexpr size_t LL_SMEM_BYTES = sizeof(double2) * LL_STAGES * LL_CHUNK
-		+ sizeof(double) * LL_MAX_TILE * APM_MAX_PAR + sizeof(double) * LL_MAX_TILE * LL_WARPS
+		+ sizeof(double) * LL_MAX_TILE * APM_MAX_PAR + sizeof(double) * LL_MAX_TILE * LL_THREADS
 		+ sizeof(int) * LL_MAX_TILE + sizeof(uint64_t) * LL_STAGES;
 
 // ------------------------------------------------------------------ control kernel
@@ -294,13 +358,14 @@ __global__ void eval_finish_kernel(int n, int n_par, const double * params, cons
 }
 
 // ------------------------------------------------------------------ FP64 peak
-// 8 independent DFMA chains per thread; the result is stored so nothing is elided.
+// 8 independent DFMA chains per thread, 256 DFMAs per loop trip (loop overhead ~1%); the
+// result is stored so nothing is elided.
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double * out, int iters, double a, double b) {
 	double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
 	double x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
 	for (int i = 0; i < iters; i++) {
 #pragma unroll
-		for (int u = 0; u < 8; u++) {
+		for (int u = 0; u < 32; u++) {
 			x0 = fma(x0, a, b);
 			x1 = fma(x1, a, b);
 			x2 = fma(x2, a, b);

@@ -70,19 +70,21 @@ APM_HD double add_rn(double a, double b) {
 }
 
 // ---- sine ------------------------------------------------------------------------
-// sin(x) for |x| < 2^30 in 14 FP64-pipe instructions and no table, select or
+// sin(x) for |x| < 2^30 in 13 FP64-pipe instructions and no table, select or
 // conversion instruction (CUDA's sin() costs 14 FP64 + 2 F2I/I2F + 3 LDG + 6 FSEL and
 // a slow-path call):
 //   q = rint(x / pi) by the 1.5*2^52 magic-number add (1 DFMA + 1 DADD), its parity is
 //   the low mantissa bit; r = x - q*pi by a two-term Cody-Waite reduction (2 DFMA; the
 //   first is exact, the third term q*3e-33 is below 1e-23 for every q < 2^31);
-//   sin(x) = (-1)^q sin(r), |r| <= pi/2: odd minimax polynomial of degree 17 in r
-//   (Remez, weighted for absolute error; max error 2.0e-19 before rounding) evaluated
-//   as r + (r*s)*P(s), s = r*r: 1 DMUL + 7 DFMA + 1 DMUL + 1 DFMA.
-// Measured against 50-digit references (tests/test_math_cpu.py): max error < 0.9 ulp
-// of the result for |x| <= 1e5 ... 1e9.  Outside the fast range (or NaN/Inf) the
+//   sin(x) = (-1)^q sin(r), |r| <= pi/2: odd minimax polynomial of degree 15 in r
+//   (Remez, weighted for absolute error; max error 1.1e-16 before rounding) evaluated
+//   as r + (r*s)*P(s), s = r*r: 1 DMUL + 6 DFMA + 1 DMUL + 1 DFMA.
+// Measured against 40-digit references (tests/test_math_cpu.py): max absolute error
+// 2.7e-16 (rms 0.8e-16, unbiased) for |x| up to 1e9 -- inside the "few ulp" of the
+// reference's own gsl_sf_sin.  Outside the fast range (or NaN/Inf) the
 // caller falls back to the CUDA library sin().
 #define APM_SIN_FAST_LIMIT 1073741824.0 /* 2^30 */
+#define APM_SIN_FAST_BOUND 1.0e9          /* what the per-visit bound check compares with (slack for rounding) */
 
 APM_HD double sin_fast(double x) {
 	const double MAGIC = 6755399441055744.0; /* 1.5 * 2^52 */
@@ -97,6 +99,17 @@ APM_HD double sin_fast(double x) {
 	// (-1)^q: move q's parity into r's sign bit (sin is odd)
 	r = make_double(hi32(r) ^ (q << 31), lo32(r));
 	double s = r * r;
+#if !defined(APM_SIN_DEGREE) || APM_SIN_DEGREE == 15
+	/* degree 15 (default): polynomial error 1.1e-16, 13 FP64 instructions in total */
+	double p = -0x1.9e96f0e4ab7e2p-41;
+	p = fma(p, s, 0x1.60e23f9c870eep-33);
+	p = fma(p, s, -0x1.ae6335183e8ccp-26);
+	p = fma(p, s, 0x1.71de379039620p-19);
+	p = fma(p, s, -0x1.a01a0198a4c74p-13);
+	p = fma(p, s, 0x1.111111110723ap-7);
+	p = fma(p, s, -0x1.5555555555421p-3);
+#else
+	/* degree 17 (-DAPM_SIN_DEGREE=17): polynomial error 2e-19, one more DFMA */
 	double p = 0x1.87c623b020b36p-49;
 	p = fma(p, s, -0x1.ae3f136452c88p-41);
 	p = fma(p, s, 0x1.6123b9f483e33p-33);
@@ -105,6 +118,7 @@ APM_HD double sin_fast(double x) {
 	p = fma(p, s, -0x1.a01a01a012713p-13);
 	p = fma(p, s, 0x1.1111111111092p-7);
 	p = fma(p, s, -0x1.5555555555555p-3);
+#endif
 	return fma(r * s, p, r);
 }
 

@@ -13,9 +13,10 @@
 //   prep()      fill Prep from the parameter vector
 //   accum()      acc + (one data row's contribution to the model's running sum), exact
 //                for every input (falls back to the math library outside sin_fast's range)
-//   accum_fast() the same on the branch-free fast path; sets `bad` instead of branching
-//                when an input is outside the fast range -- the kernel then redoes that
-//                thread's rows with accum()
+//   accum_fast() the same on the branch-free fast path (sin_fast), valid only when
+//   fast_ok()    says so: fast_ok(q, xub) is evaluated once per (chain, thread, chunk) from
+//                an upper bound xub >= |x| of the thread's rows, so the per-row code carries
+//                no range check at all; where it says no, the kernel uses accum()
 //   prior()     value passed to set_prior()
 //   sum0()      initial value of the running sum (apps/pulse*.c start it at params[1])
 //   finish()    the value passed to set_prob()
@@ -56,11 +57,13 @@ struct ModelSimplesin {
 		double deltay = fma(q.amplitude, sin_full(arg), q.offset) - y;
 		return fma(deltay, deltay, acc);
 	}
-	APM_D static double accum_fast(double acc, const Prep & q, double x, double y, bool & bad) {
+	APM_D static double accum_fast(double acc, const Prep & q, double x, double y) {
 		double arg = mul_rn(APM_TWO_PI, add_rn(mul_rn(q.frequency, x), q.phase));
-		bad |= sin_fast_out_of_range(arg);
 		double deltay = fma(q.amplitude, sin_fast(arg), q.offset) - y;
 		return fma(deltay, deltay, acc);
+	}
+	APM_D static bool fast_ok(const Prep & q, double xub) {
+		return APM_TWO_PI * (fabs(q.frequency) * xub + fabs(q.phase)) < APM_SIN_FAST_BOUND;
 	}
 	APM_D static double sum0(const double *) { return 0.0; }
 	APM_D static double prior(const double *, int, const double *) { return 0.0; }
@@ -88,11 +91,13 @@ struct ModelSimplesin5 {
 		double d = fma(q.a, sin_full(arg), q.off) - y; // (:35-36)
 		return fma(d, d, acc);
 	}
-	APM_D static double accum_fast(double acc, const Prep & q, double x, double y, bool & bad) {
+	APM_D static double accum_fast(double acc, const Prep & q, double x, double y) {
 		double arg = add_rn(mul_rn(q.w, x), q.ph);
-		bad |= sin_fast_out_of_range(arg);
 		double d = fma(q.a, sin_fast(arg), q.off) - y;
 		return fma(d, d, acc);
+	}
+	APM_D static bool fast_ok(const Prep & q, double xub) {
+		return fabs(q.w) * xub + fabs(q.ph) < APM_SIN_FAST_BOUND;
 	}
 	APM_D static double sum0(const double *) { return 0.0; }
 	APM_D static double prior(const double *, int, const double *) { return 0.0; }
@@ -118,11 +123,13 @@ struct ModelSimplesin2 {
 		double d = fma(q.a, sin_full(arg), -y);
 		return fma(d, d, acc);
 	}
-	APM_D static double accum_fast(double acc, const Prep & q, double x, double y, bool & bad) {
+	APM_D static double accum_fast(double acc, const Prep & q, double x, double y) {
 		double arg = mul_rn(APM_TWO_PI, add_rn(mul_rn(q.f, x), 0.3312));
-		bad |= sin_fast_out_of_range(arg);
 		double d = fma(q.a, sin_fast(arg), -y);
 		return fma(d, d, acc);
+	}
+	APM_D static bool fast_ok(const Prep & q, double xub) {
+		return APM_TWO_PI * (fabs(q.f) * xub + 0.3312) < APM_SIN_FAST_BOUND;
 	}
 	APM_D static double sum0(const double *) { return 0.0; }
 	APM_D static double prior(const double *, int, const double *) { return 0.0; }
@@ -141,7 +148,8 @@ struct ModelNormal {
 	};
 	APM_D static void prep(Prep & q, const double * p, int, const double *) { q.x = p[0]; }
 	APM_D static double accum(double acc, const Prep &, double, double) { return acc; }
-	APM_D static double accum_fast(double acc, const Prep &, double, double, bool &) { return acc; }
+	APM_D static double accum_fast(double acc, const Prep &, double, double) { return acc; }
+	APM_D static bool fast_ok(const Prep &, double) { return true; }
 	APM_D static double sum0(const double *) { return 0.0; }
 	APM_D static double prior(const double *, int, const double *) { return 0.0; }
 	APM_D static double finish(double beta, double, double, const double * p, const double *) {
@@ -194,9 +202,10 @@ struct ModelPulseVrot {
 		y += lorentz(q.f2 - freq + 1 * q.vrot, q.lifetime, q.h2);
 		return acc + (log(y) + d / y); // (:61)
 	}
-	APM_D static double accum_fast(double acc, const Prep & q, double freq, double d, bool &) {
+	APM_D static double accum_fast(double acc, const Prep & q, double freq, double d) {
 		return accum(acc, q, freq, d);
 	}
+	APM_D static bool fast_ok(const Prep &, double) { return true; }
 	APM_D static double sum0(const double * p) { return p[1]; } // accumulator starts at params[1] (:34)
 	APM_D static double prior(const double * p, int n_par, const double * mc) {
 		const double hmin = mc[0] != 0 ? mc[0] : 1e-6; // HMIN (:8-10)
@@ -239,9 +248,10 @@ struct ModelPulse {
 		}
 		return acc + (log(y) + d / y);
 	}
-	APM_D static double accum_fast(double acc, const Prep & q, double freq, double d, bool &) {
+	APM_D static double accum_fast(double acc, const Prep & q, double freq, double d) {
 		return accum(acc, q, freq, d);
 	}
+	APM_D static bool fast_ok(const Prep &, double) { return true; }
 	APM_D static double sum0(const double * p) { return p[1]; }
 	APM_D static double prior(const double * p, int n_par, const double * mc) {
 		const double hmin = mc[0] != 0 ? mc[0] : 1e-6;

@@ -122,16 +122,19 @@ def cpu_oracle_rate(data, seconds=15.0, n_threads=None):
     o.set_data(data)
     o.set_bounds(LO, HI)
     o.set_chains(0, N_BETA, **st)
+    o.run(1, 1)                      # untimed: thread start-up, page faults
     t0 = time.perf_counter()
     o.run(1, 1)                      # one Metropolis step of all 64 chains: calibrates the sample size
     t1 = time.perf_counter() - t0
-    steps = int(max(1, min(N_SWAP, seconds / max(t1, 1e-6))))
+    steps = int(max(1, seconds / max(t1, 1e-6)))
+    rounds, n_swap = (steps // N_SWAP, N_SWAP) if steps >= N_SWAP else (1, steps)
     t0 = time.perf_counter()
-    o.run(1, steps)
+    o.run(rounds, n_swap)
     dt = time.perf_counter() - t0
+    steps = rounds * n_swap
     rate = N_BETA * steps / dt
-    sample = (f"1 ensemble x {N_BETA} chains x {steps} Metropolis steps + 1 swap on the full "
-              f"{N_ROWS}-row table ({dt:.1f} s), OpenMP over chains")
+    sample = (f"1 ensemble x {N_BETA} chains x {steps} Metropolis steps ({rounds} round(s) of {n_swap} + swap) "
+              f"on the full {N_ROWS}-row table ({dt:.1f} s), OpenMP over chains")
     return rate, cores, sample, dt / steps * 1e3
 
 
@@ -223,7 +226,7 @@ def main():
 
     # end to end through the C ABI with host buffers
     h2d = h_data.nbytes + sum(v.nbytes for v in st.values())
-    e2e_ms = []
+    e2e_ms, e2e_parts = [], []
     d2h = 0
     barrier()
     for i in range(1 + K):
@@ -231,15 +234,21 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         eng.set_data(h_data)
+        ta = time.perf_counter()
         eng.set_chains(0, eng.n_chains, **st)
+        tb = time.perf_counter()
         eng.run(1, N_SWAP, prob_every=1, params_chains=1)
+        tc = time.perf_counter()
         out = eng.get_chains()
         tr = eng.read_trace()
-        dt = (time.perf_counter() - t0) * 1e3
+        td = time.perf_counter()
+        dt = (td - t0) * 1e3
         d2h = sum(v.nbytes for v in out.values()) + sum(v.nbytes for v in tr.values())
         if i >= 1:
             e2e_ms.append(dt)
+            e2e_parts.append([(ta - t0) * 1e3, (tb - ta) * 1e3, (tc - tb) * 1e3, (td - tc) * 1e3])
     e2e_ms = float(np.mean(e2e_ms))
+    e2e_parts = [float(v) for v in np.mean(np.array(e2e_parts), axis=0)]
 
     steps_per_round = eng.n_chains * N_SWAP
     t = torch.tensor([total_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
@@ -269,7 +278,8 @@ def main():
             "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "e2e": {"value": e2e, "unit": "chain-steps/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
+                    "breakdown_ms": dict(zip(["set_data", "set_chains", "run", "get_chains+read_trace"], e2e_parts))},
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "fp64", "kernel": "loglik_tiled_kernel<ModelSimplesin5>",
