@@ -60,6 +60,7 @@ struct apm_gpu {
 	int ll_grid = 0;
 	// data
 	double * d_data = nullptr;
+	size_t data_cap = 0, tr_prob_cap = 0, tr_dl_cap = 0, tr_params_cap = 0;
 	long long n_rows = 0;
 	int n_cols = 0;
 	int n_chunks = 0;
@@ -303,6 +304,22 @@ static void make_plan(const apm_gpu * h, int n_slots, int & tile, int & n_ctiles
 	n_splits = (n_chunks + cps - 1) / cps;
 }
 
+// grow-only device buffers: cudaMalloc/cudaFree cost up to tens of ms, so repeated set_data /
+// run calls reuse what is there and only the padding or the contents are rewritten
+template<class T>
+static cudaError_t ensure_cap(T ** p, size_t * cap, size_t count) {
+	if (count <= *cap && *p != nullptr)
+		return cudaSuccess;
+	if (*p)
+		cudaFree(*p);
+	*p = nullptr;
+	*cap = 0;
+	cudaError_t e = cudaMalloc((void **) p, std::max<size_t>(count, 1) * sizeof(T));
+	if (e == cudaSuccess)
+		*cap = std::max<size_t>(count, 1);
+	return e;
+}
+
 static int ensure_partial(apm_gpu * h, size_t count) {
 	if (count <= h->partial_cap)
 		return APM_OK;
@@ -329,9 +346,6 @@ extern "C" int apm_gpu_set_data(apm_gpu * h, const double * rowmajor, long long 
 		return fail(h, APM_EINVAL, "model reads %d data columns, table has %d", need, n_cols);
 	if (need > 2)
 		return fail(h, APM_EINVAL, "models reading more than 2 columns are not supported yet");
-	if (h->d_data)
-		cudaFree(h->d_data);
-	h->d_data = nullptr;
 	h->n_rows = n_rows;
 	h->n_cols = n_cols;
 	h->n_chunks = 0;
@@ -340,7 +354,10 @@ extern "C" int apm_gpu_set_data(apm_gpu * h, const double * rowmajor, long long 
 		// row-major layout for two columns (tda = 2); wider tables are narrowed on upload
 		h->n_chunks = (int) ((n_rows + LL_CHUNK - 1) / LL_CHUNK);
 		const size_t padded = (size_t) h->n_chunks * LL_CHUNK;
-		CU(dalloc(&h->d_data, padded * 2));
+		CU(ensure_cap(&h->d_data, &h->data_cap, padded * 2));
+		if (padded > (size_t) n_rows) // zero the padding rows of the last chunk
+			CU(cudaMemsetAsync(h->d_data + (size_t) n_rows * 2, 0, (padded - (size_t) n_rows) * 2 * sizeof(double),
+					h->stream));
 		if (n_cols == 2) {
 			CU(cudaMemcpyAsync(h->d_data, rowmajor, (size_t) n_rows * 2 * sizeof(double),
 					cudaMemcpyHostToDevice, h->stream));
@@ -573,11 +590,6 @@ extern "C" int apm_gpu_eval(apm_gpu * h, int n, const double * params, const dou
 
 // ------------------------------------------------------------------ run (tiled path)
 static int setup_trace(apm_gpu * h, long long n_steps, const apm_gpu_trace_cfg * tr) {
-	for (double ** p : { &h->d_tr_prob, &h->d_tr_dl, &h->d_tr_params }) {
-		if (*p)
-			cudaFree(*p);
-		*p = nullptr;
-	}
 	h->tr_prob_rows = h->tr_param_rows = 0;
 	h->tr_dumped = 0;
 	DevState & S = h->S;
@@ -588,17 +600,17 @@ static int setup_trace(apm_gpu * h, long long n_steps, const apm_gpu_trace_cfg *
 		return fail(h, APM_EINVAL, "bad trace configuration");
 	if (S.tr_prob_every > 0) {
 		h->tr_prob_rows = (n_steps + S.tr_prob_every - 1) / S.tr_prob_every;
-		CU(dalloc(&h->d_tr_prob, (size_t) h->tr_prob_rows * h->n_chains));
-		CU(dalloc(&h->d_tr_dl, (size_t) h->tr_prob_rows * h->n_chains));
+		CU(ensure_cap(&h->d_tr_prob, &h->tr_prob_cap, (size_t) h->tr_prob_rows * h->n_chains));
+		CU(ensure_cap(&h->d_tr_dl, &h->tr_dl_cap, (size_t) h->tr_prob_rows * h->n_chains));
+		S.tr_prob = h->d_tr_prob;
+		S.tr_dl = h->d_tr_dl;
 	}
 	h->tr_dumped = S.tr_params_chains == 2 ? h->n_chains : (S.tr_params_chains == 1 ? h->cfg.n_ensembles : 0);
 	if (h->tr_dumped > 0) {
 		h->tr_param_rows = n_steps;
-		CU(dalloc(&h->d_tr_params, (size_t) n_steps * h->tr_dumped * h->cfg.n_par));
+		CU(ensure_cap(&h->d_tr_params, &h->tr_params_cap, (size_t) n_steps * h->tr_dumped * h->cfg.n_par));
+		S.tr_params = h->d_tr_params;
 	}
-	S.tr_prob = h->d_tr_prob;
-	S.tr_dl = h->d_tr_dl;
-	S.tr_params = h->d_tr_params;
 	S.tr_dumped = h->tr_dumped;
 	return APM_OK;
 }
@@ -667,13 +679,13 @@ extern "C" int apm_gpu_read_trace(apm_gpu * h, double * prob, double * dl, doubl
 	if (!h)
 		return APM_EINVAL;
 	CU(cudaSetDevice(h->cfg.device));
-	if (prob && h->d_tr_prob)
+	if (prob && h->d_tr_prob && h->tr_prob_rows > 0)
 		CU(cudaMemcpy(prob, h->d_tr_prob, (size_t) h->tr_prob_rows * h->n_chains * sizeof(double),
 				cudaMemcpyDeviceToHost));
-	if (dl && h->d_tr_dl)
+	if (dl && h->d_tr_dl && h->tr_prob_rows > 0)
 		CU(cudaMemcpy(dl, h->d_tr_dl, (size_t) h->tr_prob_rows * h->n_chains * sizeof(double),
 				cudaMemcpyDeviceToHost));
-	if (params && h->d_tr_params)
+	if (params && h->d_tr_params && h->tr_param_rows > 0)
 		CU(cudaMemcpy(params, h->d_tr_params,
 				(size_t) h->tr_param_rows * h->tr_dumped * h->cfg.n_par * sizeof(double),
 				cudaMemcpyDeviceToHost));
