@@ -87,6 +87,11 @@ struct DevState {
 	long long progress_cap;
 	unsigned long long * progress_n;
 	int * n_active;    // chains still calibrating (device counter)
+	// compacted list of the chains whose proposal is pending (calibration: the likelihood
+	// kernel only visits these).  Two buffers / counters used alternately: the control kernel
+	// of step s fills [w] for the next likelihood launch and clears [1 - w].
+	int * act_idx;     // [2][n_chains]
+	int * act_n;       // [2]
 	// trace of the current run
 	double * tr_prob, *tr_dl, *tr_params;
 	int tr_prob_every, tr_params_chains, tr_dumped;

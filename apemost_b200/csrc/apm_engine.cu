@@ -65,9 +65,10 @@ struct apm_gpu {
 	int n_cols = 0;
 	int n_chunks = 0;
 	bool have_data = false, have_bounds = false;
-	// plan for n_chains slots
-	int plan_tile = 0, plan_ctiles = 0, plan_splits = 0, plan_cps = 0;
+	// row-split plan for n_chains slots
+	int plan_splits = 0, plan_cps = 0;
 	size_t partial_cap = 0;
+	unsigned long long * d_xabsmax = nullptr; // bits of max |x| over the table
 	// trace (device)
 	double * d_tr_prob = nullptr, *d_tr_dl = nullptr, *d_tr_params = nullptr;
 	long long tr_prob_rows = 0, tr_param_rows = 0;
@@ -229,7 +230,8 @@ extern "C" int apm_gpu_create(apm_gpu ** out, const apm_gpu_config * cfg) {
 		A(S.pmin, np); A(S.pmax, np); A(S.pend, n);
 		A(S.stat_n, n); A(S.stat_sum_dl, n); A(S.stat_sum_p, nv); A(S.stat_sum_p2, nv);
 		A(S.cal, n); A(S.progress_n, 1); A(S.n_active, 1);
-		A(h->d_select, n); A(h->d_shard_sum, n);
+		A(h->d_select, n); A(h->d_shard_sum, n); A(h->d_xabsmax, 1);
+		A(S.act_idx, 2 * n); A(S.act_n, 2);
 #undef A
 		if (e != cudaSuccess) {
 			rc = fail(nullptr, APM_ENOMEM, "device allocation failed: %s", cudaGetErrorString(e));
@@ -268,8 +270,8 @@ extern "C" int apm_gpu_destroy(apm_gpu * h) {
 	void * ptrs[] = { S.params, S.params_best, S.steps, S.prop, S.prob, S.prior, S.prob_best, S.beta,
 			S.accept, S.reject, S.pacc, S.prej, S.n_iter, S.swapcount, S.rng_ctr, S.swap_round, S.pmin,
 			S.pmax, S.pend, S.partial, S.stat_n, S.stat_sum_dl, S.stat_sum_p, S.stat_sum_p2, S.cal,
-			S.progress, S.progress_n, S.n_active, h->d_select, h->d_shard_sum, h->d_data, h->d_tr_prob,
-			h->d_tr_dl, h->d_tr_params };
+			S.progress, S.progress_n, S.n_active, S.act_idx, S.act_n, h->d_select, h->d_shard_sum,
+			h->d_xabsmax, h->d_data, h->d_tr_prob, h->d_tr_dl, h->d_tr_params };
 	for (void * p : ptrs)
 		if (p)
 			cudaFree(p);
@@ -284,24 +286,38 @@ extern "C" int apm_gpu_destroy(apm_gpu * h) {
 }
 
 // ------------------------------------------------------------------ launch plan
-static void make_plan(const apm_gpu * h, int n_slots, int & tile, int & n_ctiles, int & n_splits,
-		int & cps) {
+// How many row splits for n_slots chains in tiles of `tile`: work items = chain tiles x
+// splits are dealt round-robin to the persistent grid, so pick the split count whose last
+// round is fullest (all items of a plan cost the same), charging a small per-item overhead
+// (parameter load + fold) so that items do not get needlessly small.
+static void make_plan(const apm_gpu * h, int n_slots, int tile, int & n_splits, int & cps) {
 	const int n_chunks = std::max(h->n_chunks, 1);
-	tile = std::min(16, (int) LL_MAX_TILE);
-	if (const char * t = getenv("APM_TILE")) // kernel-sweep override
-		tile = std::max(1, std::min(atoi(t), (int) LL_MAX_TILE));
-	// few chains: smaller tiles so that the chain axis alone gives some parallelism
-	while (tile > 1 && (n_slots + tile - 1) / tile < 4 && n_slots > 1)
-		tile /= 2;
-	n_ctiles = (n_slots + tile - 1) / tile;
-	long long per_cta = 40;
-	if (const char * t = getenv("APM_ITEMS_PER_CTA"))
-		per_cta = std::max(1, atoi(t));
-	long long target_items = per_cta * std::max(h->ll_grid, 1);
-	long long want = (target_items + n_ctiles - 1) / n_ctiles;
-	n_splits = (int) std::min<long long>(std::max<long long>(want, 1), n_chunks);
-	cps = (n_chunks + n_splits - 1) / n_splits;
-	n_splits = (n_chunks + cps - 1) / cps;
+	const long long grid = std::max(h->ll_grid, 1);
+	const long long n_ctiles = std::max((n_slots + tile - 1) / tile, 1);
+	if (const char * t = getenv("APM_SPLITS")) { // kernel-sweep override
+		n_splits = std::max(1, std::min(atoi(t), n_chunks));
+		cps = (n_chunks + n_splits - 1) / n_splits;
+		n_splits = (n_chunks + cps - 1) / cps;
+		return;
+	}
+	const double item_overhead = 0.15; // in units of one chunk's compute time
+	double best = 1e300;
+	n_splits = 1;
+	cps = n_chunks;
+	for (int s = 1; s <= std::min(n_chunks, 512); s++) {
+		const int c = (n_chunks + s - 1) / s;
+		const int s_eff = (n_chunks + c - 1) / c;
+		if (s_eff != s)
+			continue;
+		const long long items = n_ctiles * s_eff;
+		const long long rounds = (items + grid - 1) / grid;
+		const double makespan = rounds * (c + item_overhead);
+		if (makespan < best * (1 - 1e-9)) {
+			best = makespan;
+			n_splits = s_eff;
+			cps = c;
+		}
+	}
 }
 
 // grow-only device buffers: cudaMalloc/cudaFree cost up to tens of ms, so repeated set_data /
@@ -329,6 +345,23 @@ static int ensure_partial(apm_gpu * h, size_t count) {
 	h->partial_cap = 0;
 	CU(dalloc(&h->S.partial, count));
 	h->partial_cap = count;
+	return APM_OK;
+}
+
+// (re)plan the row splits for n_slots pending chains; the partial-sum buffer is laid out
+// [n_chains][n_splits] whatever subset is evaluated
+template<class M> static int model_tile_t(apm_gpu *) { return M::LL_C; }
+static int model_tile(apm_gpu * h) { DISPATCH(h->cfg.model_id, model_tile_t, h) }
+
+static int replan(apm_gpu * h, int n_slots) {
+	const int tile = model_tile(h);
+	if (tile < 0)
+		return tile;
+	make_plan(h, std::max(n_slots, 1), tile, h->plan_splits, h->plan_cps);
+	int rc = ensure_partial(h, (size_t) h->n_chains * h->plan_splits);
+	if (rc != APM_OK)
+		return rc;
+	h->S.n_splits = h->plan_splits;
 	return APM_OK;
 }
 
@@ -365,13 +398,14 @@ extern "C" int apm_gpu_set_data(apm_gpu * h, const double * rowmajor, long long 
 			CU(cudaMemcpy2DAsync(h->d_data, 2 * sizeof(double), rowmajor, (size_t) n_cols * sizeof(double),
 					2 * sizeof(double), (size_t) n_rows, cudaMemcpyHostToDevice, h->stream));
 		}
+		CU(cudaMemsetAsync(h->d_xabsmax, 0, sizeof(unsigned long long), h->stream));
+		absmax_col0_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_data, n_rows, h->d_xabsmax);
+		h->launches++;
 		CU(cudaStreamSynchronize(h->stream));
 	}
-	make_plan(h, h->n_chains, h->plan_tile, h->plan_ctiles, h->plan_splits, h->plan_cps);
-	int rc = ensure_partial(h, (size_t) h->n_chains * h->plan_splits);
+	int rc = replan(h, h->n_chains);
 	if (rc != APM_OK)
 		return rc;
-	h->S.n_splits = h->plan_splits;
 	h->have_data = true;
 	return APM_OK;
 }
@@ -447,27 +481,31 @@ static cudaEvent_t next_event(apm_gpu * h) {
 constexpr size_t MAX_TIMED_LAUNCHES = 8192;
 
 template<class M>
-static int launch_loglik(apm_gpu * h, const double * prop, const int * pend, int n_slots, int tile,
-		int n_ctiles, int n_splits, int cps, double * partial, bool timed) {
+static int launch_loglik(apm_gpu * h, const double * prop, const int * act_idx, const int * act_n,
+		int n_slots, int n_upper, int n_splits, int cps, double * partial, bool timed) {
+	// n_slots = rows of prop / partial; n_upper = upper bound of the number of slots evaluated
+	// (= n_slots without an active list) -- it only sizes the grid
 	if (!M::HAS_DATA)
 		return APM_OK;
 	LLArgs a;
 	a.data = h->d_data;
 	a.n_rows = h->n_rows;
 	a.prop = prop;
-	a.pend = pend;
+	a.act_idx = act_idx;
+	a.act_n = act_n;
 	a.n_slots = n_slots;
 	a.n_par = h->cfg.n_par;
-	a.tile = tile;
-	a.n_ctiles = n_ctiles;
 	a.n_splits = n_splits;
 	a.chunks_per_split = cps;
 	a.n_chunks = h->n_chunks;
+	a.xabsmax = reinterpret_cast<const double *>(h->d_xabsmax);
 	a.partial = partial;
 	for (int i = 0; i < 4; i++)
 		a.model_const[i] = h->cfg.model_const[i];
-	const long long n_items = (long long) n_ctiles * n_splits;
-	const int grid = (int) std::min<long long>(h->ll_grid, n_items);
+	const long long n_items = (long long) ((n_upper + M::LL_C - 1) / M::LL_C) * n_splits;
+	if ((long long) ((n_slots + M::LL_C - 1) / M::LL_C) * n_splits >= (1ll << 31))
+		return fail(h, APM_EINVAL, "too many work items");
+	const int grid = (int) std::max<long long>(1, std::min<long long>(h->ll_grid, n_items));
 	timed = timed && h->ev_used + 2 <= 2 * MAX_TIMED_LAUNCHES;
 	if (timed)
 		cudaEventRecord(next_event(h), h->stream);
@@ -490,10 +528,12 @@ __global__ void fold_splits_kernel(const double * partial, int n_splits, int n, 
 }
 
 template<class M>
-static int step_likelihood(apm_gpu * h, bool timed) {
+static int step_likelihood(apm_gpu * h, bool timed, int act_w = -1, int n_upper = -1) {
 	// likelihood of every pending proposal -> S.partial (or, data-sharded, the all-reduced
-	// per-chain sums in d_shard_sum)
-	int rc = launch_loglik<M>(h, h->S.prop, h->S.pend, h->n_chains, h->plan_tile, h->plan_ctiles,
+	// per-chain sums in d_shard_sum).  act_w >= 0: only the chains of active list act_w.
+	const int * idx = act_w >= 0 ? h->S.act_idx + (size_t) act_w * h->n_chains : nullptr;
+	const int * cnt = act_w >= 0 ? h->S.act_n + act_w : nullptr;
+	int rc = launch_loglik<M>(h, h->S.prop, idx, cnt, h->n_chains, n_upper >= 0 ? n_upper : h->n_chains,
 			h->plan_splits, h->plan_cps, h->S.partial, timed);
 	if (rc != APM_OK)
 		return rc;
@@ -525,8 +565,8 @@ static int eval_t(apm_gpu * h, int n, const double * params, const double * beta
 		double * prior_out) {
 	const int np = h->cfg.n_par;
 	double * d_params = nullptr, *d_beta = nullptr, *d_prob = nullptr, *d_prior = nullptr, *d_partial = nullptr;
-	int tile = 1, n_ctiles = 1, n_splits = 1, cps = 1;
-	make_plan(h, n, tile, n_ctiles, n_splits, cps);
+	int n_splits = 1, cps = 1;
+	make_plan(h, n, M::LL_C, n_splits, cps);
 	int rc = APM_OK;
 	cudaError_t e = dalloc(&d_params, (size_t) n * np);
 	if (e == cudaSuccess) e = dalloc(&d_beta, (size_t) n);
@@ -541,7 +581,7 @@ static int eval_t(apm_gpu * h, int n, const double * params, const double * beta
 		h->ev_used = 0;
 		cudaEvent_t t0 = next_event(h), t1 = next_event(h);
 		cudaEventRecord(t0, h->stream);
-		rc = launch_loglik<M>(h, d_params, nullptr, n, tile, n_ctiles, n_splits, cps, d_partial, true);
+		rc = launch_loglik<M>(h, d_params, nullptr, nullptr, n, n, n_splits, cps, d_partial, true);
 		const double * mc = h->cfg.model_const;
 		eval_finish_kernel<M><<<(n + 127) / 128, 128, 0, h->stream>>>(n, np, d_params, d_beta, d_partial,
 				n_splits, d_prob, d_prior, mc[0], mc[1], mc[2], mc[3]);
@@ -620,6 +660,9 @@ static int run_tiled_t(apm_gpu * h, long long n_rounds, int n_swap) {
 	const long long total = n_rounds * n_swap;
 	AdvArgs a;
 	memset(&a, 0, sizeof(a));
+	int rc0 = replan(h, h->n_chains);
+	if (rc0 != APM_OK)
+		return rc0;
 	h->ev_used = 0;
 	cudaEvent_t t0 = next_event(h), t1 = next_event(h);
 	// ev[0], ev[1] are the run brackets; pairs from ev[2] on are likelihood launches
@@ -698,7 +741,7 @@ extern "C" int apm_gpu_read_trace(apm_gpu * h, double * prob, double * dl, doubl
 
 // ------------------------------------------------------------------ calibrate
 template<class M>
-static int calibrate_t(apm_gpu * h, const apm_gpu_calib_cfg * cfg, int * status) {
+static int calibrate_t(apm_gpu * h, const apm_gpu_calib_cfg * cfg, int * status, int n_selected) {
 	AdvArgs a;
 	memset(&a, 0, sizeof(a));
 	a.cal.burn_in_iterations = cfg->burn_in_iterations;
@@ -714,17 +757,26 @@ static int calibrate_t(apm_gpu * h, const apm_gpu_calib_cfg * cfg, int * status)
 	h->ev_used = 0;
 	cudaEvent_t t0 = next_event(h), t1 = next_event(h);
 	CU(cudaEventRecord(t0, h->stream));
+	// the likelihood kernel walks a compacted list of the chains still calibrating; the
+	// control kernel of step s fills list (s + 1) & 1 and clears list s & 1
+	CU(cudaMemsetAsync(h->S.act_n, 0, 2 * sizeof(int), h->stream));
 	a.flags = ADV_CALIB_BEGIN;
+	a.act_w = 0;
 	advance_kernel<M><<<h->cfg.n_ensembles, ADV_THREADS, 0, h->stream>>>(state_for_advance(h), a);
 	h->launches++;
-	int active = 1;
+	int active = n_selected;
 	const int block = 200;
+	long long step = 0;
 	while (active > 0) {
-		for (int i = 0; i < block; i++) {
-			int rc = step_likelihood<M>(h, true);
+		int rc = replan(h, active); // the row splits follow the number of chains left
+		if (rc != APM_OK)
+			return rc;
+		for (int i = 0; i < block; i++, step++) {
+			rc = step_likelihood<M>(h, true, (int) (step & 1), active);
 			if (rc != APM_OK)
 				return rc;
 			a.flags = ADV_FINALIZE | ADV_CALIB;
+			a.act_w = (int) ((step + 1) & 1);
 			advance_kernel<M><<<h->cfg.n_ensembles, ADV_THREADS, 0, h->stream>>>(state_for_advance(h), a);
 			h->launches++;
 		}
@@ -783,7 +835,10 @@ extern "C" int apm_gpu_calibrate(apm_gpu * h, const unsigned char * select, cons
 		CU(dalloc(&h->S.progress, (size_t) progress_capacity));
 		h->S.progress_cap = progress_capacity;
 	}
-	auto go = [&]() -> int { DISPATCH(h->cfg.model_id, calibrate_t, h, cfg, status) };
+	int n_selected = 0;
+	for (unsigned char c : sel)
+		n_selected += c != 0;
+	auto go = [&]() -> int { DISPATCH(h->cfg.model_id, calibrate_t, h, cfg, status, n_selected) };
 	int rc = go();
 	if (rc != APM_OK && rc != APM_ECALIB)
 		return rc;

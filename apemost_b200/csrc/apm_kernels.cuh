@@ -72,197 +72,225 @@ __device__ __forceinline__ double warp_sum(double v) {
 #ifndef APM_LL_RPT
 #define APM_LL_RPT 16
 #endif
-#ifndef APM_LL_MINBLOCKS
-#define APM_LL_MINBLOCKS 1
-#endif
 #ifndef APM_LL_STAGES
-#define APM_LL_STAGES 2
+#define APM_LL_STAGES 3
 #endif
-#ifndef APM_LL_CPV
-#define APM_LL_CPV 1
+#ifndef APM_LL_UNROLL
+#define APM_LL_UNROLL 4
 #endif
 constexpr int LL_THREADS = APM_LL_THREADS;
 constexpr int LL_WARPS = LL_THREADS / 32;
-constexpr int LL_RPT = APM_LL_RPT;                       // rows per thread per chunk (held in registers)
-constexpr int LL_CHUNK = LL_THREADS * LL_RPT;   // 2048 rows = 32 KB per stage
+constexpr int LL_RPT = APM_LL_RPT;              // rows per thread per chunk
+constexpr int LL_CHUNK = LL_THREADS * LL_RPT;   // rows per TMA chunk (4096 rows = 64 KB)
 constexpr int LL_STAGES = APM_LL_STAGES;
-#ifndef APM_LL_MAX_TILE
-#define APM_LL_MAX_TILE 16
-#endif
-constexpr int LL_MAX_TILE = APM_LL_MAX_TILE;    // chains per work item (upper bound)
-constexpr int LL_CPV = APM_LL_CPV;              // chains evaluated together in one visit
+constexpr int LL_UNROLL = APM_LL_UNROLL;          // inner iterations unrolled together
+constexpr int LL_MAX_C = 8;                     // upper bound of M::LL_C (chains per work item)
 
 struct LLArgs {
 	const double * data;    // [n_rows_padded][2], padded with zeros to a multiple of LL_CHUNK
 	long long n_rows;
 	const double * prop;    // [n_slots][n_par] parameter vectors to evaluate
-	const int * pend;       // optional [n_slots]: skip slots with pend < 0 (NULL = all active)
+	const int * act_idx;    // optional compacted list of the slots to evaluate (NULL = all n_slots)
+	const int * act_n;      // device-side length of act_idx (read only when act_idx != NULL)
 	int n_slots;
 	int n_par;
-	int tile;               // chains per work item
-	int n_ctiles;
 	int n_splits;
 	int chunks_per_split;
 	int n_chunks;
+	const double * xabsmax; // device scalar: max |x| over the table (bound for the fast sine)
 	double * partial;       // [n_slots][n_splits]
 	double model_const[4];
 };
 
-// One visit: NC chains of the tile against the thread's LL_RPT register-held rows.  All
-// NC x LL_RPT row evaluations are independent, so the compiler interleaves them and the fp64
-// pipe sees long runs of back-to-back independent instructions; the per-visit costs (constant
-// loads, accumulator update, loop control, pipeline drain at the branch) are paid once per
-// NC x LL_RPT evaluations.  rows[] is only ever indexed by unrolled constants (registers).
-template<class M, int NC>
-__device__ __forceinline__ void ll_visit(const double2 (&rows)[LL_RPT], const double * sparams,
-		double * sacc, const int c, const int n_par, const double * mc, const bool full_chunk,
-		const int n_valid, const int tid, const double xub) {
-	typename M::Prep q[NC];
-	double acc[NC][2];
-#pragma unroll
-	for (int u = 0; u < NC; u++) {
-		M::prep(q[u], sparams + (c + u) * APM_MAX_PAR, n_par, mc);
-		acc[u][0] = 0.0;
-		acc[u][1] = 0.0;
-	}
-	// branch-free fast path when the model says every row of this thread is inside the fast
-	// range for these chains (one bound check per visit, none per row); otherwise -- and for
-	// every thread of a ragged last chunk -- the exact, masked path
-	bool fast = full_chunk;
-#pragma unroll
-	for (int u = 0; u < NC; u++)
-		fast = fast && M::fast_ok(q[u], xub);
-	if (fast) {
-#pragma unroll
-		for (int j = 0; j < LL_RPT; j += 2) {
-#pragma unroll
-			for (int u = 0; u < NC; u++) {
-				acc[u][0] = M::accum_fast(acc[u][0], q[u], rows[j].x, rows[j].y);
-				acc[u][1] = M::accum_fast(acc[u][1], q[u], rows[j + 1].x, rows[j + 1].y);
-			}
-		}
-	} else {
-#pragma unroll
-		for (int u = 0; u < NC; u++) {
-			acc[u][0] = 0.0;
-			acc[u][1] = 0.0;
-#pragma unroll
-			for (int j = 0; j < LL_RPT; j++)
-				if (j * LL_THREADS + tid < n_valid)
-					acc[u][0] = M::accum(acc[u][0], q[u], rows[j].x, rows[j].y);
-		}
-	}
-#pragma unroll
-	for (int u = 0; u < NC; u++)
-		sacc[(c + u) * LL_THREADS + tid] += acc[u][0] + acc[u][1];
+__device__ __forceinline__ void mbar_arrive(uint64_t * bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
+// Work item = (tile of C = M::LL_C chains) x (row split).  Each thread keeps the C chains'
+// constants (M::Prep) and C x U fp64 accumulators in registers for the whole item and walks
+// its rows of every staged chunk: one conflict-free LDS.128 per row feeds C row evaluations,
+// so the inner loop is a steady stream of C x U independent dependency chains on the fp64
+// pipe with no per-chain loop, branch, shared-memory accumulator or barrier inside it.
+//
+// The rows stream through an LL_STAGES-deep shared-memory ring filled by the TMA engine
+// (cp.async.bulk, completion on a `full` mbarrier with expect_tx).  A stage is handed back
+// through an `empty` mbarrier on which every warp arrives once it has read its rows, so no
+// CTA-wide barrier exists in the chunk loop; the ring runs ahead across work-item boundaries
+// (the producer walks the CTA's item list on its own), so the first chunk of the next item
+// is already resident when the fold of the current one ends.
 template<class M>
-__global__ void __launch_bounds__(LL_THREADS, APM_LL_MINBLOCKS) loglik_tiled_kernel(const LLArgs a) {
+__global__ void __launch_bounds__(LL_THREADS, 1) loglik_tiled_kernel(const LLArgs a) {
+	constexpr int C = M::LL_C, U = M::LL_U;
+	static_assert(C <= LL_MAX_C && LL_RPT % U == 0, "tile shape");
 	extern __shared__ __align__(128) unsigned char ll_smem[];
-	double2 * sdata = reinterpret_cast<double2 *>(ll_smem);                      // [STAGES][CHUNK]
-	double * sparams = reinterpret_cast<double *>(sdata + LL_STAGES * LL_CHUNK); // [MAX_TILE][MAX_PAR]
-	double * sacc = sparams + LL_MAX_TILE * APM_MAX_PAR;                         // [MAX_TILE][THREADS]
-	int * sact = reinterpret_cast<int *>(sacc + LL_MAX_TILE * LL_THREADS);       // [MAX_TILE]
-	uint64_t * full = reinterpret_cast<uint64_t *>(sact + LL_MAX_TILE);          // [STAGES]
+	double2 * sdata = reinterpret_cast<double2 *>(ll_smem);                  // [STAGES][CHUNK]
+	double * sacc = reinterpret_cast<double *>(sdata + LL_STAGES * LL_CHUNK); // [MAX_C][THREADS]
+	uint64_t * full = reinterpret_cast<uint64_t *>(sacc + LL_MAX_C * LL_THREADS); // [STAGES]
+	uint64_t * empty = full + LL_STAGES;                                     // [STAGES]
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int n_par = a.n_par;
 	if (tid == 0) {
-		for (int s = 0; s < LL_STAGES; s++)
+		for (int s = 0; s < LL_STAGES; s++) {
 			mbar_init(&full[s], 1);
+			mbar_init(&empty[s], LL_WARPS);
+		}
 		mbar_fence_init();
 	}
 	__syncthreads();
 
-	const long long n_items = (long long) a.n_ctiles * a.n_splits;
-	uint32_t it = 0; // chunks consumed so far by this CTA: stage = it % STAGES, parity = (it / STAGES) & 1
+	const int n_act = a.act_idx ? *a.act_n : a.n_slots;
+	const int n_ctiles = (n_act + C - 1) / C;
+	const int n_items = n_ctiles * a.n_splits; // < 2^31, checked by the host
+	const double xub = *a.xabsmax;
 	constexpr uint32_t CHUNK_BYTES = LL_CHUNK * sizeof(double2);
 
-	for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-		const int ctile = (int) (item % a.n_ctiles); // chain tile fastest: neighbours share rows in L2
-		const int split = (int) (item / a.n_ctiles);
-		const int c0 = ctile * a.tile;
-		const int nT = min(a.tile, a.n_slots - c0);
+	// ---- producer (thread 0): walks this CTA's items chunk by chunk, LL_STAGES - 1 ahead
+	int p_item = blockIdx.x;
+	int p_k = 0;
+	uint32_t p_n = 0;
+	auto produce = [&]() {
+		if (p_item >= n_items)
+			return;
+		const int k0 = (p_item / n_ctiles) * a.chunks_per_split;
+		const int nk = min(a.chunks_per_split, a.n_chunks - k0);
+		const uint32_t st = p_n % LL_STAGES;
+		if (p_n >= LL_STAGES) // chunk p_n - LL_STAGES must have been read by every warp
+			mbar_wait(&empty[st], ((p_n / LL_STAGES) + 1u) & 1u);
+		mbar_arrive_expect_tx(&full[st], CHUNK_BYTES);
+		tma_bulk_g2s(sdata + st * LL_CHUNK, a.data + (size_t) (k0 + p_k) * LL_CHUNK * 2, CHUNK_BYTES,
+				&full[st]);
+		p_n++;
+		if (++p_k == nk) {
+			p_k = 0;
+			p_item += gridDim.x;
+		}
+	};
+	if (tid == 0)
+		for (int s = 0; s < LL_STAGES - 1; s++)
+			produce();
+
+	uint32_t it = 0; // chunks consumed so far: stage = it % STAGES, parity = (it / STAGES) & 1
+	for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+		const int split = item / n_ctiles;
+		const int ctile = item - split * n_ctiles; // chain tile fastest: neighbours share rows in L2
+		const int c0 = ctile * C;
 		const int k0 = split * a.chunks_per_split;
 		const int nk = min(a.chunks_per_split, a.n_chunks - k0);
 
-		// stage the tile's parameter vectors, clear the accumulators.  Every thread owns one
-		// fp64 accumulator per chain of the tile in shared memory (sacc[c][tid], conflict-free):
-		// a chain visit costs one LDS + one STS instead of a 5-stage shuffle reduction, and the
-		// cross-thread reduction happens once per work item, in a fixed order.
-		for (int i = tid; i < nT * n_par; i += LL_THREADS)
-			sparams[(i / n_par) * APM_MAX_PAR + (i % n_par)] = a.prop[(size_t) c0 * n_par + i];
-		for (int c = 0; c < nT; c++)
-			sacc[c * LL_THREADS + tid] = 0.0;
-		if (tid < nT)
-			sact[tid] = a.pend ? (a.pend[c0 + tid] >= 0) : 1;
-		// prologue of the TMA ring
-		if (tid == 0) {
-			for (int s = 0; s < LL_STAGES && s < nk; s++) {
-				const uint32_t st = (it + s) % LL_STAGES;
-				mbar_arrive_expect_tx(&full[st], CHUNK_BYTES);
-				tma_bulk_g2s(sdata + st * LL_CHUNK, a.data + (size_t) (k0 + s) * LL_CHUNK * 2, CHUNK_BYTES,
-						&full[st]);
-			}
+		typename M::Prep q[C];
+		int gid[C];
+		double acc[C][U];
+		bool fast = true;
+#pragma unroll
+		for (int c = 0; c < C; c++) {
+			const int slot = c0 + c;
+			gid[c] = slot < n_act ? (a.act_idx ? a.act_idx[slot] : slot) : -1;
+			// slots past the end of the list evaluate the tile's first chain again (never written)
+			const int src = gid[c] >= 0 ? gid[c] : gid[0];
+			M::prep(q[c], a.prop + (size_t) src * n_par, n_par, a.model_const);
+			fast = fast && M::fast_ok(q[c], xub);
+#pragma unroll
+			for (int u = 0; u < U; u++)
+				acc[c][u] = 0.0;
 		}
-		__syncthreads();
 
 		for (int k = 0; k < nk; k++, it++) {
 			const uint32_t st = it % LL_STAGES;
 			mbar_wait(&full[st], (it / LL_STAGES) & 1u);
-			double2 rows[LL_RPT];
-#pragma unroll
-			for (int j = 0; j < LL_RPT; j++)
-				rows[j] = sdata[st * LL_CHUNK + j * LL_THREADS + tid];
-			__syncthreads(); // every thread holds its rows: the stage can be refilled
-			if (tid == 0 && k + LL_STAGES < nk) {
-				mbar_arrive_expect_tx(&full[st], CHUNK_BYTES);
-				tma_bulk_g2s(sdata + st * LL_CHUNK, a.data + (size_t) (k0 + k + LL_STAGES) * LL_CHUNK * 2,
-						CHUNK_BYTES, &full[st]);
-			}
+			if (tid == 0)
+				produce(); // chunk it + STAGES - 1 goes where chunk it - 1 was
+			const double2 * srow = sdata + st * LL_CHUNK + tid;
 			const long long row0 = (long long) (k0 + k) * LL_CHUNK;
 			const int n_valid = (int) min((long long) LL_CHUNK, a.n_rows - row0);
-			const bool full_chunk = n_valid == LL_CHUNK;
-			// upper bound of |x| over this thread's rows: max of the high words (monotonic for
-			// |doubles|; Inf/NaN give the largest), rounded up to the next high word
-			int xhi = 0;
+			if (fast && n_valid == LL_CHUNK) {
+				// branch-free path: every row of the chunk is real and inside the fast range
+#pragma unroll LL_UNROLL
+				for (int j = 0; j < LL_RPT; j += U) {
+					double2 r[U];
 #pragma unroll
-			for (int j = 0; j < LL_RPT; j++)
-				xhi = max(xhi, hi32(rows[j].x) & 0x7fffffff);
-			const double xub = make_double(xhi + 1, 0);
-			int c = 0;
-			for (; c + LL_CPV <= nT; c += LL_CPV) {
-				bool any = false;
+					for (int u = 0; u < U; u++)
+						r[u] = srow[(j + u) * LL_THREADS];
 #pragma unroll
-				for (int u = 0; u < LL_CPV; u++)
-					any |= sact[c + u] != 0;
-				if (any)
-					ll_visit<M, LL_CPV>(rows, sparams, sacc, c, n_par, a.model_const, full_chunk, n_valid, tid, xub);
+					for (int c = 0; c < C; c++)
+#pragma unroll
+						for (int u = 0; u < U; u++)
+							acc[c][u] = M::accum_fast(acc[c][u], q[c], r[u].x, r[u].y);
+				}
+			} else if (fast) {
+				// ragged last chunk: padding rows masked out
+#pragma unroll 1
+				for (int j = 0; j < LL_RPT; j++) {
+					const double2 r = srow[j * LL_THREADS];
+					if (j * LL_THREADS + tid < n_valid) {
+#pragma unroll
+						for (int c = 0; c < C; c++)
+							acc[c][0] = M::accum_fast(acc[c][0], q[c], r.x, r.y);
+					}
+				}
+			} else {
+				// some chain of the tile is outside the fast sine's range: exact path
+#pragma unroll 1
+				for (int j = 0; j < LL_RPT; j++) {
+					const double2 r = srow[j * LL_THREADS];
+					if (j * LL_THREADS + tid < n_valid) {
+#pragma unroll
+						for (int c = 0; c < C; c++)
+							acc[c][0] = M::accum(acc[c][0], q[c], r.x, r.y);
+					}
+				}
 			}
-			for (; c < nT; c++)
-				if (sact[c])
-					ll_visit<M, 1>(rows, sparams, sacc, c, n_par, a.model_const, full_chunk, n_valid, tid, xub);
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(&empty[st]);
+		}
+
+		// fold the item in a fixed order: a thread's U accumulators in index order, then per
+		// chain the 8 strided thread slots of a lane in index order, then a butterfly
+#pragma unroll
+		for (int c = 0; c < C; c++) {
+			double v = acc[c][0];
+#pragma unroll
+			for (int u = 1; u < U; u++)
+				v += acc[c][u];
+			sacc[c * LL_THREADS + tid] = v;
 		}
 		__syncthreads();
-		// fold the tile: warp w reduces chains w, w + WARPS, ...; lane l first adds its 8 strided
-		// thread slots in index order, then a butterfly -- the same order every run
-		for (int c = warp; c < nT; c += LL_WARPS) {
+		for (int c = warp; c < C; c += LL_WARPS) {
 			double v = 0.0;
 #pragma unroll
-			for (int k = 0; k < LL_THREADS / 32; k++)
-				v += sacc[c * LL_THREADS + k * 32 + lane];
+			for (int w = 0; w < LL_WARPS; w++)
+				v += sacc[c * LL_THREADS + w * 32 + lane];
 			v = warp_sum(v);
-			if (lane == 0)
-				a.partial[(size_t) (c0 + c) * a.n_splits + split] = v;
+			const int g = c0 + c < n_act ? (a.act_idx ? a.act_idx[c0 + c] : c0 + c) : -1;
+			if (lane == 0 && g >= 0)
+				a.partial[(size_t) g * a.n_splits + split] = v;
 		}
 		__syncthreads();
 	}
 }
 
 constexpr size_t LL_SMEM_BYTES = sizeof(double2) * LL_STAGES * LL_CHUNK
-		+ sizeof(double) * LL_MAX_TILE * APM_MAX_PAR + sizeof(double) * LL_MAX_TILE * LL_THREADS
-		+ sizeof(int) * LL_MAX_TILE + sizeof(uint64_t) * LL_STAGES;
+		+ sizeof(double) * LL_MAX_C * LL_THREADS + sizeof(uint64_t) * 2 * LL_STAGES;
+
+// max |x| over the table (first column): bound for the per-item fast-sine range check.
+// |double| ordering == unsigned ordering of the bit pattern; NaN compares above everything,
+// which switches the fast path off.
+__global__ void absmax_col0_kernel(const double * data, long long n_rows, unsigned long long * out) {
+	unsigned long long m = 0;
+	for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < n_rows;
+			i += (long long) gridDim.x * blockDim.x) {
+		unsigned long long b = (unsigned long long) __double_as_longlong(data[2 * i]) & 0x7fffffffffffffffull;
+		m = b > m ? b : m;
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+		m = t > m ? t : m;
+	}
+	if ((threadIdx.x & 31) == 0)
+		atomicMax(out, m);
+}
 
 // ------------------------------------------------------------------ control kernel
 enum {
@@ -274,7 +302,15 @@ struct AdvArgs {
 	long long step_index;
 	CalibCfgDev cal;
 	const unsigned char * select; // calibration selection (ADV_CALIB_BEGIN)
+	int act_w;                    // calibration: which active-list buffer this launch fills
 };
+
+// calibration: append chain g to the list the next likelihood launch walks (the order of the
+// list does not influence any result: a chain's sum does not depend on its tile)
+APM_D void act_push(const DevState & S, int w, int g) {
+	const int slot = atomicAdd(&S.act_n[w], 1);
+	S.act_idx[(size_t) w * S.n_chains + slot] = g;
+}
 
 constexpr int ADV_THREADS = 128;
 
@@ -301,8 +337,10 @@ __global__ void __launch_bounds__(ADV_THREADS) advance_kernel(const DevState S, 
 				atomicAdd(S.n_active, 1);
 				cal_begin(S, g, a.cal);
 				int kind = cal_next_kind(S, g);
-				if (kind != PEND_NONE)
+				if (kind != PEND_NONE) {
 					chain_propose(S, g, kind);
+					act_push(S, a.act_w, g);
+				}
 			} else {
 				S.cal[g].phase = CAL_IDLE;
 				S.cal[g].status = -1;
@@ -310,6 +348,8 @@ __global__ void __launch_bounds__(ADV_THREADS) advance_kernel(const DevState S, 
 		}
 		return;
 	}
+	if ((a.flags & ADV_CALIB) && blockIdx.x == 0 && threadIdx.x == 0)
+		S.act_n[1 - a.act_w] = 0; // consumed by the likelihood launch before this one
 	if (a.flags & ADV_FINALIZE) {
 		for (int k = threadIdx.x; k < S.n_beta; k += blockDim.x) {
 			const int g = base + k;
@@ -321,8 +361,10 @@ __global__ void __launch_bounds__(ADV_THREADS) advance_kernel(const DevState S, 
 			if (a.flags & ADV_CALIB) {
 				cal_after_step(S, g, a.cal);
 				int kind = cal_next_kind(S, g);
-				if (kind != PEND_NONE)
+				if (kind != PEND_NONE) {
 					chain_propose(S, g, kind);
+					act_push(S, a.act_w, g);
+				}
 			}
 		}
 	}

@@ -9,6 +9,8 @@
 //   NCOLS       data columns the model reads (the row-major table may not be narrower)
 //   HAS_DATA    false for models that never touch m->data (apps/normal.c)
 //   HAS_PRIOR   whether calc_model calls set_prior()
+//   LL_C, LL_U  register tile of the likelihood kernel: chains per work item x rows per
+//               inner iteration (LL_C x LL_U independent row evaluations in flight per thread)
 //   Prep        per-chain constants derived once per proposal (kept in registers)
 //   prep()      fill Prep from the parameter vector
 //   accum()      acc + (one data row's contribution to the model's running sum), exact
@@ -37,9 +39,16 @@ namespace apm {
 
 #define APM_MAX_PAR 16
 #define APM_TWO_PI 6.283185307179586 /* (2.0 * M_PI) as the compiler folds it */
+#ifndef APM_LL_C
+#define APM_LL_C 8
+#endif
+#ifndef APM_LL_U
+#define APM_LL_U 2
+#endif
 
 // ---- apps/simplesin.c:12-38 -----------------------------------------------------------
 struct ModelSimplesin {
+	static constexpr int LL_C = APM_LL_C, LL_U = APM_LL_U;
 	static constexpr int NPAR = 4, NCOLS = 2;
 	static constexpr bool HAS_DATA = true, HAS_PRIOR = false;
 	struct Prep {
@@ -75,6 +84,7 @@ struct ModelSimplesin {
 
 // ---- apps/simplesin5.c:15-41 (formula) ----------------------------------
 struct ModelSimplesin5 {
+	static constexpr int LL_C = APM_LL_C, LL_U = APM_LL_U;
 	static constexpr int NPAR = 4, NCOLS = 2;
 	static constexpr bool HAS_DATA = true, HAS_PRIOR = false;
 	struct Prep {
@@ -109,6 +119,7 @@ struct ModelSimplesin5 {
 
 // ---- apps/simplesin2.c:12-32 ------------------------------------------------------------
 struct ModelSimplesin2 {
+	static constexpr int LL_C = APM_LL_C, LL_U = APM_LL_U;
 	static constexpr int NPAR = 2, NCOLS = 2;
 	static constexpr bool HAS_DATA = true, HAS_PRIOR = false;
 	struct Prep {
@@ -141,6 +152,7 @@ struct ModelSimplesin2 {
 
 // ---- apps/normal.c:8-34 (data-free) -------------------------------------------------------
 struct ModelNormal {
+	static constexpr int LL_C = 1, LL_U = 1;
 	static constexpr int NPAR = 1, NCOLS = 0;
 	static constexpr bool HAS_DATA = false, HAS_PRIOR = false;
 	struct Prep {
@@ -176,6 +188,7 @@ struct ModelNormal {
 
 // ---- apps/pulse_vrot.c:12-65 ----------------------------------------------------------------
 struct ModelPulseVrot {
+	static constexpr int LL_C = 4, LL_U = 1;
 	static constexpr int NPAR = 7, NCOLS = 2;
 	static constexpr bool HAS_DATA = true, HAS_PRIOR = true;
 	struct Prep {
@@ -221,6 +234,7 @@ struct ModelPulseVrot {
 
 // ---- apps/pulse.c:12-56 (n_par = 2 + 2k, k modes) -------------------------------------------
 struct ModelPulse {
+	static constexpr int LL_C = 2, LL_U = 1;
 	static constexpr int NPAR = 0, NCOLS = 2;
 	static constexpr bool HAS_DATA = true, HAS_PRIOR = true;
 	struct Prep {

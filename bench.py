@@ -138,6 +138,24 @@ def cpu_oracle_rate(data, seconds=15.0, n_threads=None):
     return rate, cores, sample, dt / steps * 1e3
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one likelihood launch, from the newest
+    committed `ncu --set full` summary under profiles/ (tools/ncu_summary.py); None if absent"""
+    import glob
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_loglik_full.json")), reverse=True):
+        try:
+            m = json.load(open(path))["launches"][0]["metrics"]
+            tot = 0.0
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v, u = m[k].split()
+                tot += float(v) * mult[u]
+            return tot
+        except Exception:
+            continue
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -267,7 +285,7 @@ def main():
     if rank == 0:
         row_evals_per_launch = eng.n_chains * N_ROWS
         achieved = row_evals_per_launch * ALG_FP64_PER_ROW / (ll_ms / max(ll_launches, 1) * 1e-3)
-        hbm_alg_bytes = N_ROWS * 16 * (eng.n_chains / 16)  # the table once per 16-chain tile
+        hbm_alg_bytes = N_ROWS * 16 * (eng.n_chains / 8)  # the table once per 8-chain work-item tile
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -284,7 +302,7 @@ def main():
             "roofline": {
                 "bound": "fp64", "kernel": "loglik_tiled_kernel<ModelSimplesin5>",
                 "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "GFP64-instr/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
                 "peak_source": "measured live: fp64_peak_kernel DFMA issue rate on this GPU "
                                "(MEASURED_PEAKS.json has no fp64 entry)",
                 "algorithmic": "17 FP64 instr per row-evaluation x 4096 chains x 1e6 rows per launch",
@@ -292,7 +310,8 @@ def main():
                 "kernel_share_of_step": ll_ms / total_ms,
                 "hbm": {"achieved": hbm_alg_bytes / (ll_ms / max(ll_launches, 1) * 1e-3) / 1e9,
                         "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                        "note": "algorithmic bytes = table once per 16-chain tile; it is served by L2"},
+                        "note": "algorithmic bytes = table once per 8-chain tile; it is served by L2 "
+                                "(traffic = DRAM bytes of one launch from the committed ncu capture)"},
             },
             "cpu_baseline": cpu, "clocks": clocks, "wall_ms_per_step": wall_ms / K,
             "row_evals_per_s": value * N_ROWS,

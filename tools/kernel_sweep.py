@@ -17,14 +17,21 @@ OUT = os.path.join(ROOT, "build_variants")
 VARIANTS = {
     "base": [],
     "deg17": ["-DAPM_SIN_DEGREE=17"],
-    "t320_rpt16_mb1": ["-DAPM_LL_THREADS=320"],
-    "t384_rpt12_mb1": ["-DAPM_LL_THREADS=384", "-DAPM_LL_RPT=12"],
-    "t128_rpt16_mb2": ["-DAPM_LL_THREADS=128", "-DAPM_LL_MINBLOCKS=2"],
-    "t192_rpt16_mb2_tile8": ["-DAPM_LL_THREADS=192", "-DAPM_LL_MINBLOCKS=2", "-DAPM_LL_MAX_TILE=8"],
-    "t256_rpt20_mb1": ["-DAPM_LL_RPT=20"],
-    "t256_rpt24_mb1": ["-DAPM_LL_RPT=24", "-DAPM_LL_MAX_TILE=8"],
-    "t512_rpt8_mb1": ["-DAPM_LL_THREADS=512", "-DAPM_LL_RPT=8"],
+    "unroll4": ["-DAPM_LL_UNROLL=4"],
+    "unroll8": ["-DAPM_LL_UNROLL=8"],
+    "unroll1": ["-DAPM_LL_UNROLL=1"],
+    "c4u4": ["-DAPM_LL_C=4", "-DAPM_LL_U=4"],
+    "c8u1": ["-DAPM_LL_C=8", "-DAPM_LL_U=1"],
+    "c6u2": ["-DAPM_LL_C=6", "-DAPM_LL_U=2"],
+    "c4u2_t512_rpt8": ["-DAPM_LL_C=4", "-DAPM_LL_U=2", "-DAPM_LL_THREADS=512", "-DAPM_LL_RPT=8"],
+    "c8u1_t512_rpt8": ["-DAPM_LL_C=8", "-DAPM_LL_U=1", "-DAPM_LL_THREADS=512", "-DAPM_LL_RPT=8"],
+    "c6u2_t384_rpt8": ["-DAPM_LL_C=6", "-DAPM_LL_U=2", "-DAPM_LL_THREADS=384", "-DAPM_LL_RPT=8", "-DAPM_LL_STAGES=4"],
+    "rpt8_s4": ["-DAPM_LL_RPT=8", "-DAPM_LL_STAGES=4"],
+    "rpt8_s6": ["-DAPM_LL_RPT=8", "-DAPM_LL_STAGES=6"],
+    "t128_rpt16_s6": ["-DAPM_LL_THREADS=128", "-DAPM_LL_STAGES=6"],
 }
+# run-time knobs tried on the base build
+ENVS = [{}, {"APM_SPLITS": "4"}, {"APM_SPLITS": "13"}, {"APM_SPLITS": "26"}, {"APM_SPLITS": "61"}]
 
 
 def build():
@@ -45,13 +52,13 @@ def run():
     params = bench.TRUTH[None, :] + rng.normal(0, 1e-3, (4096, 4))
     beta = np.ones(4096)
     results = {}
-    envs = [{}]
+    envs = ENVS
     for name in VARIANTS:
         path = os.path.join(OUT, f"libapm_{name}.so")
         if not os.path.exists(path):
             continue
         for env in (envs if name == "base" else [{}]):
-            for k in ("APM_TILE", "APM_ITEMS_PER_CTA"):
+            for k in ("APM_SPLITS",):
                 os.environ.pop(k, None)
             os.environ.update(env)
             lib = capi.load_library(path)
