@@ -1,0 +1,294 @@
+/*
+ * apm_analyse.c -- the `analyse` phase: marginal distributions and the model evidence.
+ *
+ * Both work from the files `run` wrote, exactly like the reference (src/analyse.c), so
+ * runs made with either program can be analysed with either program.  In addition, when
+ * `run` left its on-device accumulators in `run_statistics`, the evidence is also printed
+ * from those: the prob-chain dumps carry only 7 significant digits ("%6e", reference
+ * src/parallel_tempering.c:399), the accumulators are full fp64 sums.
+ */
+#include <gsl/gsl_histogram.h>
+#include <gsl/gsl_sf.h>
+#include "apm_session.h"
+
+/* chain structs of one ensemble without an engine: analyse never touches the GPU */
+static mcmc ** chains_from_files(void) {
+	mcmc ** chains = setup_chains();
+	read_calibration_file(chains, N_BETA);
+	return chains;
+}
+
+static void free_chains(mcmc ** chains) {
+	int i;
+	for (i = N_BETA - 1; i >= 0; i--) {
+		free(chains[i]->additional_data);
+		if (i != 0)
+			set_data(chains[i], NULL);
+		free(mcmc_free(chains[i]));
+	}
+	free(chains);
+}
+
+static void print_evidence(double data_logprob) {
+	/* reference src/analyse.c:95-112 */
+	const double l3 = gsl_sf_log(3), l10 = gsl_sf_log(10), l30 = gsl_sf_log(30), l100 = gsl_sf_log(100);
+	printf("Model probability ln(p(D|M, I)): [about 10^%.0f] %.5f"
+			"\n"
+			"\nTable to compare support against other models (Jeffrey):\n"
+			" other model ln(p(D|M,I)) | supporting evidence for this model\n"
+			" --------------------------------- \n"
+			"        >  %04.1f \tnegative (supports other model)\n"
+			"  %04.1f .. %04.1f \tBarely worth mentioning\n"
+			"  %04.1f .. %04.1f \tSubstantial\n"
+			"  %04.1f .. %04.1f \tStrong\n"
+			"  %04.1f .. %04.1f \tVery strong\n"
+			"        <  %04.1f \tDecisive\n", data_logprob / l10, data_logprob, data_logprob, data_logprob,
+			data_logprob - l3, data_logprob - l3, data_logprob - l10, data_logprob - l10, data_logprob - l30,
+			data_logprob - l30, data_logprob - l100, data_logprob - l100);
+	printf("\nbe careful.\n");
+}
+
+/* thermodynamic integration by the reference's right-endpoint rectangle rule
+ * (src/analyse.c:82-93): sums[k] = mean of (prob - prior) of chain k divided by beta_k */
+static double integrate_over_beta(mcmc ** chains, const double * sums, unsigned int n_beta) {
+	double previous_beta = 0, total = 0;
+	unsigned int j;
+	for (j = n_beta - 1;; j--) {
+		assert(get_beta(chains[j]) > previous_beta);
+		total += sums[j] * (get_beta(chains[j]) - previous_beta);
+		if (j == 0)
+			break;
+		previous_beta = get_beta(chains[j]);
+	}
+	return total;
+}
+
+static int evidence_from_dumps(mcmc ** chains, unsigned int n_beta, double * result) {
+	double * sums = (double *) calloc(n_beta, sizeof(double));
+	unsigned int i;
+	char name[64];
+	for (i = 0; i < n_beta; i++) {
+		unsigned long n = 0;
+		double w, v;
+		FILE * f;
+		snprintf(name, sizeof(name), "prob-chain%d.dump", i);
+		printf("reading probabilities of chain %d\r", i);
+		fflush(stdout);
+		f = fopen(apm_out_path(name), "r");
+		if (f == NULL) {
+			fprintf(stderr, "calculating data probability failed: file %s not found\n", name);
+			free(sums);
+			return 1;
+		}
+		while (!feof(f)) {
+			if (fscanf(f, "%le\t%le", &w, &v) == 2) {
+				sums[i] += v;
+				n++;
+			} else if (!feof(f)) {
+				int c = fgetc(f); /* skip what cannot be parsed */
+				(void) c;
+			}
+		}
+		fclose(f);
+		if (n == 0) {
+			fprintf(stderr, "calculating data probability failed: no data points found in %s\n", name);
+			free(sums);
+			return 1;
+		}
+		sums[i] = sums[i] / get_beta(chains[i]) / n;
+	}
+	*result = integrate_over_beta(chains, sums, n_beta);
+	free(sums);
+	return 0;
+}
+
+static int evidence_from_accumulators(mcmc ** chains, unsigned int n_beta, double * result) {
+	FILE * f = fopen(apm_out_path("run_statistics"), "r");
+	double * sums;
+	unsigned int i, j, n_par = get_n_par(chains[0]);
+	int ok = 1;
+	if (f == NULL)
+		return 1;
+	sums = (double *) calloc(n_beta, sizeof(double));
+	for (i = 0; i < n_beta && ok; i++) {
+		int k;
+		unsigned long long n;
+		double beta, mean_dl, skip;
+		ok = fscanf(f, "%d %lf %llu %lf", &k, &beta, &n, &mean_dl) == 4 && k == (int) i && n > 0;
+		for (j = 0; j < 2 * n_par && ok; j++)
+			ok = fscanf(f, "%lf", &skip) == 1;
+		if (ok)
+			sums[i] = mean_dl / get_beta(chains[i]);
+	}
+	fclose(f);
+	if (ok)
+		*result = integrate_over_beta(chains, sums, n_beta);
+	free(sums);
+	return ok ? 0 : 1;
+}
+
+void analyse_data_probability(void) {
+	double sum = 0, sum2 = 0, acc_sum = 0;
+	int e, n_ok = 0, n_acc = 0;
+	for (e = 0; e < N_ENSEMBLES; e++) {
+		mcmc ** chains;
+		double lnz;
+		apm_set_output_dir(e);
+		chains = chains_from_files();
+		if (evidence_from_dumps(chains, N_BETA, &lnz) == 0) {
+			if (N_ENSEMBLES > 1)
+				printf("ensemble %d: ", e);
+			print_evidence(lnz);
+			sum += lnz;
+			sum2 += lnz * lnz;
+			n_ok++;
+		}
+		if (evidence_from_accumulators(chains, N_BETA, &lnz) == 0) {
+			printf("%sModel probability from the on-device accumulators (full precision): %.5f\n",
+					N_ENSEMBLES > 1 ? "            " : "", lnz);
+			acc_sum += lnz;
+			n_acc++;
+		}
+		free_chains(chains);
+	}
+	apm_set_output_dir(-1);
+	if (N_ENSEMBLES > 1 && n_ok > 1) {
+		const double mean = sum / n_ok;
+		printf("\n%d independent ensembles: ln(p(D|M, I)) = %.5f +- %.5f (standard error of the mean)\n", n_ok,
+				mean, sqrt((sum2 / n_ok - mean * mean) / (n_ok - 1)));
+		if (n_acc == n_ok)
+			printf("from the accumulators: %.5f\n", acc_sum / n_acc);
+	}
+}
+
+/* ---- marginal distributions: reference src/analyse.c:115-285, src/histogram.c:34-106 ---- */
+static gsl_histogram * uniform_histogram(int nbins, double min, double max) {
+	gsl_histogram * h = gsl_histogram_alloc(nbins);
+	gsl_histogram_set_ranges_uniform(h, min, max);
+	h->range[h->n] += (max - min) / 10000; /* so that the maximum falls into the last bin */
+	return h;
+}
+
+static void fill_from_file(gsl_histogram * h, const char * filename, double * min, double * max) {
+	FILE * f = fopen(filename, "r");
+	double v;
+	if (f == NULL) {
+		fprintf(stderr, "error opening file %s\n", filename);
+		perror("file could not be opened");
+		exit(1);
+	}
+	while (fscanf(f, "%lf", &v) == 1) {
+		if (h != NULL)
+			gsl_histogram_increment(h, v);
+		if (min != NULL && v < *min)
+			*min = v;
+		if (max != NULL && v > *max)
+			*max = v;
+	}
+	if (!feof(f)) {
+		fprintf(stderr, "field could not be read in %s\n", filename);
+		exit(1);
+	}
+	fclose(f);
+}
+
+/* batch-means estimate of the Monte Carlo error of the mean (reference src/analyse.c:115-142) */
+static double batch_means_error(const double mean, const char * filename, unsigned long batchsize) {
+	FILE * f = fopen(filename, "r");
+	unsigned long n = 0;
+	int nbatches = 0;
+	double v, batchsum = 0, errorsum = 0;
+	if (f == NULL)
+		return 0;
+	while (fscanf(f, "%lf", &v) == 1) {
+		n++;
+		batchsum += v;
+		if (n % batchsize == batchsize - 1) {
+			const double batchmean = batchsum / batchsize;
+			errorsum += pow(batchmean - mean, 2);
+			batchsum = 0;
+			nbatches++;
+		}
+	}
+	fclose(f);
+	return sqrt(errorsum / nbatches);
+}
+
+static void marginal_distribution(mcmc ** chains, unsigned int n_beta, unsigned int param) {
+	const char * paramname = get_params_descr(chains[0])[param];
+	double lo = get_params_min_for(chains[0], param), hi = get_params_max_for(chains[0], param);
+	char in_name[APM_PATH_MAX], out_name[APM_PATH_MAX];
+	gsl_histogram * h;
+	double iter, mean, sigma;
+	unsigned int i, filecount = 1;
+	FILE * out;
+#ifdef HISTOGRAMS_ALLCHAINS
+	filecount = n_beta;
+#else
+	(void) n_beta;
+#endif
+#ifdef HISTOGRAMS_MINMAX
+	{
+		double dmin = HUGE_VAL, dmax = -HUGE_VAL;
+		for (i = 0; i < filecount; i++) {
+			snprintf(in_name, sizeof(in_name), "%s-chain-%d.prob.dump", paramname, i);
+			fill_from_file(NULL, apm_out_path(in_name), &dmin, &dmax);
+		}
+		lo = dmin;
+		hi = dmax;
+	}
+#endif
+	h = uniform_histogram(NBINS, lo, hi);
+	for (i = 0; i < filecount; i++) {
+		snprintf(in_name, sizeof(in_name), "%s-chain-%d.prob.dump", paramname, i);
+		printf("reading values: chain %3d parameter %s   \r", i, paramname);
+		fflush(stdout);
+		fill_from_file(h, apm_out_path(in_name), NULL, NULL);
+	}
+	iter = gsl_histogram_sum(h);
+	gsl_histogram_scale(h, (hi - lo) / NBINS / iter);
+	snprintf(out_name, sizeof(out_name), "%s.histogram", paramname);
+	out = fopen(apm_out_path(out_name), "w");
+	assert(out != NULL);
+	gsl_histogram_fprintf(out, h, DUMP_FORMAT, DUMP_FORMAT);
+	fclose(out);
+	mean = gsl_histogram_mean(h);
+	sigma = gsl_histogram_sigma(h);
+	for (i = 0; i < filecount; i++) {
+		double err;
+		snprintf(in_name, sizeof(in_name), "%s-chain-%d.prob.dump", paramname, i);
+		err = batch_means_error(mean, apm_out_path(in_name), (unsigned long) sqrt(iter));
+		printf("mcmc error estimate of %s: %f %s\n", paramname, err, err > sigma * 0.01 ? "** high!" : " (ok)");
+	}
+	printf("Note: Include a error estimate in your publication!\n");
+	gsl_histogram_free(h);
+}
+
+void analyse_marginal_distributions(void) {
+	int e;
+	for (e = 0; e < N_ENSEMBLES; e++) {
+		mcmc ** chains;
+		unsigned int i, n_par;
+		FILE * plot;
+		apm_set_output_dir(e);
+		chains = chains_from_files();
+		n_par = get_n_par(chains[0]);
+		for (i = 0; i < n_par; i++)
+			marginal_distribution(chains, N_BETA, i);
+		plot = fopen(apm_out_path("marginal_distributions.gnuplot"), "w");
+		assert(plot != NULL);
+		fprintf(plot, "# set terminal png size %d,%d; set output \"marginal_distributions.png\"\n", 600,
+				300 * n_par);
+		fprintf(plot, "set multiplot\n");
+		fprintf(plot, "set size 1,%f\n", 1. / n_par);
+		for (i = 0; i < n_par; i++) {
+			fprintf(plot, "set origin 0,%f\n", (n_par - i - 1) * 1. / n_par);
+			fprintf(plot, "plot \"%s.histogram\" u 1:3 title \"%s\" " GNUPLOT_STYLE "\n",
+					get_params_descr(chains[0])[i], get_params_descr(chains[0])[i]);
+		}
+		fprintf(plot, "unset multiplot\n");
+		fclose(plot);
+		free_chains(chains);
+	}
+	apm_set_output_dir(-1);
+}

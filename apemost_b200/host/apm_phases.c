@@ -1,0 +1,699 @@
+/*
+ * apm_phases.c -- the phases calibrate_first / calibrate_rest / run over the GPU engine.
+ *
+ * Each phase follows the reference's order of operations (cited per function) with the
+ * three CPU hot loops replaced by engine calls:
+ *     calc_model(chains[i], NULL)        -> apm_gpu_eval
+ *     markov_chain_calibrate(chains[i])  -> apm_gpu_calibrate (all selected chains at once)
+ *     run_sampler()'s step/swap loop     -> apm_gpu_run + apm_gpu_read_trace
+ * Everything read from or written to disk goes through the chain structs, so the files are
+ * produced by the same formatting code paths as in the reference.
+ */
+#include <signal.h>
+#include <time.h>
+#include "apm_session.h"
+
+/* ------------------------------------------------------------------ configuration */
+static unsigned circular_mask(void) {
+	/* CIRCULAR_PARAMS is a 1-based list (reference src/markov_chain.h:34-46) */
+	const unsigned int list[] = { CIRCULAR_PARAMS, 0 };
+	unsigned mask = 0;
+	unsigned int j;
+	for (j = 0; j < sizeof(list) / sizeof(list[0]); j++)
+		if (list[j] >= 1 && list[j] <= 32)
+			mask |= 1u << (list[j] - 1);
+	return mask;
+}
+
+static void engine_config(apm_gpu_config * cfg, int n_ens, int n_beta, int n_par) {
+	const char * seed = getenv("GSL_RNG_SEED"); /* the reference's seed variable (src/mcmc.c:27-35) */
+	const char * dev = getenv("APM_DEVICE");
+	memset(cfg, 0, sizeof(*cfg));
+	cfg->device = dev ? atoi(dev) : 0;
+	cfg->model_id = APM_MODEL_ID;
+	cfg->n_ensembles = n_ens;
+	cfg->n_beta = n_beta;
+	cfg->n_par = n_par;
+	cfg->seed = seed ? strtoull(seed, NULL, 10) : 0;
+#if defined(PROPOSAL_UNIFORM)
+	cfg->proposal = APM_PROPOSAL_UNIFORM;
+#elif defined(PROPOSAL_LOGISTIC)
+	cfg->proposal = APM_PROPOSAL_LOGISTIC;
+#else
+	cfg->proposal = APM_PROPOSAL_GAUSSIAN;
+#endif
+	cfg->circular_mask = circular_mask();
+#ifdef APM_EXACT_SWAP
+	cfg->quirks = 0;                    /* statistically exact swap and revert */
+#else
+	cfg->quirks = APM_QUIRKS_REFERENCE; /* behave exactly like the reference */
+#endif
+	cfg->path = APM_PATH_AUTO;
+#if defined(SIGMA)
+	cfg->model_const[0] = SIGMA;        /* apps/simplesin*.c */
+#elif defined(HMIN)
+	cfg->model_const[0] = HMIN;         /* apps/pulse*.c */
+#endif
+}
+
+static void calib_config(apm_gpu_calib_cfg * c, int skip) {
+	memset(c, 0, sizeof(*c));
+	c->burn_in_iterations = BURN_IN_ITERATIONS;
+	c->desired_acceptance_rate = TARGET_ACCEPTANCE_RATE;
+	c->max_ar_deviation = MAX_AR_DEVIATION;
+	c->iter_limit = ITER_LIMIT;
+	c->mul = MUL;
+	c->adjust_step = DEFAULT_ADJUST_STEP;
+	c->skip_calibrate = skip;
+	c->iter_readjust = ITER_READJUST;
+	c->no_rescaling_limit = NO_RESCALING_LIMIT;
+}
+
+/* ------------------------------------------------------------------ session */
+void apm_gpu_check(apm_session * s, int rc, const char * what) {
+	if (rc == APM_OK)
+		return;
+	fprintf(stderr, "%s failed: %s\n", what, apm_gpu_last_error(s ? s->gpu : NULL));
+	exit(1);
+}
+
+mcmc ** apm_ensemble(apm_session * s, int e) {
+	return s->chains + (size_t) e * s->n_beta;
+}
+
+static void attach_pt_data(mcmc * m) {
+	m->additional_data = calloc(1, sizeof(parallel_tempering_mcmc));
+	assert(m->additional_data != NULL);
+	set_beta(m, 1.0);
+}
+
+/* N_BETA chains from the params file sharing chain 0's data table
+ * (reference src/parallel_tempering_config.c:95-123) */
+mcmc ** setup_chains(void) {
+	const unsigned int n_beta = N_BETA;
+	mcmc ** chains = (mcmc **) calloc(n_beta, sizeof(mcmc *));
+	unsigned int i;
+	assert(chains != NULL);
+	printf("Initializing %d chains ...\n", n_beta);
+	for (i = 0; i < n_beta; i++) {
+		chains[i] = mcmc_load_params(PARAMS_FILENAME);
+		if (i == 0)
+			mcmc_load_data(chains[i], DATA_FILENAME);
+		else
+			mcmc_reuse_data(chains[i], chains[0]);
+		attach_pt_data(chains[i]);
+		mcmc_check(chains[i]);
+	}
+	return chains;
+}
+
+apm_session * apm_session_open(void) {
+	apm_session * s = (apm_session *) calloc(1, sizeof(*s));
+	mcmc ** first;
+	apm_gpu_config cfg;
+	const gsl_matrix * d;
+	size_t n, nv;
+	int g;
+	assert(s != NULL);
+	s->n_ens = N_ENSEMBLES;
+	s->n_beta = N_BETA;
+	s->n_chains = s->n_ens * s->n_beta;
+	s->chains = (mcmc **) calloc(s->n_chains, sizeof(mcmc *));
+	first = setup_chains();
+	memcpy(s->chains, first, s->n_beta * sizeof(mcmc *));
+	free(first);
+	for (g = s->n_beta; g < s->n_chains; g++) { /* further ensembles: same params, same table */
+		s->chains[g] = mcmc_load_params(PARAMS_FILENAME);
+		mcmc_reuse_data(s->chains[g], s->chains[0]);
+		attach_pt_data(s->chains[g]);
+	}
+	s->n_par = get_n_par(s->chains[0]);
+	n = s->n_chains;
+	nv = n * s->n_par;
+	s->beta = (double *) calloc(n, sizeof(double));
+	s->prob = (double *) calloc(n, sizeof(double));
+	s->prior = (double *) calloc(n, sizeof(double));
+	s->prob_best = (double *) calloc(n, sizeof(double));
+	s->params = (double *) calloc(nv, sizeof(double));
+	s->steps = (double *) calloc(nv, sizeof(double));
+	s->params_best = (double *) calloc(nv, sizeof(double));
+	s->accept = (unsigned long long *) calloc(n, sizeof(unsigned long long));
+	s->reject = (unsigned long long *) calloc(n, sizeof(unsigned long long));
+	s->n_iter = (unsigned long long *) calloc(n, sizeof(unsigned long long));
+	s->swapcount = (unsigned long long *) calloc(n, sizeof(unsigned long long));
+	s->pacc = (unsigned long long *) calloc(nv, sizeof(unsigned long long));
+	s->prej = (unsigned long long *) calloc(nv, sizeof(unsigned long long));
+
+	engine_config(&cfg, s->n_ens, s->n_beta, s->n_par);
+	if (apm_gpu_create(&s->gpu, &cfg) != APM_OK) {
+		fprintf(stderr, "could not start the GPU engine: %s\n", apm_gpu_last_error(NULL));
+		exit(1);
+	}
+	d = s->chains[0]->data;
+	assert(d->tda == d->size2);
+	apm_gpu_check(s, apm_gpu_set_data(s->gpu, d->data, (long long) d->size1, (int) d->size2), "uploading the data table");
+	apm_gpu_check(s, apm_gpu_set_bounds(s->gpu, get_params_min(s->chains[0])->data,
+			get_params_max(s->chains[0])->data), "setting the parameter bounds");
+	apm_session_push(s, 0, s->n_chains);
+	return s;
+}
+
+void apm_session_close(apm_session * s) {
+	int g;
+	apm_gpu_destroy(s->gpu);
+	for (g = s->n_chains - 1; g >= 0; g--) {
+		free(s->chains[g]->additional_data);
+		if (g != 0)
+			set_data(s->chains[g], NULL); /* borrowed from chain 0 */
+		free(mcmc_free(s->chains[g]));
+	}
+	free(s->chains);
+	free(s->beta); free(s->prob); free(s->prior); free(s->prob_best); free(s->params); free(s->steps);
+	free(s->params_best); free(s->accept); free(s->reject); free(s->n_iter); free(s->swapcount);
+	free(s->pacc); free(s->prej);
+	free(s);
+}
+
+static void chain_io(apm_session * s, int first, apm_gpu_chain_io * io) {
+	const size_t o = first, ov = (size_t) first * s->n_par;
+	memset(io, 0, sizeof(*io));
+	io->beta = s->beta + o;
+	io->params = s->params + ov;
+	io->steps = s->steps + ov;
+	io->prob = s->prob + o;
+	io->prior = s->prior + o;
+	io->prob_best = s->prob_best + o;
+	io->params_best = s->params_best + ov;
+	io->accept = s->accept + o;
+	io->reject = s->reject + o;
+	io->params_accepts = s->pacc + ov;
+	io->params_rejects = s->prej + ov;
+	io->n_iter = s->n_iter + o;
+	io->swapcount = s->swapcount + o;
+}
+
+void apm_session_push(apm_session * s, int first, int count) {
+	apm_gpu_chain_io io;
+	int g, j;
+	for (g = first; g < first + count; g++) {
+		const mcmc * m = s->chains[g];
+		s->beta[g] = get_beta(m);
+		s->prob[g] = m->prob;
+		s->prior[g] = m->prior;
+		s->prob_best[g] = m->prob_best;
+		s->accept[g] = m->accept;
+		s->reject[g] = m->reject;
+		s->n_iter[g] = m->n_iter;
+		s->swapcount[g] = get_swapcount(m);
+		for (j = 0; j < s->n_par; j++) {
+			const size_t k = (size_t) g * s->n_par + j;
+			s->params[k] = gsl_vector_get(m->params, j);
+			s->steps[k] = gsl_vector_get(m->params_step, j);
+			s->params_best[k] = gsl_vector_get(m->params_best, j);
+			s->pacc[k] = m->params_accepts[j];
+			s->prej[k] = m->params_rejects[j];
+		}
+	}
+	chain_io(s, first, &io);
+	apm_gpu_check(s, apm_gpu_set_chains(s->gpu, first, count, &io), "uploading the chain state");
+}
+
+void apm_session_pull(apm_session * s, int first, int count) {
+	apm_gpu_chain_io io;
+	int g, j;
+	chain_io(s, first, &io);
+	apm_gpu_check(s, apm_gpu_get_chains(s->gpu, first, count, &io), "downloading the chain state");
+	for (g = first; g < first + count; g++) {
+		mcmc * m = s->chains[g];
+		parallel_tempering_mcmc * pt = (parallel_tempering_mcmc *) m->additional_data;
+		pt->beta = s->beta[g];
+		pt->swapcount = (unsigned long) s->swapcount[g];
+		m->prob = s->prob[g];
+		m->prior = s->prior[g];
+		m->prob_best = s->prob_best[g];
+		m->accept = (unsigned long) s->accept[g];
+		m->reject = (unsigned long) s->reject[g];
+		m->n_iter = (unsigned long) s->n_iter[g];
+		for (j = 0; j < s->n_par; j++) {
+			const size_t k = (size_t) g * s->n_par + j;
+			gsl_vector_set(m->params, j, s->params[k]);
+			gsl_vector_set(m->params_step, j, s->steps[k]);
+			gsl_vector_set(m->params_best, j, s->params_best[k]);
+			m->params_accepts[j] = (unsigned long) s->pacc[k];
+			m->params_rejects[j] = (unsigned long) s->prej[k];
+		}
+	}
+}
+
+/* calc_model(chains[g], NULL) for g in which[]: one batched evaluation on the device */
+void apm_session_calc_model(apm_session * s, const int * which, int n) {
+	double * p = (double *) calloc((size_t) n * s->n_par, sizeof(double));
+	double * b = (double *) calloc(n, sizeof(double));
+	double * prob = (double *) calloc(n, sizeof(double));
+	double * prior = (double *) calloc(n, sizeof(double));
+	apm_gpu_chain_io io;
+	int i, j;
+	for (i = 0; i < n; i++) {
+		const mcmc * m = s->chains[which[i]];
+		b[i] = get_beta(m);
+		for (j = 0; j < s->n_par; j++)
+			p[(size_t) i * s->n_par + j] = gsl_vector_get(m->params, j);
+	}
+	apm_gpu_check(s, apm_gpu_eval(s->gpu, n, p, b, prob, prior), "evaluating the model");
+	for (i = 0; i < n; i++) {
+		mcmc * m = s->chains[which[i]];
+		set_prior(m, prior[i]);
+		set_prob(m, prob[i]);
+		memset(&io, 0, sizeof(io));
+		io.prob = &prob[i];
+		io.prior = &prior[i];
+		apm_gpu_check(s, apm_gpu_set_chains(s->gpu, which[i], 1, &io), "storing the model value");
+	}
+	free(p); free(b); free(prob); free(prior);
+}
+
+/* markov_chain_calibrate for the selected chains, all at once on the device.  On failure:
+ * the reference's message and exit code (src/markov_chain_calibrate.c:1104-1110,1169-1174) */
+static void calibrate_selected(apm_session * s, const unsigned char * select, int skip,
+		apm_gpu_calib_progress ** rows_out, long long * n_rows_out) {
+	apm_gpu_calib_cfg cfg;
+	int * status = (int *) calloc(s->n_chains, sizeof(int));
+	long long cap = 0, n_rows = 0;
+	apm_gpu_calib_progress * rows = NULL;
+	int g, rc, n_sel = 0;
+	calib_config(&cfg, skip);
+	for (g = 0; g < s->n_chains; g++)
+		n_sel += select[g] != 0;
+	if (rows_out != NULL) {
+		cap = ((long long) ITER_LIMIT / ITER_READJUST + 2) * s->n_par * n_sel;
+		rows = (apm_gpu_calib_progress *) calloc(cap > 0 ? cap : 1, sizeof(*rows));
+	}
+	rc = apm_gpu_calibrate(s->gpu, select, &cfg, status, rows, cap, &n_rows);
+	if (rc == APM_ECALIB) {
+		for (g = 0; g < s->n_chains; g++) {
+			if (status[g] == APM_CALIB_STEP_TOO_LARGE)
+				fprintf(stderr, "calibration failed: step width became too large (chain %d).\n", g);
+			else if (status[g] == APM_CALIB_ITER_LIMIT)
+				fprintf(stderr, "calibration failed: limit of %d iterations reached (chain %d).\n",
+						(int) ITER_LIMIT, g);
+		}
+		exit(1);
+	}
+	apm_gpu_check(s, rc, "calibration");
+	free(status);
+	if (rows_out != NULL) {
+		*rows_out = rows;
+		*n_rows_out = n_rows < cap ? n_rows : cap;
+	}
+}
+
+/* ------------------------------------------------------------------ calibrate_first
+ * reference src/parallel_tempering.c:78-95 */
+void calibrate_first(void) {
+	apm_session * s = apm_session_open();
+	unsigned char * select = (unsigned char *) calloc(s->n_chains, 1);
+	int * which = (int *) calloc(s->n_ens, sizeof(int));
+	apm_gpu_calib_progress * rows = NULL;
+	long long n_rows = 0;
+	int e;
+
+	printf("Starting markov chain calibration\n");
+	fflush(stdout);
+	for (e = 0; e < s->n_ens; e++) {
+		which[e] = e * s->n_beta;
+		select[which[e]] = 1;
+	}
+	apm_session_calc_model(s, which, s->n_ens);
+	calibrate_selected(s, select, 0, &rows, &n_rows);
+	apm_session_pull(s, 0, s->n_chains);
+	for (e = 0; e < s->n_ens; e++) {
+		apm_set_output_dir(e);
+		apm_write_calibration_progress(rows, n_rows, which[e]);
+		write_calibrations_file(apm_ensemble(s, e), 1);
+		write_params_file(apm_ensemble(s, e)[0]);
+	}
+	apm_set_output_dir(-1);
+	free(rows); free(select); free(which);
+	apm_session_close(s);
+}
+
+/* ------------------------------------------------------------------ calibrate_rest
+ * reference src/parallel_tempering.c:115-207: learn per-parameter step-width factors by
+ * calibrating chain 1, choose beta_0, predict every chain's step widths as
+ * steps(chain 0) * beta^-1/2 * factors, then calibrate (or only burn in) chains 1..n-1.
+ * All ensembles go through each stage together. */
+static void place_chain(mcmc * c, const mcmc * c0, double beta, const gsl_vector * factors) {
+	set_beta(c, beta);
+	gsl_vector_memcpy(get_steps(c), get_steps(c0));
+	gsl_vector_scale(get_steps(c), pow(get_beta(c), -0.5));
+	if (factors != NULL)
+		gsl_vector_mul(get_steps(c), factors);
+	set_params(c, dup_vector(get_params_best(c0)));
+}
+
+void calibrate_rest(void) {
+	apm_session * s = apm_session_open();
+	const int n_beta = s->n_beta, n_ens = s->n_ens;
+	gsl_vector ** factors = (gsl_vector **) calloc(n_ens, sizeof(gsl_vector *));
+	double * beta_0 = (double *) calloc(n_ens, sizeof(double));
+	unsigned char * select = (unsigned char *) calloc(s->n_chains, 1);
+	int * which = (int *) calloc(s->n_chains, sizeof(int));
+	apm_gpu_calib_progress * rows = NULL;
+	long long n_rows = 0;
+	int e, i, n;
+#ifdef SKIP_CALIBRATE_ALLCHAINS
+	const int skip = 1;
+#else
+	const int skip = 0;
+#endif
+
+	for (e = 0; e < n_ens; e++) {
+		apm_set_output_dir(e);
+		read_calibration_file(apm_ensemble(s, e), 1);
+		factors[e] = gsl_vector_alloc(s->n_par);
+		gsl_vector_set_all(factors[e], 1);
+		beta_0[e] = BETA_0;
+	}
+	printf("Calibrating chains\n");
+	fflush(stdout);
+
+	if (n_beta > 1) {
+		/* the second chain tells how step widths really scale with beta */
+		for (e = 0, n = 0; e < n_ens; e++) {
+			mcmc ** c = apm_ensemble(s, e);
+			const double b0 = beta_0[e] < 0 ? calc_beta_0(c[0], factors[e]) : beta_0[e];
+			place_chain(c[1], c[0], get_chain_beta(1, n_beta, b0), NULL);
+			which[n++] = e * n_beta + 1;
+			select[e * n_beta + 1] = 1;
+		}
+		apm_session_push(s, 0, s->n_chains);
+		apm_session_calc_model(s, which, n);
+		printf("Calibrating second chain to infer stepwidth factor\n");
+		printf("\tChain %2d - beta = %f\tsteps: ", 1, get_beta(s->chains[1]));
+		dump_vectorln(get_steps(s->chains[1]));
+		fflush(stdout);
+		calibrate_selected(s, select, 0, NULL, NULL);
+		apm_session_pull(s, 0, s->n_chains);
+		for (e = 0; e < n_ens; e++) {
+			mcmc ** c = apm_ensemble(s, e);
+			gsl_vector_scale(factors[e], pow(get_beta(c[1]), -0.5));
+			gsl_vector_mul(factors[e], get_steps(c[0]));
+			gsl_vector_div(factors[e], get_steps(c[1]));
+		}
+	}
+	printf("stepwidth factors: ");
+	dump_vectorln(factors[0]);
+	for (e = 0; e < n_ens; e++) {
+		if (beta_0[e] < 0) {
+			beta_0[e] = calc_beta_0(apm_ensemble(s, e)[0], factors[e]);
+			if (e == 0)
+				printf("automatic beta_0: %f\n", beta_0[e]);
+		}
+	}
+	fflush(stdout);
+
+	if (n_beta > 1) {
+		memset(select, 0, s->n_chains);
+		for (e = 0, n = 0; e < n_ens; e++) {
+			mcmc ** c = apm_ensemble(s, e);
+			for (i = 1; i < n_beta; i++) {
+				place_chain(c[i], c[0], get_chain_beta(i, n_beta, beta_0[e]), factors[e]);
+				which[n++] = e * n_beta + i;
+				select[e * n_beta + i] = 1;
+				if (e == 0) {
+					printf("\tChain %2d - beta = %f\tsteps: ", i, get_beta(c[i]));
+					dump_vectorln(get_steps(c[i]));
+				}
+			}
+		}
+		apm_session_push(s, 0, s->n_chains);
+		apm_session_calc_model(s, which, n);
+		calibrate_selected(s, select, skip, &rows, &n_rows);
+		apm_session_pull(s, 0, s->n_chains);
+	}
+	printf("all chains calibrated.\n");
+	for (i = 0; i < n_beta; i++) {
+		printf("\tChain %2d - beta = %f \tsteps: ", i, get_beta(s->chains[i]));
+		dump_vectorln(get_steps(s->chains[i]));
+	}
+	for (e = 0; e < n_ens; e++) {
+		apm_set_output_dir(e);
+		if (rows != NULL && !skip)
+			apm_write_calibration_progress(rows, n_rows, e * n_beta + n_beta - 1);
+		write_calibration_summary(apm_ensemble(s, e), n_beta);
+		write_calibrations_file(apm_ensemble(s, e), n_beta);
+		gsl_vector_free(factors[e]);
+	}
+	apm_set_output_dir(-1);
+	free(rows); free(select); free(which); free(factors); free(beta_0);
+	apm_session_close(s);
+}
+
+/* ------------------------------------------------------------------ run
+ * reference src/parallel_tempering.c:209-250 (prepare_and_run_sampler), :347-419
+ * (run_sampler), :308-345 (dump), :36-52 (report), src/parallel_tempering_run.c:28-58 */
+static volatile sig_atomic_t keep_running = 1;
+static volatile sig_atomic_t dump_requested = 0;
+
+static void on_sigint(int signalnr) {
+	(void) signalnr;
+	keep_running = 0;
+}
+static void on_sigusr(int signalnr) {
+	signal(signalnr, on_sigusr);
+	dump_requested = 1;
+}
+
+static void report(apm_session * s) {
+	int e, i;
+	printf("printing chain parameters: \n");
+	for (i = 0; i < s->n_beta; i++) {
+		const mcmc * m = s->chains[i];
+		printf("\tchain %d: swapped %lu times: ", i, get_swapcount(m));
+		printf("\tchain %d: current %f: ", i, get_prob(m));
+		dump_vectorln(get_params(m));
+		printf("\tchain %d: best %f: ", i, get_prob_best(m));
+		dump_vectorln(get_params_best(m));
+	}
+	printf("\nwriting out visited parameters ");
+	for (e = 0; e < s->n_ens; e++)
+		for (i = 0; i < s->n_beta; i++)
+			mcmc_dump_flush(apm_ensemble(s, e)[i]);
+	printf(".done.\n");
+	fflush(stdout);
+}
+
+static unsigned long gcd_ul(unsigned long a, unsigned long b) {
+	while (b != 0) {
+		unsigned long t = a % b;
+		a = b;
+		b = t;
+	}
+	return a;
+}
+
+/* what `analyse` needs, taken from the on-device accumulators at full precision (the text
+ * dumps carry 7 digits): per chain beta, n, mean(prob - prior), then mean and variance of
+ * every parameter */
+static void write_run_statistics(apm_session * s) {
+	const size_t n = s->n_chains, nv = n * s->n_par;
+	unsigned long long * cnt = (unsigned long long *) calloc(n, sizeof(*cnt));
+	double * sdl = (double *) calloc(n, sizeof(double));
+	double * sp = (double *) calloc(nv, sizeof(double)), *sp2 = (double *) calloc(nv, sizeof(double));
+	int e, k, j;
+	apm_gpu_check(s, apm_gpu_get_stats(s->gpu, cnt, sdl, sp, sp2), "reading the accumulators");
+	for (e = 0; e < s->n_ens; e++) {
+		FILE * f;
+		apm_set_output_dir(e);
+		f = fopen(apm_out_path("run_statistics"), "w");
+		if (f == NULL)
+			continue;
+		for (k = 0; k < s->n_beta; k++) {
+			const size_t g = (size_t) e * s->n_beta + k;
+			const double c = cnt[g] > 0 ? (double) cnt[g] : 1;
+			fprintf(f, "%d\t" DUMP_FORMAT "\t%llu\t" DUMP_FORMAT, k, get_beta(s->chains[g]), cnt[g], sdl[g] / c);
+			for (j = 0; j < s->n_par; j++) {
+				const double mean = sp[g * s->n_par + j] / c;
+				fprintf(f, "\t" DUMP_FORMAT "\t" DUMP_FORMAT, mean, sp2[g * s->n_par + j] / c - mean * mean);
+			}
+			fprintf(f, "\n");
+		}
+		fclose(f);
+	}
+	apm_set_output_dir(-1);
+	free(cnt); free(sdl); free(sp); free(sp2);
+}
+
+void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
+	apm_session * s = apm_session_open();
+	const int n_beta = s->n_beta, n_ens = s->n_ens, n_par = s->n_par, n_chains = s->n_chains;
+	char * mode = append == 1 ? "a" : "w";
+	int n_swap = N_SWAP;
+	FILE ** prob_files = (FILE **) calloc(n_chains, sizeof(FILE *));
+	FILE ** accept_files = (FILE **) calloc(n_ens, sizeof(FILE *));
+	apm_gpu_trace_cfg trace;
+	unsigned long iter, interval_rounds;
+	long long max_rows, call_cap = 1;
+	double * t_prob = NULL, *t_dl = NULL, *t_par = NULL;
+	size_t t_cap = 0;
+	char name[64];
+	int e, i, j, n_dumped;
+
+#ifdef DUMP_ALL_CHAINS
+	trace.params_chains = 2;
+	n_dumped = n_chains;
+#else
+	trace.params_chains = 1;
+	n_dumped = n_ens;
+#endif
+	trace.prob_every = 1;
+
+	for (e = 0; e < n_ens; e++) {
+		mcmc ** c = apm_ensemble(s, e);
+		apm_set_output_dir(e);
+		read_calibration_file(c, n_beta);
+		for (i = 0; i < (trace.params_chains == 2 ? n_beta : 1); i++)
+			mcmc_open_dump_files(c[i], "-chain", i, mode);
+		for (i = 0; i < n_beta; i++) {
+			snprintf(name, sizeof(name), "prob-chain%d.dump", i);
+			prob_files[e * n_beta + i] = fopen(apm_out_path(name), mode);
+			if (prob_files[e * n_beta + i] == NULL) {
+				fprintf(stderr, "opening file %s failed\n", name);
+				perror("opening file failed");
+				exit(1);
+			}
+			setvbuf(prob_files[e * n_beta + i], NULL, _IOFBF, 1 << 18);
+		}
+		accept_files[e] = fopen(apm_out_path("acceptance_rate.dump.gnuplot"), "w");
+		if (accept_files[e] != NULL) {
+			FILE * f = accept_files[e];
+			fprintf(f, "# format: iteration | number of accepts for each chain\nplot ");
+			for (i = 0; i < n_beta; i++)
+				fprintf(f, "\"acceptance_rate.dump\" u 1:%d title \"chain %d, beta = %f\"%s", i + 2, i,
+						get_beta(c[i]), i != n_beta - 1 ? ", " : "");
+			fprintf(f, "\n");
+			fclose(f);
+		}
+		accept_files[e] = fopen(apm_out_path("acceptance_rate.dump"), mode);
+		assert(accept_files[e] != NULL);
+	}
+	apm_set_output_dir(-1);
+	apm_session_push(s, 0, n_chains);
+	apm_gpu_check(s, apm_gpu_reset_stats(s->gpu), "resetting the accumulators");
+
+	if (n_swap < 0) {
+		n_swap = 2000 / n_beta;
+		if (n_swap < 1)
+			n_swap = 1;
+		printf("automatic n_swap: %d\n", n_swap);
+	}
+	/* rounds between two acceptance_rate.dump rows: iter advances by n_swap per round and a
+	 * row is due whenever iter % PRINT_PROB_INTERVAL == 0 */
+	interval_rounds = PRINT_PROB_INTERVAL / gcd_ul(PRINT_PROB_INTERVAL, (unsigned long) n_swap);
+	/* bound the trace of one engine call to ~256 MB of host memory */
+	max_rows = (long long) (16u << 20) / n_chains;
+	if (max_rows < n_swap)
+		max_rows = n_swap;
+
+	signal(SIGINT, on_sigint);
+	signal(SIGUSR1, on_sigusr);
+	signal(SIGUSR2, on_sigusr);
+	keep_running = 1;
+	dump_requested = 0;
+	iter = s->chains[0]->n_iter;
+	printf("starting the analysis\n");
+	fflush(stdout);
+
+	while (keep_running && (max_iterations == 0 || iter < max_iterations)) {
+		/* one engine call: up to the next status row, the end of the run, the trace bound and
+		 * about half a second of device time, so that signals are honoured promptly */
+		const unsigned long done_rounds = iter / n_swap;
+		long long rounds = (long long) (interval_rounds - done_rounds % interval_rounds);
+		long long n_prob_rows = 0, n_par_rows = 0, r;
+		struct timespec t0, t1;
+		double secs;
+		size_t need;
+		if (max_iterations != 0) {
+			const long long left = (long long) ((max_iterations - iter + n_swap - 1) / n_swap);
+			if (rounds > left)
+				rounds = left;
+		}
+		if (rounds > call_cap)
+			rounds = call_cap;
+		if (rounds * n_swap > max_rows)
+			rounds = max_rows / n_swap;
+		clock_gettime(CLOCK_MONOTONIC, &t0);
+		apm_gpu_check(s, apm_gpu_run(s->gpu, rounds, n_swap, &trace), "sampling");
+		need = (size_t) rounds * n_swap;
+		if (need > t_cap) {
+			free(t_prob); free(t_dl); free(t_par);
+			t_cap = need;
+			t_prob = (double *) malloc(t_cap * n_chains * sizeof(double));
+			t_dl = (double *) malloc(t_cap * n_chains * sizeof(double));
+			t_par = (double *) malloc(t_cap * n_dumped * n_par * sizeof(double));
+			assert(t_prob != NULL && t_dl != NULL && t_par != NULL);
+		}
+		apm_gpu_check(s, apm_gpu_read_trace(s->gpu, t_prob, t_dl, t_par, &n_prob_rows, &n_par_rows),
+				"reading the trace");
+		clock_gettime(CLOCK_MONOTONIC, &t1);
+		secs = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+		if (secs < 0.25 && call_cap < (1ll << 40))
+			call_cap *= 2;
+		else if (secs > 1.0 && call_cap > 1)
+			call_cap /= 2;
+
+		/* the per-iteration text of run_sampler(): prob-chain<k>.dump gets "prob, prob - prior"
+		 * of every chain, the parameter dumps get the dumped chains' vectors */
+		for (i = 0; i < n_chains; i++) {
+			FILE * f = prob_files[i];
+			for (r = 0; r < n_prob_rows; r++)
+				fprintf(f, "%6e\t%6e\n", t_prob[r * n_chains + i], t_dl[r * n_chains + i]);
+		}
+		for (i = 0; i < n_dumped; i++) {
+			const mcmc * m = trace.params_chains == 2 ? s->chains[i] : s->chains[i * n_beta];
+			if (m->files == NULL)
+				continue;
+			for (j = 0; j < n_par; j++) {
+				FILE * f = m->files[j];
+				if (f == NULL)
+					continue;
+				for (r = 0; r < n_par_rows; r++)
+					fprintf(f, DUMP_FORMAT "\n", t_par[((size_t) r * n_dumped + i) * n_par + j]);
+			}
+		}
+		iter += (unsigned long) rounds * n_swap;
+
+		if (iter % PRINT_PROB_INTERVAL == 0) { /* dump() */
+			const mcmc * m = s->chains[0];
+			apm_session_pull(s, 0, n_chains);
+			if (dump_requested) {
+				report(s);
+				dump_requested = 0;
+				for (i = 0; i < n_chains; i++)
+					fflush(prob_files[i]);
+			}
+			for (e = 0; e < n_ens; e++) {
+				fprintf(accept_files[e], "%lu", iter);
+				for (i = 0; i < n_beta; i++)
+					fprintf(accept_files[e], "\t%lu", get_params_accepts_global(apm_ensemble(s, e)[i]));
+				fprintf(accept_files[e], "\n");
+				fflush(accept_files[e]);
+			}
+			printf("iteration: %lu, a/r: %.3f(%lu/%lu), v:", iter,
+					(double) m->accept / (double) (m->accept + m->reject), m->accept, m->reject);
+			dump_vector(get_params(m));
+			printf(" [%.0f chain-steps/s]\r", (double) rounds * n_swap * n_chains / (secs > 0 ? secs : 1));
+			fflush(stdout);
+		}
+	}
+	apm_session_pull(s, 0, n_chains);
+	for (e = 0; e < n_ens; e++)
+		fclose(accept_files[e]);
+	for (i = 0; i < n_chains; i++)
+		fclose(prob_files[i]);
+	printf("handled %lu iterations on %d chains\n", iter, n_chains);
+	report(s);
+	write_run_statistics(s);
+	free(t_prob); free(t_dl); free(t_par); free(prob_files); free(accept_files);
+	apm_session_close(s);
+}

@@ -1,0 +1,2 @@
+/* forwarder: a model file written for APEMoST includes "mcmc_struct.h"; everything it can use from it is in apm_host.h */
+#include "apm_host.h"

@@ -171,6 +171,19 @@ def phases_fixture(model, rows, data_file, data, cfg, ccflags_extra="", suffix="
         m = re.search(r"Model probability ln\(p\(D\|M, I\)\): \[about 10\^(-?\d+)\] (-?[\d.]+)", r.stdout)
         out["evidence_line"] = m.group(0)
         out["evidence"] = m.group(2)
+        # every other file the four phases leave behind (params_suggested, calibration_summary,
+        # calibration_progress.data, acceptance_rate.dump[.gnuplot], <name>.histogram,
+        # marginal_distributions.gnuplot) and what analyse prints: pins the host layer's formats
+        out["files"] = {}
+        for f in sorted(os.listdir(d)):
+            if f in ("params", "data", "gmon.out") or f in out["dumps"]:
+                continue
+            text = open(os.path.join(d, f)).read()
+            lines = text.splitlines()
+            out["files"][f] = dict(sha256=sha(os.path.join(d, f)), n_lines=len(lines),
+                                   text=text if len(text) <= 6000 else None,
+                                   head=lines[:3], tail=lines[-3:])
+        out["analyse_stdout"] = r.stdout
     return out
 
 

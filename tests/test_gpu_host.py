@@ -1,0 +1,140 @@
+"""The product's C host layer over the real engine (GPU box): `make <model>.exe`, then the
+reference's phases in a scratch working directory.  The same flow is driven in Python over the CPU
+oracle in PHILOX mode (tests/pt_flow.py, itself byte-pinned to the reference in MT19937 mode), so
+the files must agree number for number: same accept / swap / rescale decisions, values to 1e-9
+(the device's log / sqrt / cos in the Box-Muller transform differ from libm by an ulp, so the
+text is not bit-identical); prob-chain dumps carry 7 digits of a sum whose order differs."""
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import pt_flow
+from oracle_binding import Oracle, RNG_PHILOX, write_data_file, write_params_file
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+HOST = os.path.join(ROOT, "apemost_b200", "host")
+
+
+def make(target, ccflags, out):
+    os.makedirs(out, exist_ok=True)
+    subprocess.run(["make", "-s", "-C", HOST, f"OUT={out}", f"CCFLAGS={ccflags}", os.path.join(out, target)],
+                   check=True)
+    return os.path.join(out, target)
+
+
+def setup_workdir(wd, fx):
+    os.makedirs(wd, exist_ok=True)
+    write_params_file(os.path.join(wd, "params"), [tuple(r) for r in fx["rows"]])
+    if fx["data_file"]:
+        data = np.loadtxt(os.path.join(GOLDEN, fx["data_file"]))
+        open(os.path.join(wd, "data"), "wb").write(open(os.path.join(GOLDEN, fx["data_file"]), "rb").read())
+    else:
+        data = np.array(fx["data"], dtype=float).reshape(-1, fx["n_cols"])
+        write_data_file(os.path.join(wd, "data"), data)
+    return data
+
+
+def numbers(path):
+    return np.array(open(path).read().split(), dtype=float)
+
+
+@pytest.mark.parametrize("name", ["c1_phases", "c4_phases", "c2_phases"])
+def test_phases_on_gpu_equal_oracle_flow(name, tmp_path):
+    fx = json.load(open(os.path.join(GOLDEN, name + ".json")))
+    cfg, opts = fx["config"], fx["engine_opts"]
+    seed = cfg["GSL_RNG_SEED"]
+    flags = " ".join(f"-D{k}={v}" for k, v in cfg.items() if k != "GSL_RNG_SEED")
+    exe = make(fx["model"] + ".exe", flags, str(tmp_path / "bin"))
+    wd_gpu, wd_cpu = str(tmp_path / "gpu"), str(tmp_path / "cpu")
+    data = setup_workdir(wd_gpu, fx)
+    setup_workdir(wd_cpu, fx)
+    rows = [tuple(r) for r in fx["rows"]]
+    env = dict(os.environ, GSL_RNG_SEED=str(seed))
+
+    def oracle():
+        e = Oracle(fx["model"], 1, cfg["N_BETA"], n_par=len(rows), seed=seed, rng=RNG_PHILOX)
+        e.set_data(data)
+        return e
+
+    burn = cfg["BURN_IN_ITERATIONS"]
+    steps = {
+        "calibrate_first": lambda: pt_flow.calibrate_first(oracle(), rows, wd_cpu, burn_in_iterations=burn),
+        "calibrate_rest": lambda: pt_flow.calibrate_rest(oracle(), rows, wd_cpu, beta_0=opts.get("beta_0", -0.001),
+                                                         burn_in_iterations=burn),
+        "run": lambda: pt_flow.run(oracle(), rows, wd_cpu, cfg["MAX_ITERATIONS"]),
+    }
+    for phase, cpu_phase in steps.items():
+        subprocess.run([exe, phase], cwd=wd_gpu, env=env, check=True, capture_output=True)
+        cpu_phase()
+        got = numbers(os.path.join(wd_gpu, "calibration_results"))
+        want = numbers(os.path.join(wd_cpu, "calibration_results"))
+        assert got.shape == want.shape, phase
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-300, err_msg=phase)
+    for f in sorted(os.listdir(wd_cpu)):
+        if f.endswith(".prob.dump"):
+            a, b = numbers(os.path.join(wd_gpu, f)), numbers(os.path.join(wd_cpu, f))
+            assert a.shape == b.shape, f
+            np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-300, err_msg=f)
+        elif f.startswith("prob-chain"):
+            a, b = numbers(os.path.join(wd_gpu, f)), numbers(os.path.join(wd_cpu, f))
+            assert a.shape == b.shape, f
+            np.testing.assert_allclose(a, b, rtol=2e-6, atol=1e-12, err_msg=f)
+    r = subprocess.run([exe, "analyse"], cwd=wd_gpu, env=env, check=True, capture_output=True, text=True)
+    m = re.search(r"Model probability ln\(p\(D\|M, I\)\): \[about 10\^(-?\d+)\] (-?[\d.]+)", r.stdout)
+    beta = pt_flow.read_calibration_results(os.path.join(wd_cpu, "calibration_results"), cfg["N_BETA"], len(rows))[0]
+    mean_dl = [np.mean(numbers(os.path.join(wd_cpu, f"prob-chain{k}.dump")).reshape(-1, 2)[:, 1])
+               for k in range(cfg["N_BETA"])]
+    assert abs(float(m.group(2)) - pt_flow.evidence(beta, mean_dl)) < 1e-4
+    for f in ("params_suggested", "calibration_summary", "acceptance_rate.dump.gnuplot", "run_statistics",
+              "marginal_distributions.gnuplot"):
+        assert os.path.getsize(os.path.join(wd_gpu, f)) > 0, f
+
+
+def test_eval_exe_matches_reference_fixture(tmp_path):
+    """eval_<model>.exe (reference apps/eval_main.c) answered by the GPU: 1e-12 against what the
+    unmodified reference printed for the same parameter vectors"""
+    for model in ("simplesin", "pulse_vrot"):
+        fx = json.load(open(os.path.join(GOLDEN, f"eval_{model}.json")))
+        exe = make(f"eval_{model}.exe", "-DN_BETA=1", str(tmp_path / "bin"))
+        wd = str(tmp_path / model)
+        os.makedirs(wd)
+        write_params_file(os.path.join(wd, "params"), [tuple(r) for r in fx["rows"]])
+        data = np.array(fx["data"], dtype=float).reshape(-1, fx["n_cols"])
+        write_data_file(os.path.join(wd, "data"), data)
+        vectors = np.array(fx["params"], dtype=float).reshape(fx["n_vectors"], -1)
+        text = "\n".join(" ".join(repr(float(v)) for v in row) for row in vectors) + "\n"
+        r = subprocess.run([exe], cwd=wd, input=text, capture_output=True, text=True, check=True)
+        out = np.array([l.split() for l in r.stdout.splitlines() if re.match(r"^-?\d", l)], dtype=float)
+        np.testing.assert_allclose(out[:, 0], np.array(fx["prob"], dtype=float), rtol=1e-12)
+        np.testing.assert_allclose(out[:, 1], np.array(fx["prior"], dtype=float), rtol=1e-12, atol=1e-300)
+
+
+def test_several_ensembles_side_by_side(tmp_path):
+    """N_ENSEMBLES=3: one working directory per ensemble; ensemble 0 (chain ids 0..n_beta-1,
+    ensemble id 0) repeats the single-ensemble run exactly, the others differ"""
+    fx = json.load(open(os.path.join(GOLDEN, "c1_phases.json")))
+    base = "-DN_BETA=4 -DBURN_IN_ITERATIONS=600 -DMAX_ITERATIONS=1500"
+    exe1 = make("simplesin.exe", base, str(tmp_path / "bin1"))
+    exe3 = make("simplesin.exe", base + " -DN_ENSEMBLES=3", str(tmp_path / "bin3"))
+    wd1, wd3 = str(tmp_path / "one"), str(tmp_path / "three")
+    setup_workdir(wd1, fx)
+    setup_workdir(wd3, fx)
+    env = dict(os.environ, GSL_RNG_SEED="21")
+    for phase in ("calibrate_first", "calibrate_rest", "run"):
+        subprocess.run([exe1, phase], cwd=wd1, env=env, check=True, capture_output=True)
+        subprocess.run([exe3, phase], cwd=wd3, env=env, check=True, capture_output=True)
+    for f in ("calibration_results", "amplitude-chain-0.prob.dump", "prob-chain3.dump", "acceptance_rate.dump"):
+        assert open(os.path.join(wd1, f)).read() == open(os.path.join(wd3, "ens0", f)).read(), f
+    a = open(os.path.join(wd3, "ens1", "frequency-chain-0.prob.dump")).read()
+    b = open(os.path.join(wd3, "ens2", "frequency-chain-0.prob.dump")).read()
+    assert a != b and a != open(os.path.join(wd3, "ens0", "frequency-chain-0.prob.dump")).read()
+    assert len(a.splitlines()) == 1500
+    r = subprocess.run([exe3, "analyse"], cwd=wd3, env=env, check=True, capture_output=True, text=True)
+    assert "3 independent ensembles" in r.stdout

@@ -1,0 +1,107 @@
+"""The C host layer (apemost_b200/host) pinned against the unmodified reference, without a GPU.
+
+The host layer's sources are compiled UNCHANGED and linked, instead of libapemost_gpu.so, against
+tests/host_shim/apm_gpu_over_oracle.c, which serves the same C ABI from the CPU oracle in
+MT19937 mode (the oracle itself is byte-pinned to the reference by test_oracle_golden.py).  Then
+`<model>.exe calibrate_first / calibrate_rest / run / analyse` must leave exactly the files the
+reference left (tests/golden/*_phases.json, recorded by tests/golden/make_golden.py):
+calibration_results after every phase, every dump, params_suggested, calibration_summary,
+calibration_progress.data, acceptance_rate.dump[.gnuplot], the histograms, the gnuplot script and
+the evidence line.  On a GPU box tests/test_gpu_host.py runs the same executables over the real
+engine."""
+import hashlib
+import json
+import os
+import re
+import subprocess
+
+import pytest
+
+from oracle_binding import build_oracle, write_data_file, write_params_file
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+HOST = os.path.join(ROOT, "apemost_b200", "host")
+BUILD = os.path.join(ROOT, "oracle", "_build")
+FIXTURES = ["c1_phases", "c1_circular_phases", "c1_logistic_phases", "c1_uniform_phases", "c4_phases", "c2_phases"]
+MODEL_IDS = {"simplesin": 0, "simplesin5": 1, "normal": 2, "pulse_vrot": 3, "simplesin2": 4, "pulse": 5}
+
+
+def build_host_over_oracle(name, model, ccflags):
+    """gcc: host layer + shim + liboracle.so -> oracle/_build/host_<name>.exe"""
+    build_oracle()
+    exe = os.path.join(BUILD, f"host_{name}.exe")
+    src = [os.path.join(HOST, f) for f in ("apm_main.c", "apm_chainobj.c", "apm_files.c", "apm_phases.c",
+                                           "apm_analyse.c")]
+    src += [os.path.join(ROOT, "apemost_b200", "compat", "gsl", "gsl_compat.c"),
+            os.path.join(ROOT, "tests", "host_shim", "apm_gpu_over_oracle.c")]
+    cmd = ["gcc", "-O2", "-std=gnu99", "-I", os.path.join(HOST, "include"), "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(ROOT, "apemost_b200", "compat"), "-I", os.path.join(ROOT, "oracle"),
+           f"-DAPM_MODEL_ID={MODEL_IDS[model]}", f'-DAPM_MODEL_NAME="{model}"', *ccflags, *src,
+           os.path.join(BUILD, "liboracle.so"), f"-Wl,-rpath,{BUILD}", "-lm", "-lgomp", "-o", exe]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def sha(path):
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_host_layer_files_byte_identical_to_reference(name, tmp_path):
+    fx = json.load(open(os.path.join(GOLDEN, name + ".json")))
+    cfg = fx["config"]
+    flags = [f"-D{k}={v}" for k, v in cfg.items() if k != "GSL_RNG_SEED"] + fx["ccflags_extra"].split()
+    exe = build_host_over_oracle(name, fx["model"], flags)
+    wd = str(tmp_path)
+    write_params_file(os.path.join(wd, "params"), [tuple(r) for r in fx["rows"]])
+    if fx["data_file"]:
+        open(os.path.join(wd, "data"), "wb").write(open(os.path.join(GOLDEN, fx["data_file"]), "rb").read())
+    else:
+        import numpy as np
+        write_data_file(os.path.join(wd, "data"), np.array(fx["data"], dtype=float).reshape(-1, fx["n_cols"]))
+    env = dict(os.environ, GSL_RNG_SEED=str(cfg["GSL_RNG_SEED"]), APM_TEST_ORACLE_RNG="mt19937")
+    for phase in ("calibrate_first", "calibrate_rest", "run"):
+        subprocess.run([exe, phase], cwd=wd, env=env, check=True, capture_output=True)
+        assert open(os.path.join(wd, "calibration_results")).read() == fx["phases"][phase], phase
+    for fname, want in fx["dumps"].items():
+        lines = open(os.path.join(wd, fname)).read().splitlines()
+        assert len(lines) == want["n_lines"], fname
+        assert lines[:5] == want["head"] and lines[-5:] == want["tail"], fname
+        assert sha(os.path.join(wd, fname)) == want["sha256"], fname
+    r = subprocess.run([exe, "analyse"], cwd=wd, env=env, check=True, capture_output=True, text=True)
+    for fname, want in fx["files"].items():
+        path = os.path.join(wd, fname)
+        assert os.path.exists(path), fname
+        if want["text"] is not None:
+            assert open(path).read() == want["text"], fname
+        assert sha(path) == want["sha256"], fname
+    # what analyse prints: the evidence block and the per-parameter error estimates
+    m = re.search(r"Model probability ln\(p\(D\|M, I\)\): \[about 10\^(-?\d+)\] (-?[\d.]+)", r.stdout)
+    assert m and m.group(0) == fx["evidence_line"]
+    want_block = fx["analyse_stdout"][fx["analyse_stdout"].index("Model probability"):]
+    got = r.stdout[r.stdout.index("Model probability"):]
+    assert got.startswith(want_block)
+    assert re.findall(r"mcmc error estimate of .*", r.stdout) == re.findall(r"mcmc error estimate of .*",
+                                                                           fx["analyse_stdout"])
+    # new: the evidence from the accumulators of `run` agrees with the one from the 7-digit dumps
+    m2 = re.search(r"on-device accumulators \(full precision\): (-?[\d.]+)", r.stdout)
+    assert m2 and abs(float(m2.group(1)) - float(fx["evidence"])) < 2e-4 * max(1.0, abs(float(fx["evidence"])))
+
+
+def test_host_layer_rejects_bad_params_file(tmp_path):
+    """the parser's checks (reference src/mcmc_parser.c:61-82): start outside [min, max] -> exit(1)"""
+    exe = build_host_over_oracle("c1_phases", "simplesin", ["-DN_BETA=4"])
+    wd = str(tmp_path)
+    write_params_file(os.path.join(wd, "params"), [(5.0, 0.0, 3.0, "amplitude", -1.0)])
+    open(os.path.join(wd, "data"), "w").write("0 0\n1 1\n")
+    r = subprocess.run([exe, "calibrate_first"], cwd=wd, capture_output=True, text=True)
+    assert r.returncode == 1 and "start(5.000000) > max(3.000000)" in r.stderr
+
+
+def test_product_host_sources_never_touch_the_oracle():
+    """the product's host layer knows nothing about the oracle (the shim lives in tests/)"""
+    for f in os.listdir(HOST):
+        if f.endswith((".c", ".h")) or f == "Makefile":
+            text = open(os.path.join(HOST, f)).read()
+            assert "orc_" not in text and "oracle" not in text.lower(), f
