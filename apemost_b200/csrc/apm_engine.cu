@@ -162,6 +162,9 @@ static int configure_kernels(apm_gpu * h) {
 	if (occ < 1)
 		return fail(h, APM_ECUDA, "likelihood kernel does not fit on an SM");
 	h->ll_grid = h->sm_count * occ;
+	const int fused_smem = (int) (FUSED_MAX_TABLE_BYTES + 64);
+	CU(cudaFuncSetAttribute(fused_run_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
+	CU(cudaFuncSetAttribute(fused_calibrate_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
 	return APM_OK;
 }
 
@@ -628,6 +631,69 @@ extern "C" int apm_gpu_eval(apm_gpu * h, int n, const double * params, const dou
 	DISPATCH(h->cfg.model_id, eval_t, h, n, params, beta, prob_out, prior_out)
 }
 
+// ------------------------------------------------------------------ path selection
+// fused (one launch per run / calibration, table in shared memory) when the table fits and the
+// likelihood is not sharded over GPUs; tiled otherwise.  cfg.path can force either.
+template<class M> static int model_has_data_t(apm_gpu *) { return M::HAS_DATA ? 1 : 0; }
+static int model_has_data(apm_gpu * h) { DISPATCH(h->cfg.model_id, model_has_data_t, h) }
+
+static int choose_path(apm_gpu * h, int * path) {
+	const int has_data = model_has_data(h);
+	if (has_data < 0)
+		return has_data;
+	const bool fits = !has_data || (size_t) h->n_rows * sizeof(double2) <= FUSED_MAX_TABLE_BYTES;
+	if (h->cfg.path == APM_PATH_FUSED) {
+		if (h->comm)
+			return fail(h, APM_EINVAL, "the fused path cannot be used with a data-sharded likelihood");
+		if (!fits)
+			return fail(h, APM_EINVAL, "the fused path needs the table in shared memory: %lld rows > %lld",
+					h->n_rows, (long long) (FUSED_MAX_TABLE_BYTES / sizeof(double2)));
+		*path = APM_PATH_FUSED;
+	} else if (h->cfg.path == APM_PATH_TILED) {
+		*path = APM_PATH_TILED;
+	} else {
+		*path = (fits && !h->comm) ? APM_PATH_FUSED : APM_PATH_TILED;
+	}
+	return APM_OK;
+}
+
+static void fused_geometry(const apm_gpu * h, bool has_data, int * threads, size_t * smem, FusedArgs * a) {
+	const int passes = (h->cfg.n_beta + FUSED_MAX_WARPS - 1) / FUSED_MAX_WARPS;
+	const int warps = (h->cfg.n_beta + passes - 1) / passes;
+	*threads = 32 * warps;
+	const size_t table = has_data ? (size_t) h->n_rows * sizeof(double2) : 0;
+	*smem = ((table + 15) & ~(size_t) 15) + 16;
+	memset(a, 0, sizeof(*a));
+	a->data = has_data ? h->d_data : nullptr;
+	a->n_rows = has_data ? (int) h->n_rows : 0;
+	a->xabsmax = reinterpret_cast<const double *>(h->d_xabsmax);
+}
+
+template<class M>
+static int run_fused_t(apm_gpu * h, long long n_rounds, int n_swap) {
+	int threads = 0;
+	size_t smem = 0;
+	FusedArgs a;
+	fused_geometry(h, M::HAS_DATA, &threads, &smem, &a);
+	a.n_rounds = n_rounds;
+	a.n_swap = n_swap;
+	h->ev_used = 0;
+	cudaEvent_t t0 = next_event(h), t1 = next_event(h);
+	CU(cudaEventRecord(t0, h->stream));
+	fused_run_kernel<M><<<h->cfg.n_ensembles, threads, smem, h->stream>>>(h->S, a);
+	h->launches++;
+	CU(cudaEventRecord(t1, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	CU(cudaGetLastError());
+	float tot = 0;
+	cudaEventElapsedTime(&tot, t0, t1);
+	h->last_total_ms = tot;
+	h->last_ll_ms = 0;
+	h->last_ll_launches = 0;
+	h->last_path = APM_PATH_FUSED;
+	return APM_OK;
+}
+
 // ------------------------------------------------------------------ run (tiled path)
 static int setup_trace(apm_gpu * h, long long n_steps, const apm_gpu_trace_cfg * tr) {
 	h->tr_prob_rows = h->tr_param_rows = 0;
@@ -714,6 +780,13 @@ extern "C" int apm_gpu_run(apm_gpu * h, long long n_rounds, int n_swap, const ap
 		return rc;
 	if (n_rounds == 0)
 		return APM_OK;
+	int path = APM_PATH_TILED;
+	rc = choose_path(h, &path);
+	if (rc != APM_OK)
+		return rc;
+	if (path == APM_PATH_FUSED) {
+		DISPATCH(h->cfg.model_id, run_fused_t, h, n_rounds, n_swap)
+	}
 	DISPATCH(h->cfg.model_id, run_tiled_t, h, n_rounds, n_swap)
 }
 
@@ -757,13 +830,30 @@ static int calibrate_t(apm_gpu * h, const apm_gpu_calib_cfg * cfg, int * status,
 	h->ev_used = 0;
 	cudaEvent_t t0 = next_event(h), t1 = next_event(h);
 	CU(cudaEventRecord(t0, h->stream));
+	int path = APM_PATH_TILED;
+	int rcp = choose_path(h, &path);
+	if (rcp != APM_OK)
+		return rcp;
+	if (path == APM_PATH_FUSED) {
+		int threads = 0;
+		size_t smem = 0;
+		FusedArgs f;
+		fused_geometry(h, M::HAS_DATA, &threads, &smem, &f);
+		f.cal = a.cal;
+		f.select = h->d_select;
+		fused_calibrate_kernel<M><<<h->cfg.n_ensembles, threads, smem, h->stream>>>(h->S, f);
+		h->launches++;
+		n_selected = 0; // skips the tiled loop below
+	}
 	// the likelihood kernel walks a compacted list of the chains still calibrating; the
 	// control kernel of step s fills list (s + 1) & 1 and clears list s & 1
 	CU(cudaMemsetAsync(h->S.act_n, 0, 2 * sizeof(int), h->stream));
-	a.flags = ADV_CALIB_BEGIN;
-	a.act_w = 0;
-	advance_kernel<M><<<h->cfg.n_ensembles, ADV_THREADS, 0, h->stream>>>(state_for_advance(h), a);
-	h->launches++;
+	if (path == APM_PATH_TILED) {
+		a.flags = ADV_CALIB_BEGIN;
+		a.act_w = 0;
+		advance_kernel<M><<<h->cfg.n_ensembles, ADV_THREADS, 0, h->stream>>>(state_for_advance(h), a);
+		h->launches++;
+	}
 	int active = n_selected;
 	const int block = 200;
 	long long step = 0;
@@ -798,7 +888,7 @@ static int calibrate_t(apm_gpu * h, const apm_gpu_calib_cfg * cfg, int * status,
 	float tot = 0;
 	cudaEventElapsedTime(&tot, t0, t1);
 	h->last_total_ms = tot;
-	h->last_path = APM_PATH_TILED;
+	h->last_path = path;
 	// per-chain status
 	std::vector<CalState> cs(h->n_chains);
 	CU(cudaMemcpy(cs.data(), h->S.cal, h->n_chains * sizeof(CalState), cudaMemcpyDeviceToHost));

@@ -380,6 +380,161 @@ __global__ void __launch_bounds__(ADV_THREADS) advance_kernel(const DevState S, 
 	}
 }
 
+// ------------------------------------------------------------------ fused small-table path
+// One CTA per ensemble, one warp per chain (warps loop when the ladder is longer than the
+// CTA), the whole data table resident in shared memory (one TMA bulk copy per launch).  A
+// launch executes n_rounds x (n_swap Metropolis steps of every chain + the ensemble's swap),
+// or complete calibrations, without returning to the host: per step a warp evaluates its
+// chain's likelihood over the table (lane-strided rows, 4 accumulators, fp64 butterfly) and
+// lane 0 runs the very same chain_* functions the control kernel of the tiled path runs.
+constexpr int FUSED_MAX_WARPS = 16;
+constexpr size_t FUSED_MAX_TABLE_BYTES = 200 * 1024;
+
+struct FusedArgs {
+	const double * data;     // [n_rows][2]
+	int n_rows;
+	const double * xabsmax;
+	long long n_rounds;      // run
+	int n_swap;
+	CalibCfgDev cal;         // calibrate
+	const unsigned char * select;
+};
+
+__device__ __forceinline__ const double2 * fused_stage_table(const FusedArgs & a, unsigned char * smem) {
+	double2 * sdata = reinterpret_cast<double2 *>(smem);
+	uint64_t * bar = reinterpret_cast<uint64_t *>(smem + (((size_t) a.n_rows * sizeof(double2) + 15) & ~(size_t) 15));
+	if (a.n_rows > 0) {
+		if (threadIdx.x == 0) {
+			mbar_init(bar, 1);
+			mbar_fence_init();
+			// bulk copies of at most 32 KB each, all completing on the one barrier
+			const uint32_t total = (uint32_t) a.n_rows * sizeof(double2);
+			mbar_arrive_expect_tx(bar, total);
+			for (uint32_t off = 0; off < total; off += 32768u) {
+				const uint32_t n = min(32768u, total - off);
+				tma_bulk_g2s(reinterpret_cast<unsigned char *>(sdata) + off,
+						reinterpret_cast<const unsigned char *>(a.data) + off, n, bar);
+			}
+		}
+		__syncthreads();
+		mbar_wait(bar, 0);
+	}
+	return sdata;
+}
+
+// sum over the table of the model's row terms for chain g's pending proposal; every lane
+// returns the same bits (butterfly of commutative adds)
+template<class M>
+__device__ __forceinline__ double fused_loglik(const DevState & S, int g, const double2 * sdata, int n_rows,
+		double xub, int lane) {
+	if (!M::HAS_DATA)
+		return 0.0;
+	typename M::Prep q;
+	M::prep(q, S.prop + (size_t) g * S.n_par, S.n_par, S.model_const);
+	double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+	int i = lane;
+	if (M::fast_ok(q, xub)) {
+		for (; i + 96 < n_rows; i += 128) {
+			const double2 r0 = sdata[i], r1 = sdata[i + 32], r2 = sdata[i + 64], r3 = sdata[i + 96];
+			a0 = M::accum_fast(a0, q, r0.x, r0.y);
+			a1 = M::accum_fast(a1, q, r1.x, r1.y);
+			a2 = M::accum_fast(a2, q, r2.x, r2.y);
+			a3 = M::accum_fast(a3, q, r3.x, r3.y);
+		}
+		for (; i < n_rows; i += 32) {
+			const double2 r = sdata[i];
+			a0 = M::accum_fast(a0, q, r.x, r.y);
+		}
+	} else {
+		for (; i < n_rows; i += 32) {
+			const double2 r = sdata[i];
+			a0 = M::accum(a0, q, r.x, r.y);
+		}
+	}
+	return warp_sum((a0 + a1) + (a2 + a3));
+}
+
+template<class M>
+__global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_run_kernel(const DevState S, const FusedArgs a) {
+	extern __shared__ __align__(128) unsigned char fused_smem[];
+	const double2 * sdata = fused_stage_table(a, fused_smem);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+	const int ens = blockIdx.x, base = ens * S.n_beta;
+	const double xub = M::HAS_DATA ? *a.xabsmax : 0.0;
+	for (int k = warp; k < S.n_beta; k += n_warps)
+		if (lane == 0)
+			chain_propose(S, base + k, S.n_par);
+	__syncwarp();
+	long long step = 0;
+	for (long long round = 0; round < a.n_rounds; round++) {
+		for (int sub = 0; sub < a.n_swap; sub++, step++) {
+			const bool last_of_round = sub + 1 == a.n_swap;
+			for (int k = warp; k < S.n_beta; k += n_warps) {
+				const int g = base + k;
+				const double sum = fused_loglik<M>(S, g, sdata, a.n_rows, xub, lane);
+				if (lane == 0) {
+					chain_finalize<M>(S, g, M::sum0(S.prop + (size_t) g * S.n_par) + sum);
+					chain_record(S, g, step);
+					if (!last_of_round)
+						chain_propose(S, g, S.n_par);
+				}
+				__syncwarp();
+			}
+		}
+		// tempering_interaction for this ensemble, then the proposals of the next round
+		__syncthreads();
+		if (threadIdx.x == 0)
+			ensemble_swap(S, ens);
+		__syncthreads();
+		if (round + 1 < a.n_rounds) {
+			for (int k = warp; k < S.n_beta; k += n_warps)
+				if (lane == 0)
+					chain_propose(S, base + k, S.n_par);
+			__syncwarp();
+		}
+	}
+}
+
+// markov_chain_calibrate of every selected chain, start to finish in one launch: the per-chain
+// state machine of apm_chain.cuh needs nothing from other chains
+template<class M>
+__global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_calibrate_kernel(const DevState S, const FusedArgs a) {
+	extern __shared__ __align__(128) unsigned char fused_smem[];
+	const double2 * sdata = fused_stage_table(a, fused_smem);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+	const int base = blockIdx.x * S.n_beta;
+	const double xub = M::HAS_DATA ? *a.xabsmax : 0.0;
+	for (int k = warp; k < S.n_beta; k += n_warps) {
+		const int g = base + k;
+		if (lane == 0) {
+			S.pend[g] = PEND_NONE;
+			S.cal[g].phase = CAL_IDLE;
+			if (a.select == nullptr || a.select[g]) {
+				atomicAdd(S.n_active, 1);
+				cal_begin(S, g, a.cal);
+				const int kind = cal_next_kind(S, g);
+				if (kind != PEND_NONE)
+					chain_propose(S, g, kind);
+			} else {
+				S.cal[g].status = -1;
+			}
+		}
+		__syncwarp();
+		while (S.pend[g] != PEND_NONE) { // same value for the whole warp
+			const double sum = fused_loglik<M>(S, g, sdata, a.n_rows, xub, lane);
+			__syncwarp();
+			if (lane == 0) {
+				chain_finalize<M>(S, g, M::sum0(S.prop + (size_t) g * S.n_par) + sum);
+				cal_after_step(S, g, a.cal);
+				const int kind = cal_next_kind(S, g);
+				if (kind != PEND_NONE)
+					chain_propose(S, g, kind);
+			}
+			__syncwarp();
+		}
+	}
+}
+
 // ------------------------------------------------------------------ eval
 template<class M>
 __global__ void eval_finish_kernel(int n, int n_par, const double * params, const double * beta,

@@ -138,8 +138,12 @@ def test_linearity_in_rows(capi):
 
 
 # ---------------------------------------------------------------- sampler trajectories
-def _pair(capi, model, n_ens, n_beta, n_par=None, seed=1, **kw):
-    return (capi.Engine(model, n_ens, n_beta, n_par=n_par, seed=seed, **kw),
+PATHS = [pytest.param(1, id="tiled"), pytest.param(2, id="fused")]  # APM_PATH_TILED / APM_PATH_FUSED
+
+
+def _pair(capi, model, n_ens, n_beta, n_par=None, seed=1, path=0, **kw):
+    """the CUDA engine (on the requested kernel path) and the CPU oracle, configured alike"""
+    return (capi.Engine(model, n_ens, n_beta, n_par=n_par, seed=seed, path=path, **kw),
             Oracle(model, n_ens, n_beta, n_par=n_par, seed=seed, rng=RNG_PHILOX, **kw))
 
 
@@ -150,12 +154,13 @@ def _compare_state(st_gpu, st_cpu):
         np.testing.assert_allclose(st_gpu[k], st_cpu[k], rtol=RTOL_TRAJ, atol=1e-300, err_msg=k)
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("quirks", [3, 0])
 @pytest.mark.parametrize("name,kw", [("c1_phases", {}), ("c1_circular_phases", dict(circular_mask=4)),
                                       ("c1_logistic_phases", dict(proposal=1)),
                                       ("c1_uniform_phases", dict(proposal=2)), ("c4_phases", {}),
                                       ("c2_phases", {})])
-def test_run_trajectory_equals_oracle(capi, name, kw, quirks):
+def test_run_trajectory_equals_oracle(capi, name, kw, quirks, path):
     """3 ensembles x the fixture's ladder, started from the reference's own calibration_results:
     the whole run (steps, swaps, best tracking, traces, accumulators) against the oracle"""
     fx = load(name)
@@ -164,7 +169,7 @@ def test_run_trajectory_equals_oracle(capi, name, kw, quirks):
     data = (np.loadtxt(os.path.join(GOLDEN, fx["data_file"])) if fx["data_file"]
             else np.array(fx["data"], dtype=float).reshape(-1, 2))
     cal = np.array(fx["phases"]["calibrate_rest"].split(), dtype=float).reshape(n_beta, 1 + 2 * n_par)
-    engines = _pair(capi, fx["model"], n_ens, n_beta, n_par=n_par, seed=17, quirks=quirks, **kw)
+    engines = _pair(capi, fx["model"], n_ens, n_beta, n_par=n_par, seed=17, quirks=quirks, path=path, **kw)
     res = []
     for eng in engines:
         eng.set_data(data)
@@ -175,6 +180,7 @@ def test_run_trajectory_equals_oracle(capi, name, kw, quirks):
         eng.run(8, 40, prob_every=1, params_chains=2)
         res.append((eng.read_trace(), eng.get_chains(), eng.get_stats()))
     (tr_g, st_g, ac_g), (tr_c, st_c, ac_c) = res
+    assert engines[0].last_path() == path
     _compare_state(st_g, st_c)
     for k in ("prob", "prob_minus_prior", "params"):
         np.testing.assert_allclose(tr_g[k], tr_c[k], rtol=RTOL_TRAJ, atol=1e-300, err_msg=k)
@@ -184,14 +190,15 @@ def test_run_trajectory_equals_oracle(capi, name, kw, quirks):
     assert st_g["swapcount"].sum() > 0, "the test must exercise accepted swaps"
 
 
-def test_run_continues_across_calls(capi):
+@pytest.mark.parametrize("path", PATHS)
+def test_run_continues_across_calls(capi, path):
     """two runs of 4 rounds == one run of 8 rounds (state, RNG position and swap stream persist)"""
     fx = load("c1_phases")
     rows = [tuple(r) for r in fx["rows"]]
     data = np.loadtxt(os.path.join(GOLDEN, fx["data_file"]))
     outs = []
     for split in (False, True):
-        e = capi.Engine("simplesin", 2, 4, seed=3)
+        e = capi.Engine("simplesin", 2, 4, seed=3, path=path)
         e.set_data(data)
         pt_flow.setup_chains(e, rows)
         e.set_chains(0, 8, beta=np.tile([1.0, 0.6, 0.3, 0.1], 2))
@@ -215,6 +222,36 @@ def test_single_chain_ladder_never_swaps(capi):
         assert eng.get_chains()["swapcount"].sum() == 0
 
 
+def test_fused_path_refuses_a_table_that_does_not_fit(capi):
+    e = capi.Engine("simplesin5", 1, 2, path=2)
+    e.set_data(lightcurve(20_000))
+    e.set_bounds(SS5_LO, SS5_HI)
+    with pytest.raises(Exception, match="shared memory"):
+        e.run(1, 1)
+
+
+def test_fused_ladder_longer_than_the_cta(capi):
+    """40 rungs: warps take several chains each (FUSED_MAX_WARPS = 16); fused == tiled == oracle"""
+    data = lightcurve(1500)
+    n_ens, n_beta = 2, 40
+    n = n_ens * n_beta
+    rng = np.random.default_rng(5)
+    params = np.tile([1.3, 7.25, 0.31 * 2 * np.pi, 0.2], (n, 1)) + rng.normal(0, 1e-4, (n, 4))
+    beta = np.tile(pt_flow.chebyshev_ladder(n_beta, 0.01), n_ens)
+    steps = np.tile([2e-2, 3e-5, 2e-2, 1e-2], (n, 1)) * beta[:, None] ** -0.5
+    states = []
+    for path in (1, 2):
+        for eng in _pair(capi, "simplesin5", n_ens, n_beta, seed=31, path=path)[:1 if path == 2 else 2]:
+            eng.set_data(data)
+            eng.set_bounds(SS5_LO, SS5_HI)
+            eng.set_chains(0, n, beta=beta, params=params, steps=steps, params_best=params)
+            eng.run(5, 12, prob_every=1, params_chains=1)
+            states.append(eng.get_chains())
+    _compare_state(states[0], states[1])
+    _compare_state(states[2], states[1])
+    assert states[2]["swapcount"].sum() > 0
+
+
 def test_big_table_run_trajectory(capi):
     """a table that spans many chunks and row splits (300k rows), 2 x 8 chains"""
     data = lightcurve(300_000)
@@ -236,8 +273,9 @@ def test_big_table_run_trajectory(capi):
 
 
 # ---------------------------------------------------------------- calibration
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("name", ["c1_phases", "c4_phases", "c2_phases"])
-def test_calibration_trajectory_equals_oracle(capi, name):
+def test_calibration_trajectory_equals_oracle(capi, name, path):
     """markov_chain_calibrate (burn_in + _orig) for every chain of 2 ensembles concurrently:
     final step widths, positions, counters and the progress rows against the oracle"""
     fx = load(name)
@@ -247,7 +285,8 @@ def test_calibration_trajectory_equals_oracle(capi, name):
             else np.array(fx["data"], dtype=float).reshape(-1, 2))
     cal = np.array(fx["phases"]["calibrate_rest"].split(), dtype=float).reshape(n_beta, 1 + 2 * n_par)
     res = []
-    for eng in _pair(capi, fx["model"], n_ens, n_beta, n_par=n_par, seed=23):
+    engines = _pair(capi, fx["model"], n_ens, n_beta, n_par=n_par, seed=23, path=path)
+    for eng in engines:
         eng.set_data(data)
         start, lo, hi, names, step = pt_flow.setup_chains(eng, rows)
         n = n_ens * n_beta
@@ -259,6 +298,7 @@ def test_calibration_trajectory_equals_oracle(capi, name):
         status, prog = eng.calibrate(burn_in_iterations=600, progress_capacity=100000)
         res.append((status, prog, eng.get_chains()))
     (s_g, p_g, st_g), (s_c, p_c, st_c) = res
+    assert engines[0].last_path() == path
     np.testing.assert_array_equal(s_g, s_c)
     assert (s_g == 0).all()
     _compare_state(st_g, st_c)
@@ -269,13 +309,14 @@ def test_calibration_trajectory_equals_oracle(capi, name):
         np.testing.assert_allclose(a[3:], b[3:], rtol=RTOL_TRAJ)
 
 
-def test_calibration_selection_and_failure_status(capi):
+@pytest.mark.parametrize("path", PATHS)
+def test_calibration_selection_and_failure_status(capi, path):
     """only selected chains move; a chain whose acceptance rate cannot be brought down (flat
     likelihood) ends with the reference's 'iteration limit' failure (markov_chain_calibrate.c
     :1169-1174) reported per chain instead of exit(1)"""
     rows = [(100.0, -10.0, 10000.0, "x", -1.0)]
     res = []
-    for eng in _pair(capi, "normal", 1, 3, seed=4):
+    for eng in _pair(capi, "normal", 1, 3, seed=4, path=path):
         eng.set_data(np.zeros((2, 2)))
         pt_flow.setup_chains(eng, rows)
         eng.set_chains(0, 3, beta=[1.0, 0.5, 0.001])
