@@ -25,11 +25,35 @@ static unsigned circular_mask(void) {
 	return mask;
 }
 
-static void engine_config(apm_gpu_config * cfg, int n_ens, int n_beta, int n_par) {
+/* Several processes (one per GPU) can share one working directory: the N_ENSEMBLES ensembles are
+ * dealt out in contiguous blocks by rank, every ensemble keeps its global number (its ens<e>/
+ * directory and its random streams), so the files do not depend on how many processes ran.
+ * Rank and size come from APM_RANK / APM_WORLD_SIZE or, under torchrun, RANK / WORLD_SIZE;
+ * the device from APM_DEVICE or LOCAL_RANK.  Independent ensembles need no communication. */
+static int env_int(const char * a, const char * b, int fallback) {
+	const char * v = getenv(a);
+	if (v == NULL && b != NULL)
+		v = getenv(b);
+	return v != NULL ? atoi(v) : fallback;
+}
+
+static void ensemble_share(int * first, int * count) {
+	const int world = env_int("APM_WORLD_SIZE", "WORLD_SIZE", 1), rank = env_int("APM_RANK", "RANK", 0);
+	const int n = N_ENSEMBLES;
+	if (world < 1 || rank < 0 || rank >= world) {
+		fprintf(stderr, "bad rank %d / world size %d\n", rank, world);
+		exit(1);
+	}
+	*first = (int) ((long long) n * rank / world);
+	*count = (int) ((long long) n * (rank + 1) / world) - *first;
+}
+
+static void engine_config(apm_gpu_config * cfg, int ens_first, int n_ens, int n_beta, int n_par) {
 	const char * seed = getenv("GSL_RNG_SEED"); /* the reference's seed variable (src/mcmc.c:27-35) */
-	const char * dev = getenv("APM_DEVICE");
 	memset(cfg, 0, sizeof(*cfg));
-	cfg->device = dev ? atoi(dev) : 0;
+	cfg->device = env_int("APM_DEVICE", "LOCAL_RANK", 0);
+	cfg->ensemble_id_offset = ens_first;
+	cfg->chain_id_offset = ens_first * n_beta;
 	cfg->model_id = APM_MODEL_ID;
 	cfg->n_ensembles = n_ens;
 	cfg->n_beta = n_beta;
@@ -115,7 +139,11 @@ apm_session * apm_session_open(void) {
 	size_t n, nv;
 	int g;
 	assert(s != NULL);
-	s->n_ens = N_ENSEMBLES;
+	ensemble_share(&s->ens_first, &s->n_ens);
+	if (s->n_ens < 1) {
+		printf("no ensemble for this process (N_ENSEMBLES = %d)\n", (int) N_ENSEMBLES);
+		exit(0);
+	}
 	s->n_beta = N_BETA;
 	s->n_chains = s->n_ens * s->n_beta;
 	s->chains = (mcmc **) calloc(s->n_chains, sizeof(mcmc *));
@@ -144,7 +172,7 @@ apm_session * apm_session_open(void) {
 	s->pacc = (unsigned long long *) calloc(nv, sizeof(unsigned long long));
 	s->prej = (unsigned long long *) calloc(nv, sizeof(unsigned long long));
 
-	engine_config(&cfg, s->n_ens, s->n_beta, s->n_par);
+	engine_config(&cfg, s->ens_first, s->n_ens, s->n_beta, s->n_par);
 	if (apm_gpu_create(&s->gpu, &cfg) != APM_OK) {
 		fprintf(stderr, "could not start the GPU engine: %s\n", apm_gpu_last_error(NULL));
 		exit(1);
@@ -327,7 +355,7 @@ void calibrate_first(void) {
 	calibrate_selected(s, select, 0, &rows, &n_rows);
 	apm_session_pull(s, 0, s->n_chains);
 	for (e = 0; e < s->n_ens; e++) {
-		apm_set_output_dir(e);
+		apm_set_output_dir(s->ens_first + e);
 		apm_write_calibration_progress(rows, n_rows, which[e]);
 		write_calibrations_file(apm_ensemble(s, e), 1);
 		write_params_file(apm_ensemble(s, e)[0]);
@@ -368,7 +396,7 @@ void calibrate_rest(void) {
 #endif
 
 	for (e = 0; e < n_ens; e++) {
-		apm_set_output_dir(e);
+		apm_set_output_dir(s->ens_first + e);
 		read_calibration_file(apm_ensemble(s, e), 1);
 		factors[e] = gsl_vector_alloc(s->n_par);
 		gsl_vector_set_all(factors[e], 1);
@@ -437,7 +465,7 @@ void calibrate_rest(void) {
 		dump_vectorln(get_steps(s->chains[i]));
 	}
 	for (e = 0; e < n_ens; e++) {
-		apm_set_output_dir(e);
+		apm_set_output_dir(s->ens_first + e);
 		if (rows != NULL && !skip)
 			apm_write_calibration_progress(rows, n_rows, e * n_beta + n_beta - 1);
 		write_calibration_summary(apm_ensemble(s, e), n_beta);
@@ -504,7 +532,7 @@ static void write_run_statistics(apm_session * s) {
 	apm_gpu_check(s, apm_gpu_get_stats(s->gpu, cnt, sdl, sp, sp2), "reading the accumulators");
 	for (e = 0; e < s->n_ens; e++) {
 		FILE * f;
-		apm_set_output_dir(e);
+		apm_set_output_dir(s->ens_first + e);
 		f = fopen(apm_out_path("run_statistics"), "w");
 		if (f == NULL)
 			continue;
@@ -550,7 +578,7 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 
 	for (e = 0; e < n_ens; e++) {
 		mcmc ** c = apm_ensemble(s, e);
-		apm_set_output_dir(e);
+		apm_set_output_dir(s->ens_first + e);
 		read_calibration_file(c, n_beta);
 		for (i = 0; i < (trace.params_chains == 2 ? n_beta : 1); i++)
 			mcmc_open_dump_files(c[i], "-chain", i, mode);

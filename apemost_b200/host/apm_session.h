@@ -21,7 +21,8 @@
 #endif
 
 typedef struct {
-	int n_ens, n_beta, n_par, n_chains;
+	int ens_first;           /* global number of this process's first ensemble */
+	int n_ens, n_beta, n_par, n_chains; /* n_ens: ensembles handled by this process */
 	mcmc ** chains;          /* [n_chains]: chains[e * n_beta + k], k = 0 is beta = 1 */
 	apm_gpu * gpu;
 	/* flat staging buffers, chain-major like the ABI */

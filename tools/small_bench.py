@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Chain-steps/s of the small configurations of BASELINE.json (C1 simplesin on the reference's
+own light curve, C2 normal / 64 chains, C4 pulse_vrot) on both kernel paths, beside the CPU oracle.
+  python tools/small_bench.py            (on the GPU box) -> gpurun_out/small_bench.json"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import pt_flow  # noqa: E402
+from apemost_b200 import capi  # noqa: E402
+from oracle_binding import Oracle, RNG_PHILOX  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def case(name, n_ens, n_beta=None):
+    fx = json.load(open(os.path.join(GOLDEN, name + ".json")))
+    rows = [tuple(r) for r in fx["rows"]]
+    data = (np.loadtxt(os.path.join(GOLDEN, fx["data_file"])) if fx["data_file"]
+            else np.array(fx["data"], dtype=float).reshape(-1, 2))
+    nb0 = fx["config"]["N_BETA"]
+    cal = np.array(fx["phases"]["calibrate_rest"].split(), dtype=float).reshape(nb0, 1 + 2 * len(rows))
+    n_beta = n_beta or nb0
+    beta = pt_flow.chebyshev_ladder(n_beta, cal[-1, 0])
+    steps = cal[0, 1:1 + len(rows)][None, :] * beta[:, None] ** -0.5
+    params = np.tile(cal[0, 1 + len(rows):], (n_beta, 1))
+    return fx["model"], rows, data, beta, steps, params
+
+
+def time_engine(eng, rows, data, beta, steps, params, n_ens, rounds, n_swap):
+    eng.set_data(data)
+    pt_flow.setup_chains(eng, rows)
+    pt_flow.apply_calibration(eng, 0, np.tile(beta, n_ens), np.tile(steps, (n_ens, 1)), np.tile(params, (n_ens, 1)))
+    eng.run(1, n_swap)
+    t0 = time.perf_counter()
+    eng.run(rounds, n_swap)
+    dt = time.perf_counter() - t0
+    return eng.n_chains * rounds * n_swap / dt
+
+
+def main():
+    out = {}
+    for label, name, n_ens, n_beta in [("C1 simplesin testlc.dat 1x20", "c1_phases", 1, 20),
+                                       ("C1 simplesin testlc.dat 64x20", "c1_phases", 64, 20),
+                                       ("C2 normal 1x64", "c2_phases", 1, 64),
+                                       ("C2 normal 64x64", "c2_phases", 64, 64),
+                                       ("C4 pulse_vrot 200 rows 1x20", "c4_phases", 1, 20),
+                                       ("C4 pulse_vrot 200 rows 64x20", "c4_phases", 64, 20)]:
+        model, rows, data, beta, steps, params = case(name, n_ens, n_beta)
+        n_swap = max(1, 2000 // n_beta)
+        res = {}
+        for pname, path in (("tiled", 1), ("fused", 2)):
+            e = capi.Engine(model, n_ens, n_beta, n_par=len(rows), seed=1, path=path)
+            res[pname] = time_engine(e, rows, data, beta, steps, params, n_ens, 20 if path == 1 else 200, n_swap)
+            e.close()
+        threads = os.cpu_count()
+        o = Oracle(model, min(n_ens, 4), n_beta, n_par=len(rows), seed=1, rng=RNG_PHILOX, n_threads=threads)
+        res["cpu_oracle"] = time_engine(o, rows, data, beta, steps, params, min(n_ens, 4), 5, n_swap)
+        res["cpu_threads"] = threads
+        o1 = Oracle(model, 1, n_beta, n_par=len(rows), seed=1, rng=RNG_PHILOX, n_threads=1)
+        res["cpu_oracle_1thread"] = time_engine(o1, rows, data, beta, steps, params, 1, 5, n_swap)
+        out[label] = res
+        print(label, {k: (f"{v:.4g}" if isinstance(v, float) else v) for k, v in res.items()}, flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "small_bench.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
