@@ -59,6 +59,8 @@ struct DevState {
 	int proposal;
 	unsigned circular_mask, quirks;
 	int chain_id_offset, ensemble_id_offset;
+	int g_base;        // added to a chain index where it is reported (progress rows); != 0 only in
+	                   // the fused path, whose DevState is indexed by position in the ensemble
 	double model_const[4];
 	// mcmc struct members (reference src/mcmc_struct.h:30-106)
 	double * params, *params_best, *steps;
@@ -475,7 +477,7 @@ APM_D void cal_after_step(const DevState & S, int g, const CalibCfgDev & cfg) {
 				if ((long long) slot < S.progress_cap) {
 					double acc = (double) S.pacc[(size_t) g * n + i], rej = (double) S.prej[(size_t) g * n + i];
 					ProgressRow & row = S.progress[slot];
-					row.chain = g;
+					row.chain = S.g_base + g;
 					row.param = i;
 					row.iter = c.iter;
 					row.step_normalised = S.steps[(size_t) g * n + i] / (S.pmax[i] - S.pmin[i]);

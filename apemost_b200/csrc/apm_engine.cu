@@ -162,7 +162,7 @@ static int configure_kernels(apm_gpu * h) {
 	if (occ < 1)
 		return fail(h, APM_ECUDA, "likelihood kernel does not fit on an SM");
 	h->ll_grid = h->sm_count * occ;
-	const int fused_smem = (int) (FUSED_MAX_TABLE_BYTES + 64);
+	const int fused_smem = (int) FUSED_SMEM_LIMIT;
 	CU(cudaFuncSetAttribute(fused_run_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
 	CU(cudaFuncSetAttribute(fused_calibrate_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
 	return APM_OK;
@@ -641,13 +641,15 @@ static int choose_path(apm_gpu * h, int * path) {
 	const int has_data = model_has_data(h);
 	if (has_data < 0)
 		return has_data;
-	const bool fits = !has_data || (size_t) h->n_rows * sizeof(double2) <= FUSED_MAX_TABLE_BYTES;
+	const size_t need = fused_table_bytes(has_data ? h->n_rows : 0) + fused_state_bytes(h->cfg.n_beta, h->cfg.n_par);
+	const bool fits = need <= FUSED_SMEM_LIMIT && (!has_data || h->n_rows < (1ll << 24));
 	if (h->cfg.path == APM_PATH_FUSED) {
 		if (h->comm)
 			return fail(h, APM_EINVAL, "the fused path cannot be used with a data-sharded likelihood");
 		if (!fits)
-			return fail(h, APM_EINVAL, "the fused path needs the table in shared memory: %lld rows > %lld",
-					h->n_rows, (long long) (FUSED_MAX_TABLE_BYTES / sizeof(double2)));
+			return fail(h, APM_EINVAL, "the fused path needs the table and one ensemble's state in shared memory: "
+					"%lld rows x %d chains need %lld bytes > %lld", h->n_rows, h->cfg.n_beta, (long long) need,
+					(long long) FUSED_SMEM_LIMIT);
 		*path = APM_PATH_FUSED;
 	} else if (h->cfg.path == APM_PATH_TILED) {
 		*path = APM_PATH_TILED;
@@ -658,11 +660,13 @@ static int choose_path(apm_gpu * h, int * path) {
 }
 
 static void fused_geometry(const apm_gpu * h, bool has_data, int * threads, size_t * smem, FusedArgs * a) {
-	const int passes = (h->cfg.n_beta + FUSED_MAX_WARPS - 1) / FUSED_MAX_WARPS;
-	const int warps = (h->cfg.n_beta + passes - 1) / passes;
-	*threads = 32 * warps;
-	const size_t table = has_data ? (size_t) h->n_rows * sizeof(double2) : 0;
-	*smem = ((table + 15) & ~(size_t) 15) + 16;
+	if (has_data) { // a warp per chain, the ladder dealt evenly over as few passes as possible
+		const int passes = (h->cfg.n_beta + FUSED_MAX_WARPS - 1) / FUSED_MAX_WARPS;
+		*threads = 32 * ((h->cfg.n_beta + passes - 1) / passes);
+	} else {        // a thread per chain
+		*threads = std::min(FUSED_MAX_WARPS * 32, 32 * ((h->cfg.n_beta + 31) / 32));
+	}
+	*smem = fused_table_bytes(has_data ? h->n_rows : 0) + fused_state_bytes(h->cfg.n_beta, h->cfg.n_par);
 	memset(a, 0, sizeof(*a));
 	a->data = has_data ? h->d_data : nullptr;
 	a->n_rows = has_data ? (int) h->n_rows : 0;

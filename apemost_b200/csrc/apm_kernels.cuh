@@ -381,14 +381,36 @@ __global__ void __launch_bounds__(ADV_THREADS) advance_kernel(const DevState S, 
 }
 
 // ------------------------------------------------------------------ fused small-table path
-// One CTA per ensemble, one warp per chain (warps loop when the ladder is longer than the
-// CTA), the whole data table resident in shared memory (one TMA bulk copy per launch).  A
-// launch executes n_rounds x (n_swap Metropolis steps of every chain + the ensemble's swap),
-// or complete calibrations, without returning to the host: per step a warp evaluates its
-// chain's likelihood over the table (lane-strided rows, 4 accumulators, fp64 butterfly) and
-// lane 0 runs the very same chain_* functions the control kernel of the tiled path runs.
+// One CTA per ensemble, the whole data table AND the ensemble's chain state resident in shared
+// memory for the duration of the launch (one TMA bulk copy for the table, a cooperative copy
+// in / copy out for the state).  A launch executes n_rounds x (n_swap Metropolis steps of every
+// chain + the ensemble's swap), or complete calibrations, without returning to the host.
+//   models with data: one warp per chain (warps loop when the ladder is longer than the CTA);
+//     per step the warp evaluates its chain's likelihood over the table (lane-strided rows,
+//     4 accumulators, fp64 butterfly), its lanes draw the coordinates of the next proposal in
+//     parallel, and lane 0 runs the very same chain_* functions as the tiled path's control kernel;
+//   data-free models (apps/normal.c): one thread per chain.
+// The chain_* functions are used unchanged: they get a DevState whose pointers address the
+// shared-memory copies, indexed by the chain's position in the ensemble; the id offsets carry the
+// global numbering, so random streams, traces and progress rows are those of the tiled path.
 constexpr int FUSED_MAX_WARPS = 16;
-constexpr size_t FUSED_MAX_TABLE_BYTES = 200 * 1024;
+constexpr size_t FUSED_SMEM_LIMIT = 220 * 1024;
+
+#define FUSED_ARRAYS(X) \
+	X(params, double, n) X(params_best, double, n) X(steps, double, n) X(prop, double, n) \
+	X(prob, double, 1) X(prior, double, 1) X(prob_best, double, 1) X(beta, double, 1) \
+	X(accept, u64, 1) X(reject, u64, 1) X(n_iter, u64, 1) X(swapcount, u64, 1) X(rng_ctr, u64, 1) \
+	X(pacc, u64, n) X(prej, u64, n) X(stat_n, u64, 1) X(stat_sum_dl, double, 1) \
+	X(stat_sum_p, double, n) X(stat_sum_p2, double, n)
+
+// bytes of shared memory for the state of one ensemble
+__host__ __device__ inline size_t fused_state_bytes(int n_beta, int n_par) {
+	const size_t per_chain = 8 * (size_t) (8 * n_par + 11) + sizeof(CalState) + sizeof(int);
+	return (per_chain * n_beta + 8 /* swap_round */ + 15) & ~(size_t) 15;
+}
+__host__ __device__ inline size_t fused_table_bytes(long long n_rows) {
+	return (((size_t) n_rows * 16 + 127) & ~(size_t) 127) + 16 /* mbarrier */;
+}
 
 struct FusedArgs {
 	const double * data;     // [n_rows][2]
@@ -402,7 +424,7 @@ struct FusedArgs {
 
 __device__ __forceinline__ const double2 * fused_stage_table(const FusedArgs & a, unsigned char * smem) {
 	double2 * sdata = reinterpret_cast<double2 *>(smem);
-	uint64_t * bar = reinterpret_cast<uint64_t *>(smem + (((size_t) a.n_rows * sizeof(double2) + 15) & ~(size_t) 15));
+	uint64_t * bar = reinterpret_cast<uint64_t *>(smem + fused_table_bytes(a.n_rows) - 16);
 	if (a.n_rows > 0) {
 		if (threadIdx.x == 0) {
 			mbar_init(bar, 1);
@@ -420,6 +442,79 @@ __device__ __forceinline__ const double2 * fused_stage_table(const FusedArgs & a
 		mbar_wait(bar, 0);
 	}
 	return sdata;
+}
+
+// copy ensemble `ens` into shared memory; the returned DevState addresses the copies with
+// chain index = position in the ensemble
+__device__ inline DevState fused_localize(const DevState & S, int ens, unsigned char * mem) {
+	DevState L = S;
+	const int nb = S.n_beta, n = S.n_par;
+	const size_t base = (size_t) ens * nb;
+	size_t off = 0;
+#define X(name, type, width) { \
+		type * p = reinterpret_cast<type *>(mem + off); \
+		for (int i = threadIdx.x; i < nb * (width); i += blockDim.x) \
+			p[i] = S.name[base * (width) + i]; \
+		L.name = p; \
+		off += sizeof(type) * (size_t) nb * (width); }
+	FUSED_ARRAYS(X)
+#undef X
+	{
+		constexpr int W = sizeof(CalState) / 8;
+		u64 * p = reinterpret_cast<u64 *>(mem + off);
+		const u64 * src = reinterpret_cast<const u64 *>(S.cal + base);
+		for (int i = threadIdx.x; i < nb * W; i += blockDim.x)
+			p[i] = src[i];
+		L.cal = reinterpret_cast<CalState *>(p);
+		off += sizeof(CalState) * (size_t) nb;
+	}
+	{
+		u64 * p = reinterpret_cast<u64 *>(mem + off);
+		if (threadIdx.x == 0)
+			p[0] = S.swap_round[ens];
+		L.swap_round = p;
+		off += 8;
+	}
+	{
+		int * p = reinterpret_cast<int *>(mem + off);
+		for (int i = threadIdx.x; i < nb; i += blockDim.x)
+			p[i] = S.pend[base + i];
+		L.pend = p;
+	}
+	L.n_ens = 1;
+	L.g_base = S.g_base + (int) base;
+	L.chain_id_offset = S.chain_id_offset + (int) base;
+	L.ensemble_id_offset = S.ensemble_id_offset + ens;
+	if (S.tr_prob != nullptr) {
+		L.tr_prob = S.tr_prob + base;
+		L.tr_dl = S.tr_dl + base;
+	}
+	if (S.tr_params != nullptr)
+		L.tr_params = S.tr_params + (S.tr_params_chains == 2 ? base : (size_t) ens) * n;
+	__syncthreads();
+	return L;
+}
+
+__device__ inline void fused_writeback(const DevState & S, const DevState & L, int ens) {
+	const int nb = S.n_beta, n = S.n_par;
+	const size_t base = (size_t) ens * nb;
+	__syncthreads();
+#define X(name, type, width) \
+		for (int i = threadIdx.x; i < nb * (width); i += blockDim.x) \
+			S.name[base * (width) + i] = L.name[i];
+	FUSED_ARRAYS(X)
+#undef X
+	{
+		constexpr int W = sizeof(CalState) / 8;
+		u64 * dst = reinterpret_cast<u64 *>(S.cal + base);
+		const u64 * src = reinterpret_cast<const u64 *>(L.cal);
+		for (int i = threadIdx.x; i < nb * W; i += blockDim.x)
+			dst[i] = src[i];
+	}
+	if (threadIdx.x == 0)
+		S.swap_round[ens] = L.swap_round[0];
+	for (int i = threadIdx.x; i < nb; i += blockDim.x)
+		S.pend[base + i] = L.pend[i];
 }
 
 // sum over the table of the model's row terms for chain g's pending proposal; every lane
@@ -454,85 +549,126 @@ __device__ __forceinline__ double fused_loglik(const DevState & S, int g, const 
 	return warp_sum((a0 + a1) + (a2 + a3));
 }
 
+// chain_propose with the coordinates drawn by the lanes of a warp in parallel (every draw has
+// its own counter, so who computes it is immaterial)
+__device__ __forceinline__ void chain_propose_warp(const DevState & S, int g, int kind, int lane) {
+	const int n = S.n_par;
+	if (lane < n) {
+		const double old = S.params[(size_t) g * n + lane];
+		S.prop[(size_t) g * n + lane] = (kind == n || kind == lane)
+				? propose_coordinate(S, g, S.rng_ctr[g], lane, old, S.steps[(size_t) g * n + lane]) : old;
+	}
+	if (lane == 0)
+		S.pend[g] = kind;
+	__syncwarp();
+}
+
 template<class M>
 __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_run_kernel(const DevState S, const FusedArgs a) {
 	extern __shared__ __align__(128) unsigned char fused_smem[];
 	const double2 * sdata = fused_stage_table(a, fused_smem);
+	const int ens = blockIdx.x;
+	const DevState L = fused_localize(S, ens, fused_smem + fused_table_bytes(a.n_rows));
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-	const int ens = blockIdx.x, base = ens * S.n_beta;
+	const int nb = L.n_beta, n = L.n_par;
 	const double xub = M::HAS_DATA ? *a.xabsmax : 0.0;
-	for (int k = warp; k < S.n_beta; k += n_warps)
-		if (lane == 0)
-			chain_propose(S, base + k, S.n_par);
-	__syncwarp();
 	long long step = 0;
-	for (long long round = 0; round < a.n_rounds; round++) {
-		for (int sub = 0; sub < a.n_swap; sub++, step++) {
-			const bool last_of_round = sub + 1 == a.n_swap;
-			for (int k = warp; k < S.n_beta; k += n_warps) {
-				const int g = base + k;
-				const double sum = fused_loglik<M>(S, g, sdata, a.n_rows, xub, lane);
-				if (lane == 0) {
-					chain_finalize<M>(S, g, M::sum0(S.prop + (size_t) g * S.n_par) + sum);
-					chain_record(S, g, step);
+	if (M::HAS_DATA) {
+		for (int k = warp; k < nb; k += n_warps)
+			chain_propose_warp(L, k, n, lane);
+		for (long long round = 0; round < a.n_rounds; round++) {
+			for (int sub = 0; sub < a.n_swap; sub++, step++) {
+				const bool last_of_round = sub + 1 == a.n_swap;
+				for (int k = warp; k < nb; k += n_warps) {
+					const double sum = fused_loglik<M>(L, k, sdata, a.n_rows, xub, lane);
+					if (lane == 0) {
+						chain_finalize<M>(L, k, M::sum0(L.prop + (size_t) k * n) + sum);
+						chain_record(L, k, step);
+					}
+					__syncwarp();
 					if (!last_of_round)
-						chain_propose(S, g, S.n_par);
+						chain_propose_warp(L, k, n, lane);
 				}
-				__syncwarp();
 			}
+			// tempering_interaction for this ensemble, then the proposals of the next round
+			__syncthreads();
+			if (threadIdx.x == 0)
+				ensemble_swap(L, 0);
+			__syncthreads();
+			if (round + 1 < a.n_rounds)
+				for (int k = warp; k < nb; k += n_warps)
+					chain_propose_warp(L, k, n, lane);
 		}
-		// tempering_interaction for this ensemble, then the proposals of the next round
-		__syncthreads();
-		if (threadIdx.x == 0)
-			ensemble_swap(S, ens);
-		__syncthreads();
-		if (round + 1 < a.n_rounds) {
-			for (int k = warp; k < S.n_beta; k += n_warps)
-				if (lane == 0)
-					chain_propose(S, base + k, S.n_par);
-			__syncwarp();
+	} else {
+		for (int k = threadIdx.x; k < nb; k += blockDim.x)
+			chain_propose(L, k, n);
+		for (long long round = 0; round < a.n_rounds; round++) {
+			for (int sub = 0; sub < a.n_swap; sub++, step++) {
+				for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+					chain_finalize<M>(L, k, M::sum0(L.prop + (size_t) k * n));
+					chain_record(L, k, step);
+					if (sub + 1 < a.n_swap)
+						chain_propose(L, k, n);
+				}
+			}
+			__syncthreads();
+			if (threadIdx.x == 0)
+				ensemble_swap(L, 0);
+			__syncthreads();
+			if (round + 1 < a.n_rounds)
+				for (int k = threadIdx.x; k < nb; k += blockDim.x)
+					chain_propose(L, k, n);
 		}
 	}
+	fused_writeback(S, L, ens);
 }
 
 // markov_chain_calibrate of every selected chain, start to finish in one launch: the per-chain
 // state machine of apm_chain.cuh needs nothing from other chains
 template<class M>
-__global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_calibrate_kernel(const DevState S, const FusedArgs a) {
+__global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_calibrate_kernel(const DevState S,
+		const FusedArgs a) {
 	extern __shared__ __align__(128) unsigned char fused_smem[];
 	const double2 * sdata = fused_stage_table(a, fused_smem);
+	const int ens = blockIdx.x;
+	const DevState L = fused_localize(S, ens, fused_smem + fused_table_bytes(a.n_rows));
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-	const int base = blockIdx.x * S.n_beta;
+	const int nb = L.n_beta, n = L.n_par;
+	const size_t base = (size_t) ens * nb;
 	const double xub = M::HAS_DATA ? *a.xabsmax : 0.0;
-	for (int k = warp; k < S.n_beta; k += n_warps) {
-		const int g = base + k;
-		if (lane == 0) {
-			S.pend[g] = PEND_NONE;
-			S.cal[g].phase = CAL_IDLE;
-			if (a.select == nullptr || a.select[g]) {
-				atomicAdd(S.n_active, 1);
-				cal_begin(S, g, a.cal);
-				const int kind = cal_next_kind(S, g);
-				if (kind != PEND_NONE)
-					chain_propose(S, g, kind);
+	// one chain per warp (with data) or per thread (data-free); `leader` runs the state machine
+	const int first = M::HAS_DATA ? warp : (int) threadIdx.x, stride = M::HAS_DATA ? n_warps : (int) blockDim.x;
+	const bool leader = !M::HAS_DATA || lane == 0;
+	for (int k = first; k < nb; k += stride) {
+		if (leader) {
+			L.pend[k] = PEND_NONE;
+			L.cal[k].phase = CAL_IDLE;
+			if (a.select == nullptr || a.select[base + k]) {
+				atomicAdd(L.n_active, 1);
+				cal_begin(L, k, a.cal);
 			} else {
-				S.cal[g].status = -1;
+				L.cal[k].status = -1;
 			}
 		}
-		__syncwarp();
-		while (S.pend[g] != PEND_NONE) { // same value for the whole warp
-			const double sum = fused_loglik<M>(S, g, sdata, a.n_rows, xub, lane);
+		if (M::HAS_DATA)
 			__syncwarp();
-			if (lane == 0) {
-				chain_finalize<M>(S, g, M::sum0(S.prop + (size_t) g * S.n_par) + sum);
-				cal_after_step(S, g, a.cal);
-				const int kind = cal_next_kind(S, g);
-				if (kind != PEND_NONE)
-					chain_propose(S, g, kind);
+		int kind = cal_next_kind(L, k);
+		while (kind != PEND_NONE) { // same value for the whole warp
+			if (M::HAS_DATA)
+				chain_propose_warp(L, k, kind, lane);
+			else
+				chain_propose(L, k, kind);
+			const double sum = fused_loglik<M>(L, k, sdata, a.n_rows, xub, lane);
+			if (leader) {
+				chain_finalize<M>(L, k, M::sum0(L.prop + (size_t) k * n) + sum);
+				cal_after_step(L, k, a.cal);
 			}
-			__syncwarp();
+			if (M::HAS_DATA)
+				__syncwarp();
+			kind = cal_next_kind(L, k);
 		}
 	}
+	fused_writeback(S, L, ens);
 }
 
 // ------------------------------------------------------------------ eval
