@@ -2,20 +2,22 @@
 //
 //   loglik_tiled_kernel<M>   the hot kernel of the tiled path: a persistent grid walks
 //                            (chain tile x row split) work items; the data rows stream
-//                            through a 2-stage shared-memory ring filled by the TMA
-//                            engine (cp.async.bulk + mbarrier), every staged row is used
-//                            by all chains of the tile from registers, per-chain sums are
-//                            reduced by fp64 warp shuffles in a fixed order.
+//                            through a shared-memory ring filled by the TMA engine
+//                            (cp.async.bulk + full/empty mbarriers, no CTA barrier in the
+//                            chunk loop); each thread keeps the tile's chain constants and
+//                            accumulators in registers, so every LDS.128 of a row feeds all
+//                            chains of the tile; per-chain sums are folded in a fixed order
+//                            (fp64 warp shuffles).
 //   advance_kernel<M>        the control kernel of the tiled path, one CTA per ensemble:
 //                            finalise the pending step of every chain (accept/reject,
 //                            counters, best, trace, accumulators), resolve the ensemble's
 //                            swap, drive the calibration state machines, and draw the next
 //                            proposals -- all reference semantics live in apm_chain.cuh.
-//   fused_run_kernel<M>      the small-data path: one CTA per ensemble, one warp per
-//                            chain, the whole data table resident in shared memory (one
-//                            TMA bulk copy), n_rounds x (n_swap steps + swap) in a single
-//                            launch.
+//   fused_run_kernel<M>      the small-table path: one CTA per ensemble, one warp per chain,
+//   fused_calibrate_kernel<M>  table and ensemble state resident in shared memory, a whole
+//                            run (n_rounds x (n_swap steps + swap)) or calibration per launch.
 //   eval_finish_kernel<M>    turns running sums into (prob, prior) for apm_gpu_eval.
+//   absmax_col0_kernel       max |x| of the table (range bound of the fast sine).
 //   fp64_peak_kernel         DFMA issue-rate microbenchmark (the roofline denominator).
 #pragma once
 
