@@ -138,3 +138,59 @@ def test_several_ensembles_side_by_side(tmp_path):
     assert len(a.splitlines()) == 1500
     r = subprocess.run([exe3, "analyse"], cwd=wd3, env=env, check=True, capture_output=True, text=True)
     assert "3 independent ensembles" in r.stdout
+
+
+def test_user_model_device_against_host_plugin(tmp_path):
+    """apps/multisin.{c,cuh}: a model file in APEMoST's plugin style with its __device__ counterpart,
+    built as APM_MODEL_USER.  K = 1 is the reference's simplesin, so the device AND the host half
+    must reproduce what the unmodified reference printed (1e-12); for K = 3 device and host must
+    agree with each other; `check` reports the same; and the four phases run."""
+    fx = json.load(open(os.path.join(GOLDEN, "eval_simplesin.json")))
+    exe = make("eval_multisin.exe", "-DN_BETA=1", str(tmp_path / "bin"))
+    wd = str(tmp_path / "k1")
+    os.makedirs(wd)
+    write_params_file(os.path.join(wd, "params"), [tuple(r) for r in fx["rows"]])
+    data = np.array(fx["data"], dtype=float).reshape(-1, fx["n_cols"])
+    write_data_file(os.path.join(wd, "data"), data)
+    vectors = np.array(fx["params"], dtype=float).reshape(fx["n_vectors"], -1)
+    text = "\n".join(" ".join(repr(float(v)) for v in row) for row in vectors) + "\n"
+
+    def evaluate(args, cwd, stdin):
+        r = subprocess.run([exe, *args], cwd=cwd, input=stdin, capture_output=True, text=True, check=True)
+        return np.array([l.split() for l in r.stdout.splitlines() if re.match(r"^-?\d", l)], dtype=float)[:, 0]
+
+    want = np.array(fx["prob"], dtype=float)
+    np.testing.assert_allclose(evaluate([], wd, text), want, rtol=1e-12)
+    np.testing.assert_allclose(evaluate(["--host"], wd, text), want, rtol=1e-12)
+
+    # K = 3 on a 5000-row light curve
+    rng = np.random.default_rng(3)
+    x = np.sort(rng.uniform(0, 300, 5000))
+    truth = [1.0, 3.1, 0.2, 0.5, 7.7, 0.6, 0.3, 11.3, 0.9, 0.1]
+    y = sum(truth[3 * k] * np.sin(2 * np.pi * (truth[3 * k + 1] * x + truth[3 * k + 2])) for k in range(3)) + truth[9]
+    y = y + rng.normal(0, 0.5, x.size)
+    wd3 = str(tmp_path / "k3")
+    os.makedirs(wd3)
+    rows = []
+    for k in range(3):
+        rows += [(truth[3 * k], 0.0, 3.0, f"amplitude{k}", -1.0), (truth[3 * k + 1], 1.0, 15.0, f"frequency{k}", 1e-4),
+                 (truth[3 * k + 2], 0.0, 1.0, f"phase{k}", -1.0)]
+    rows.append((truth[9], -1.0, 1.0, "offset", -1.0))
+    write_params_file(os.path.join(wd3, "params"), rows)
+    write_data_file(os.path.join(wd3, "data"), np.stack([x, y], axis=1))
+    vec = np.array(truth)[None, :] + rng.normal(0, 1e-3, (16, 10))
+    text3 = "\n".join(" ".join(repr(float(v)) for v in row) for row in vec) + "\n"
+    np.testing.assert_allclose(evaluate([], wd3, text3), evaluate(["--host"], wd3, text3), rtol=1e-12)
+
+    main = make("multisin.exe", "-DN_BETA=4 -DBURN_IN_ITERATIONS=2000 -DMAX_ITERATIONS=2000 -DCIRCULAR_PARAMS=3,6,9",
+                str(tmp_path / "bin"))
+    r = subprocess.run([main, "check"], cwd=wd3, capture_output=True, text=True, check=True)
+    m = re.search(r"relative difference: ([\d.e+-]+)", r.stdout)
+    assert m and float(m.group(1)) < 1e-12, r.stdout[-400:]
+    for phase in ("calibrate_first", "calibrate_rest", "run", "analyse"):
+        r = subprocess.run([main, phase], cwd=wd3, capture_output=True, text=True, check=True)
+    assert "Model probability ln(p(D|M, I))" in r.stdout
+    assert len(open(os.path.join(wd3, "frequency1-chain-0.prob.dump")).read().splitlines()) == 2000
+    # the posterior mean of the first frequency sits at the truth
+    f0 = np.loadtxt(os.path.join(wd3, "frequency0-chain-0.prob.dump"))
+    assert abs(f0[500:].mean() - truth[1]) < 5e-3
