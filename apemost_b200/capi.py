@@ -312,6 +312,11 @@ class Engine(EngineBase):
         buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
         self._check(self._lib.apm_gpu_nccl_init(self._h, buf, C.c_int(rank), C.c_int(n_ranks)))
 
+    def ladder_init(self, unique_id: bytes, rank: int, n_ranks: int, n_beta_total: int):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        self._check(self._lib.apm_gpu_ladder_init(self._h, buf, C.c_int(rank), C.c_int(n_ranks),
+                                                   C.c_int(n_beta_total)))
+
 
 def nccl_unique_id() -> bytes:
     lib = load_library()

@@ -59,6 +59,9 @@ struct DevState {
 	int proposal;
 	unsigned circular_mask, quirks;
 	int chain_id_offset, ensemble_id_offset;
+	// ladder split over several GPUs (otherwise n_beta_total = id_stride = n_beta, k_offset = 0):
+	// this device holds rungs [k_offset, k_offset + n_beta) of every ensemble's n_beta_total
+	int n_beta_total, id_stride, k_offset;
 	int g_base;        // added to a chain index where it is reported (progress rows); != 0 only in
 	                   // the fused path, whose DevState is indexed by position in the ensemble
 	double model_const[4];
@@ -99,11 +102,17 @@ struct DevState {
 	int tr_prob_every, tr_params_chains, tr_dumped;
 };
 
+// global number of chain g = its random stream (independent of how chains are spread over
+// devices, processes, ensembles per device or kernel paths)
+APM_D uint32_t chain_rng_id(const DevState & S, int g) {
+	return (uint32_t) (S.chain_id_offset + (g / S.n_beta) * S.id_stride + S.k_offset + g % S.n_beta);
+}
+
 // ---- proposal: reference src/markov_chain.c:226-270 (do_step_for) ------------------------
 APM_D double propose_coordinate(const DevState & S, int g, u64 ctr, int i, double old_value,
 		double step) {
 	const double mx = S.pmax[i], mn = S.pmin[i];
-	const uint32_t id = (uint32_t) (S.chain_id_offset + g);
+	const uint32_t id = chain_rng_id(S, g);
 	unsigned attempt = 0;
 	double u0, u1, new_value;
 	if (S.circular_mask == 0) {
@@ -195,8 +204,7 @@ APM_D void chain_finalize(const DevState & S, int g, double sum) {
 	else {
 		// get_next_alog_urandom: reference src/mcmc_gettersetter.c:307-309
 		double u0, u1;
-		philox_uniforms(S.seed, (uint32_t) (S.chain_id_offset + g), S.rng_ctr[g], PURPOSE_ACCEPT, 0, 0,
-				u0, u1);
+		philox_uniforms(S.seed, chain_rng_id(S, g), S.rng_ctr[g], PURPOSE_ACCEPT, 0, 0, u0, u1);
 		accepted = log(u0) < (prob_new - prob_old) ? 1 : 0;
 	}
 	if (accepted) {
@@ -264,9 +272,19 @@ APM_D void chain_record(const DevState & S, int g, long long step_index) {
 // tempering_interaction for one ensemble: reference
 // src/parallel_tempering_interaction.c:125-141 -> decide_swap_now :87-97 ->
 // check_swap_probability :25-42 -> do_swap :99-123.  One thread per ensemble.
-APM_D void ensemble_swap(const DevState & S, int ens) {
-	const int n_beta = S.n_beta, n = S.n_par;
-	if (n_beta == 1)
+//
+// With the ladder split over GPUs the pair (a, a + 1) may straddle two devices.  Each device
+// then holds one chain of the pair and a copy of the other's swap-relevant state ("pack":
+// prob, beta, prior, prob_best, params[n], params_best[n]) received from its neighbour; both
+// evaluate the same expression on the same doubles with the same uniform, reach the same
+// decision and each updates the chain it owns.  pack_prev = last rung of the previous device,
+// pack_next = first rung of the next one, [n_ens][LADDER_PACK(n)] each.
+#define LADDER_PACK(n) (4 + 2 * (n))
+
+APM_D void ensemble_swap(const DevState & S, int ens, const double * pack_prev = nullptr,
+		const double * pack_next = nullptr) {
+	const int n_beta = S.n_beta, n = S.n_par, total = S.n_beta_total;
+	if (total == 1)
 		return;
 	const int base = ens * n_beta;
 	const uint32_t id = (uint32_t) (S.ensemble_id_offset + ens);
@@ -275,45 +293,66 @@ APM_D void ensemble_swap(const DevState & S, int ens) {
 	philox_uniforms(S.seed, id, round, PURPOSE_SWAP_PICK, 0, 0, u_pick, dummy);
 	philox_uniforms(S.seed, id, round, PURPOSE_SWAP_TEST, 0, 0, u_test, dummy);
 	S.swap_round[ens] = round + 1;
-	const int a = (int) (n_beta * 1000 * u_pick) % (n_beta - 1);
-	const int ga = base + a, gb = base + a + 1;
-	const double a_prob = S.prob[ga], b_prob = S.prob[gb];
-	const double a_beta = S.beta[ga], b_beta = S.beta[gb];
+	const int a = (int) (total * 1000 * u_pick) % (total - 1); // rung of the whole ladder
+	const int la = a - S.k_offset, lb = la + 1;                  // positions on this device
+	const bool own_a = la >= 0 && la < n_beta, own_b = lb >= 0 && lb < n_beta;
+	if (!own_a && !own_b)
+		return;
+	if ((!own_a && pack_prev == nullptr) || (!own_b && pack_next == nullptr))
+		return;
+	const int ga = base + la, gb = base + lb;
+	const double * pa = own_a ? nullptr : pack_prev + (size_t) ens * LADDER_PACK(n);
+	const double * pb = own_b ? nullptr : pack_next + (size_t) ens * LADDER_PACK(n);
+	const double a_prob = own_a ? S.prob[ga] : pa[0], b_prob = own_b ? S.prob[gb] : pb[0];
+	const double a_beta = own_a ? S.beta[ga] : pa[1], b_beta = own_b ? S.beta[gb] : pb[1];
+	const double a_prior = own_a ? S.prior[ga] : pa[2], b_prior = own_b ? S.prior[gb] : pb[2];
+	const double a_best = own_a ? S.prob_best[ga] : pa[3], b_best = own_b ? S.prob_best[gb] : pb[3];
+	const double * a_params = own_a ? S.params + (size_t) ga * n : pa + 4;
+	const double * b_params = own_b ? S.params + (size_t) gb * n : pb + 4;
+	const double * a_params_best = own_a ? S.params_best + (size_t) ga * n : pa + 4 + n;
+	const double * b_params_best = own_b ? S.params_best + (size_t) gb * n : pb + 4 + n;
 	double r;
 	if (S.quirks & 1u) {
 		r = a_beta * b_prob / b_beta + b_beta * a_prob / a_beta - (a_prob + b_prob);
 	} else {
-		double la = (a_prob - S.prior[ga]) / a_beta;
-		double lb = (b_prob - S.prior[gb]) / b_beta;
-		r = (a_beta - b_beta) * (lb - la);
+		double la_ = (a_prob - a_prior) / a_beta;
+		double lb_ = (b_prob - b_prior) / b_beta;
+		r = (a_beta - b_beta) * (lb_ - la_);
 	}
 	if (r > log(u_test)) {
 		for (int i = 0; i < n; i++) {
-			double t = S.params[(size_t) ga * n + i];
-			S.params[(size_t) ga * n + i] = S.params[(size_t) gb * n + i];
-			S.params[(size_t) gb * n + i] = t;
+			const double ta = a_params[i], tb = b_params[i];
+			if (own_a)
+				S.params[(size_t) ga * n + i] = tb;
+			if (own_b)
+				S.params[(size_t) gb * n + i] = ta;
 		}
 		if (!(S.quirks & 1u)) {
-			double la = (a_prob - S.prior[ga]) / a_beta;
-			double lb = (b_prob - S.prior[gb]) / b_beta;
-			double pa = S.prior[ga], pb = S.prior[gb];
-			S.prior[ga] = pb;
-			S.prior[gb] = pa;
-			S.prob[ga] = pb + a_beta * lb;
-			S.prob[gb] = pa + b_beta * la;
+			const double la_ = (a_prob - a_prior) / a_beta;
+			const double lb_ = (b_prob - b_prior) / b_beta;
+			if (own_a) {
+				S.prior[ga] = b_prior;
+				S.prob[ga] = b_prior + a_beta * lb_;
+			}
+			if (own_b) {
+				S.prior[gb] = a_prior;
+				S.prob[gb] = a_prior + b_beta * la_;
+			}
 		}
-		double rb = S.prob_best[ga];
-		if (rb > S.prob_best[gb]) {
-			S.prob_best[gb] = rb;
+		// the better of the two bests goes to both
+		if (a_best > b_best) {
+			if (own_b) {
+				S.prob_best[gb] = a_best;
+				for (int i = 0; i < n; i++)
+					S.params_best[(size_t) gb * n + i] = a_params_best[i];
+			}
+		} else if (own_a) {
+			S.prob_best[ga] = b_best;
 			for (int i = 0; i < n; i++)
-				S.params_best[(size_t) gb * n + i] = S.params_best[(size_t) ga * n + i];
-		} else {
-			rb = S.prob_best[gb];
-			S.prob_best[ga] = rb;
-			for (int i = 0; i < n; i++)
-				S.params_best[(size_t) ga * n + i] = S.params_best[(size_t) gb * n + i];
+				S.params_best[(size_t) ga * n + i] = b_params_best[i];
 		}
-		S.swapcount[ga]++; // inc_swapcount(chains[candidate]) (:139)
+		if (own_a)
+			S.swapcount[ga]++; // inc_swapcount(chains[candidate]) (:139)
 	}
 }
 

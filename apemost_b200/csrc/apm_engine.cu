@@ -31,6 +31,10 @@ struct NcclApi {
 	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
 	ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
 	const char * (*GetErrorString)(ncclResult_t) = nullptr;
 	bool load() {
 		if (lib)
@@ -45,7 +49,11 @@ struct NcclApi {
 		AllReduce = (decltype(AllReduce)) dlsym(lib, "ncclAllReduce");
 		CommDestroy = (decltype(CommDestroy)) dlsym(lib, "ncclCommDestroy");
 		GetErrorString = (decltype(GetErrorString)) dlsym(lib, "ncclGetErrorString");
-		return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+		Send = (decltype(Send)) dlsym(lib, "ncclSend");
+		Recv = (decltype(Recv)) dlsym(lib, "ncclRecv");
+		GroupStart = (decltype(GroupStart)) dlsym(lib, "ncclGroupStart");
+		GroupEnd = (decltype(GroupEnd)) dlsym(lib, "ncclGroupEnd");
+		return GetUniqueId && CommInitRank && AllReduce && CommDestroy && Send && Recv && GroupStart && GroupEnd;
 	}
 };
 static NcclApi g_nccl;
@@ -86,6 +94,9 @@ struct apm_gpu {
 	ncclComm_t comm = nullptr;
 	int rank = 0, n_ranks = 1;
 	double * d_shard_sum = nullptr;
+	// ladder split: packs of the boundary chains, [n_ens][LADDER_PACK(n_par)] each
+	bool ladder = false;
+	double * d_pack_first = nullptr, *d_pack_last = nullptr, *d_pack_prev = nullptr, *d_pack_next = nullptr;
 	std::string err;
 };
 
@@ -222,6 +233,9 @@ extern "C" int apm_gpu_create(apm_gpu ** out, const apm_gpu_config * cfg) {
 		S.quirks = cfg->quirks;
 		S.chain_id_offset = cfg->chain_id_offset;
 		S.ensemble_id_offset = cfg->ensemble_id_offset;
+		S.n_beta_total = cfg->n_beta;
+		S.id_stride = cfg->n_beta;
+		S.k_offset = 0;
 		for (int i = 0; i < 4; i++)
 			S.model_const[i] = cfg->model_const[i];
 		cudaError_t e = cudaSuccess;
@@ -274,6 +288,7 @@ extern "C" int apm_gpu_destroy(apm_gpu * h) {
 			S.accept, S.reject, S.pacc, S.prej, S.n_iter, S.swapcount, S.rng_ctr, S.swap_round, S.pmin,
 			S.pmax, S.pend, S.partial, S.stat_n, S.stat_sum_dl, S.stat_sum_p, S.stat_sum_p2, S.cal,
 			S.progress, S.progress_n, S.n_active, S.act_idx, S.act_n, h->d_select, h->d_shard_sum,
+			h->d_pack_first, h->d_pack_last, h->d_pack_prev, h->d_pack_next,
 			h->d_xabsmax, h->d_data, h->d_tr_prob, h->d_tr_dl, h->d_tr_params };
 	for (void * p : ptrs)
 		if (p)
@@ -540,7 +555,7 @@ static int step_likelihood(apm_gpu * h, bool timed, int act_w = -1, int n_upper 
 			h->plan_splits, h->plan_cps, h->S.partial, timed);
 	if (rc != APM_OK)
 		return rc;
-	if (h->comm && M::HAS_DATA) {
+	if (h->comm && !h->ladder && M::HAS_DATA) {
 		fold_splits_kernel<<<(h->n_chains + 255) / 256, 256, 0, h->stream>>>(h->S.partial, h->plan_splits,
 				h->n_chains, h->d_shard_sum);
 		h->launches++;
@@ -555,11 +570,35 @@ static int step_likelihood(apm_gpu * h, bool timed, int act_w = -1, int n_upper 
 
 static DevState state_for_advance(const apm_gpu * h) {
 	DevState S = h->S;
-	if (h->comm) {
+	if (h->comm && !h->ladder) {
 		S.partial = h->d_shard_sum;
 		S.n_splits = 1;
 	}
 	return S;
+}
+
+// ---- ladder split: every rank sends its first rung's pack down and its last rung's pack up
+static int ladder_exchange(apm_gpu * h) {
+	const size_t count = (size_t) h->cfg.n_ensembles * LADDER_PACK(h->cfg.n_par);
+	ladder_pack_kernel<<<(h->cfg.n_ensembles + 127) / 128, 128, 0, h->stream>>>(h->S, h->d_pack_first, h->d_pack_last);
+	h->launches++;
+	ncclResult_t r = g_nccl.GroupStart();
+	if (r == 0 && h->rank + 1 < h->n_ranks) {
+		r = g_nccl.Send(h->d_pack_last, count, ncclFloat64, h->rank + 1, h->comm, h->stream);
+		if (r == 0)
+			r = g_nccl.Recv(h->d_pack_next, count, ncclFloat64, h->rank + 1, h->comm, h->stream);
+	}
+	if (r == 0 && h->rank > 0) {
+		r = g_nccl.Send(h->d_pack_first, count, ncclFloat64, h->rank - 1, h->comm, h->stream);
+		if (r == 0)
+			r = g_nccl.Recv(h->d_pack_prev, count, ncclFloat64, h->rank - 1, h->comm, h->stream);
+	}
+	ncclResult_t e = g_nccl.GroupEnd();
+	if (r == 0)
+		r = e;
+	if (r != 0)
+		return fail(h, APM_ENCCL, "ladder exchange failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+	return APM_OK;
 }
 
 // ------------------------------------------------------------------ eval
@@ -625,7 +664,7 @@ extern "C" int apm_gpu_eval(apm_gpu * h, int n, const double * params, const dou
 		return APM_OK;
 	if (!h->have_data)
 		return fail(h, APM_ESTATE, "apm_gpu_set_data must be called first");
-	if (h->comm)
+	if (h->comm && !h->ladder)
 		return fail(h, APM_ESTATE, "apm_gpu_eval is not available in data-sharded mode");
 	CU(cudaSetDevice(h->cfg.device));
 	DISPATCH(h->cfg.model_id, eval_t, h, n, params, beta, prob_out, prior_out)
@@ -744,12 +783,25 @@ static int run_tiled_t(apm_gpu * h, long long n_rounds, int n_swap) {
 		int rc = step_likelihood<M>(h, true);
 		if (rc != APM_OK)
 			return rc;
+		const bool swap_now = (step + 1) % n_swap == 0;
 		a.flags = ADV_FINALIZE | ADV_RECORD;
-		if ((step + 1) % n_swap == 0)
+		a.step_index = step;
+		if (swap_now && h->ladder) {
+			// the pair may straddle two GPUs: finish the step, trade the boundary chains with the
+			// neighbours, then swap + propose with their copies at hand
+			advance_kernel<M><<<h->cfg.n_ensembles, ADV_THREADS, 0, h->stream>>>(state_for_advance(h), a);
+			h->launches++;
+			rc = ladder_exchange(h);
+			if (rc != APM_OK)
+				return rc;
+			a.flags = 0;
+			a.pack_prev = h->rank > 0 ? h->d_pack_prev : nullptr;
+			a.pack_next = h->rank + 1 < h->n_ranks ? h->d_pack_next : nullptr;
+		}
+		if (swap_now)
 			a.flags |= ADV_SWAP;
 		if (step + 1 < total)
 			a.flags |= ADV_PROPOSE_RUN;
-		a.step_index = step;
 		advance_kernel<M><<<h->cfg.n_ensembles, ADV_THREADS, 0, h->stream>>>(state_for_advance(h), a);
 		h->launches++;
 	}
@@ -1010,6 +1062,32 @@ extern "C" int apm_gpu_nccl_init(apm_gpu * h, const unsigned char id_in[128], in
 	}
 	h->rank = rank;
 	h->n_ranks = n_ranks;
+	return APM_OK;
+}
+
+extern "C" int apm_gpu_ladder_init(apm_gpu * h, const unsigned char id_in[128], int rank, int n_ranks,
+		int n_beta_total) {
+	if (!h || !id_in || n_ranks < 1 || rank < 0 || rank >= n_ranks || n_beta_total < n_ranks)
+		return APM_EINVAL;
+	if (h->comm)
+		return fail(h, APM_ESTATE, "this handle already has a communicator");
+	const int k0 = (int) ((long long) n_beta_total * rank / n_ranks);
+	const int k1 = (int) ((long long) n_beta_total * (rank + 1) / n_ranks);
+	if (k1 - k0 != h->cfg.n_beta)
+		return fail(h, APM_EINVAL, "rank %d of %d holds rungs [%d, %d) of %d: the handle must be created with "
+				"n_beta = %d, not %d", rank, n_ranks, k0, k1, n_beta_total, k1 - k0, h->cfg.n_beta);
+	int rc = apm_gpu_nccl_init(h, id_in, rank, n_ranks);
+	if (rc != APM_OK)
+		return rc;
+	const size_t count = (size_t) h->cfg.n_ensembles * LADDER_PACK(h->cfg.n_par);
+	CU(dalloc(&h->d_pack_first, count));
+	CU(dalloc(&h->d_pack_last, count));
+	CU(dalloc(&h->d_pack_prev, count));
+	CU(dalloc(&h->d_pack_next, count));
+	h->ladder = true;
+	h->S.n_beta_total = n_beta_total;
+	h->S.id_stride = n_beta_total;
+	h->S.k_offset = k0;
 	return APM_OK;
 }
 

@@ -305,6 +305,8 @@ struct AdvArgs {
 	CalibCfgDev cal;
 	const unsigned char * select; // calibration selection (ADV_CALIB_BEGIN)
 	int act_w;                    // calibration: which active-list buffer this launch fills
+	const double * pack_prev;     // ladder split: neighbours' boundary chains (see ensemble_swap)
+	const double * pack_next;
 };
 
 // calibration: append chain g to the list the next likelihood launch walks (the order of the
@@ -373,12 +375,34 @@ __global__ void __launch_bounds__(ADV_THREADS) advance_kernel(const DevState S, 
 	if (a.flags & ADV_SWAP) {
 		__syncthreads();
 		if (threadIdx.x == 0)
-			ensemble_swap(S, ens);
+			ensemble_swap(S, ens, a.pack_prev, a.pack_next);
 	}
 	if (a.flags & ADV_PROPOSE_RUN) {
 		__syncthreads();
 		for (int k = threadIdx.x; k < S.n_beta; k += blockDim.x)
 			chain_propose(S, base + k, S.n_par);
+	}
+}
+
+// ------------------------------------------------------------------ ladder split over GPUs
+// swap-relevant state of every ensemble's first and last rung on this device, laid out for the
+// neighbour exchange: [n_ens][LADDER_PACK(n_par)] each
+__global__ void ladder_pack_kernel(const DevState S, double * first_pack, double * last_pack) {
+	const int ens = blockIdx.x * blockDim.x + threadIdx.x;
+	if (ens >= S.n_ens)
+		return;
+	const int n = S.n_par;
+	for (int side = 0; side < 2; side++) {
+		const int g = ens * S.n_beta + (side == 0 ? 0 : S.n_beta - 1);
+		double * p = (side == 0 ? first_pack : last_pack) + (size_t) ens * LADDER_PACK(n);
+		p[0] = S.prob[g];
+		p[1] = S.beta[g];
+		p[2] = S.prior[g];
+		p[3] = S.prob_best[g];
+		for (int i = 0; i < n; i++) {
+			p[4 + i] = S.params[(size_t) g * n + i];
+			p[4 + n + i] = S.params_best[(size_t) g * n + i];
+		}
 	}
 }
 

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define APM_GPU_ABI_VERSION 1
+#define APM_GPU_ABI_VERSION 2
 
 /* ---- error codes -------------------------------------------------------- */
 #define APM_OK          0
@@ -217,6 +217,18 @@ int apm_gpu_get_stats(apm_gpu * h, unsigned long long * n /*[n_chains]*/,
 int apm_gpu_nccl_unique_id(unsigned char id_out[128]);
 int apm_gpu_nccl_init(apm_gpu * h, const unsigned char id[128], int rank,
 		int n_ranks);
+
+/* ---- multi-GPU, ladder split (third row): the n_beta_total rungs of
+ * every ensemble are dealt out over n_ranks GPUs in contiguous blocks (rank r holds rungs
+ * [n_beta_total * r / n_ranks, n_beta_total * (r + 1) / n_ranks); the handle must have been
+ * created with that many as n_beta, the same n_ensembles / seed / offsets on every rank).
+ * Chains step independently; once per round the ranks trade the swap-relevant state of
+ * their boundary chains (prob, beta, prior, best, params: 4 + 2 n_par doubles per ensemble)
+ * with ncclSend/ncclRecv, take the identical decision for a pair that straddles two GPUs
+ * (tempering_interaction, src/parallel_tempering_interaction.c:125-141) and each updates
+ * the chain it owns.  Results equal the single-GPU run bit for bit. ------------------- */
+int apm_gpu_ladder_init(apm_gpu * h, const unsigned char id[128], int rank,
+		int n_ranks, int n_beta_total);
 
 /* ---- introspection used by the tests and bench.py ----------------------- */
 /* number of kernels this handle has launched so far */
