@@ -238,6 +238,12 @@ class EngineBase:
                 for p in prog[:min(nprog.value, progress_capacity)]]
         return status, rows
 
+    # -- -DADAPT -------------------------------------------------------------------
+    def set_adapt(self, enabled=True, target_acceptance_rate=0.5):
+        f = self._fn("set_adapt")
+        f.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        self._check(f(self._h, int(bool(enabled)), float(target_acceptance_rate)))
+
     # -- accumulators ------------------------------------------------------------
     def reset_stats(self):
         self._check(self._fn("reset_stats")(self._h))

@@ -65,6 +65,9 @@ struct DevState {
 	int g_base;        // added to a chain index where it is reported (progress rows); != 0 only in
 	                   // the fused path, whose DevState is indexed by position in the ensemble
 	double model_const[4];
+	// -DADAPT (reference src/parallel_tempering.c:282-302): 0 = off
+	int adapt;
+	double adapt_target;
 	// mcmc struct members (reference src/mcmc_struct.h:30-106)
 	double * params, *params_best, *steps;
 	double * prob, *prior, *prob_best;
@@ -267,6 +270,30 @@ APM_D void chain_record(const DevState & S, int g, long long step_index) {
 		S.stat_sum_p[(size_t) g * n + i] += v;
 		S.stat_sum_p2[(size_t) g * n + i] += v * v;
 	}
+}
+
+// adapt() as compiled with -DADAPT (reference src/parallel_tempering.c:282-302): once per
+// round, before the swap, every chain nudges all its step widths by 1 % from the sums of its
+// per-parameter accept / reject counters (accepts / REJECTS, as coded: SURVEY App. D 7)
+APM_D void chain_adapt(const DevState & S, int g) {
+	const int n = S.n_par;
+	u64 sa = 0, sr = 0;
+	for (int i = 0; i < n; i++) {
+		sa += S.pacc[(size_t) g * n + i];
+		sr += S.prej[(size_t) g * n + i];
+	}
+	if (sa + sr < 20000)
+		return;
+	const double ratio = (double) sa * 1.0 / (double) sr;
+	if (ratio < S.adapt_target - 0.05) {
+		for (int i = 0; i < n; i++)
+			S.steps[(size_t) g * n + i] *= 0.99;
+	} else if (ratio > S.adapt_target + 0.05) {
+		for (int i = 0; i < n; i++)
+			S.steps[(size_t) g * n + i] *= 1 / 0.99;
+	}
+	if (sa + sr > 100000)
+		chain_reset_accept_rejects(S, g);
 }
 
 // tempering_interaction for one ensemble: reference

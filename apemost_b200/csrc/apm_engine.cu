@@ -376,10 +376,11 @@ static int replan(apm_gpu * h, int n_slots) {
 	if (tile < 0)
 		return tile;
 	make_plan(h, std::max(n_slots, 1), tile, h->plan_splits, h->plan_cps);
-	int rc = ensure_partial(h, (size_t) h->n_chains * h->plan_splits);
+	// the likelihood kernel leaves LL_PARTS partial sums per (chain, row split)
+	int rc = ensure_partial(h, (size_t) h->n_chains * h->plan_splits * LL_PARTS);
 	if (rc != APM_OK)
 		return rc;
-	h->S.n_splits = h->plan_splits;
+	h->S.n_splits = h->plan_splits * LL_PARTS;
 	return APM_OK;
 }
 
@@ -556,7 +557,7 @@ static int step_likelihood(apm_gpu * h, bool timed, int act_w = -1, int n_upper 
 	if (rc != APM_OK)
 		return rc;
 	if (h->comm && !h->ladder && M::HAS_DATA) {
-		fold_splits_kernel<<<(h->n_chains + 255) / 256, 256, 0, h->stream>>>(h->S.partial, h->plan_splits,
+		fold_splits_kernel<<<(h->n_chains + 255) / 256, 256, 0, h->stream>>>(h->S.partial, h->plan_splits * LL_PARTS,
 				h->n_chains, h->d_shard_sum);
 		h->launches++;
 		ncclResult_t r = g_nccl.AllReduce(h->d_shard_sum, h->d_shard_sum, (size_t) h->n_chains,
@@ -614,7 +615,7 @@ static int eval_t(apm_gpu * h, int n, const double * params, const double * beta
 	if (e == cudaSuccess) e = dalloc(&d_beta, (size_t) n);
 	if (e == cudaSuccess) e = dalloc(&d_prob, (size_t) n);
 	if (e == cudaSuccess) e = dalloc(&d_prior, (size_t) n);
-	if (e == cudaSuccess) e = dalloc(&d_partial, (size_t) n * n_splits);
+	if (e == cudaSuccess) e = dalloc(&d_partial, (size_t) n * n_splits * LL_PARTS);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(d_params, params, (size_t) n * np * sizeof(double),
 			cudaMemcpyHostToDevice, h->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(d_beta, beta, (size_t) n * sizeof(double),
@@ -626,7 +627,7 @@ static int eval_t(apm_gpu * h, int n, const double * params, const double * beta
 		rc = launch_loglik<M>(h, d_params, nullptr, nullptr, n, n, n_splits, cps, d_partial, true);
 		const double * mc = h->cfg.model_const;
 		eval_finish_kernel<M><<<(n + 127) / 128, 128, 0, h->stream>>>(n, np, d_params, d_beta, d_partial,
-				n_splits, d_prob, d_prior, mc[0], mc[1], mc[2], mc[3]);
+				n_splits * LL_PARTS, d_prob, d_prior, mc[0], mc[1], mc[2], mc[3]);
 		h->launches++;
 		cudaEventRecord(t1, h->stream);
 		e = cudaMemcpyAsync(prob_out, d_prob, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
@@ -1005,6 +1006,17 @@ extern "C" int apm_gpu_calibrate(apm_gpu * h, const unsigned char * select, cons
 		});
 	}
 	return rc;
+}
+
+// ------------------------------------------------------------------ -DADAPT
+extern "C" int apm_gpu_set_adapt(apm_gpu * h, int enabled, double target_acceptance_rate) {
+	if (!h)
+		return APM_EINVAL;
+	if (enabled && !(target_acceptance_rate > 0 && target_acceptance_rate < 1))
+		return fail(h, APM_EINVAL, "adapt: target acceptance rate must lie in (0, 1)");
+	h->S.adapt = enabled ? 1 : 0;
+	h->S.adapt_target = target_acceptance_rate;
+	return APM_OK;
 }
 
 // ------------------------------------------------------------------ accumulators

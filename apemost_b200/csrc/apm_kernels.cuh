@@ -274,6 +274,10 @@ __global__ void __launch_bounds__(LL_THREADS, 1) loglik_tiled_kernel(const LLArg
 
 constexpr size_t LL_SMEM_BYTES = sizeof(double2) * LL_STAGES * LL_CHUNK
 		+ sizeof(double) * LL_MAX_C * LL_THREADS + sizeof(uint64_t) * 2 * LL_STAGES;
+// partial sums one likelihood launch writes per (chain, row split).  (A barrier-free fold with one
+// partial per warp was measured: 4.68 ms against 4.60 ms per C3 launch -- the CTA barrier at the
+// end of an item re-aligns the warps on the ring, which is worth more than it costs.)
+constexpr int LL_PARTS = 1;
 
 // max |x| over the table (first column): bound for the per-item fast-sine range check.
 // |double| ordering == unsigned ordering of the bit pattern; NaN compares above everything,
@@ -373,6 +377,9 @@ __global__ void __launch_bounds__(ADV_THREADS) advance_kernel(const DevState S, 
 		}
 	}
 	if (a.flags & ADV_SWAP) {
+		if (S.adapt) // adapt() precedes tempering_interaction (parallel_tempering.c:404-406)
+			for (int k = threadIdx.x; k < S.n_beta; k += blockDim.x)
+				chain_adapt(S, base + k);
 		__syncthreads();
 		if (threadIdx.x == 0)
 			ensemble_swap(S, ens, a.pack_prev, a.pack_next);
@@ -616,7 +623,12 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_run_kernel(cons
 						chain_propose_warp(L, k, n, lane);
 				}
 			}
-			// tempering_interaction for this ensemble, then the proposals of the next round
+			// adapt (if compiled in), tempering_interaction for this ensemble, then the
+			// proposals of the next round
+			__syncthreads();
+			if (L.adapt)
+				for (int k = threadIdx.x; k < nb; k += blockDim.x)
+					chain_adapt(L, k);
 			__syncthreads();
 			if (threadIdx.x == 0)
 				ensemble_swap(L, 0);
@@ -637,6 +649,10 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_run_kernel(cons
 						chain_propose(L, k, n);
 				}
 			}
+			__syncthreads();
+			if (L.adapt)
+				for (int k = threadIdx.x; k < nb; k += blockDim.x)
+					chain_adapt(L, k);
 			__syncthreads();
 			if (threadIdx.x == 0)
 				ensemble_swap(L, 0);

@@ -141,6 +141,17 @@ void check(void) {
 #else
 	printf("\tPROPOSAL: gaussian/normal proposal distribution\n");
 #endif
+	printf("\tRANDOMSWAP: Random swapping: ");
+#ifdef RANDOMSWAP
+	printf("on\n");
+#else
+	printf("off\n");
+#endif
+#ifdef ADAPT
+	printf("\tADAPT: on (1%% step width rescaling per round once 20000 moves are counted)\n");
+#else
+	printf("\tADAPT: off\n");
+#endif
 #ifdef APM_EXACT_SWAP
 	printf("\tAPM_EXACT_SWAP: swaps exchange the likelihood with the position (not the reference's behaviour)\n");
 #else

@@ -177,6 +177,16 @@ apm_session * apm_session_open(void) {
 		fprintf(stderr, "could not start the GPU engine: %s\n", apm_gpu_last_error(NULL));
 		exit(1);
 	}
+#ifdef RWM
+#error "RWM does not compile in the reference either (src/parallel_tempering.c:278 calls markov_chain_step with 2 arguments)"
+#endif
+#ifdef ADAPT
+	/* adapt() once per round before the swap (reference src/parallel_tempering.c:282-302,404) */
+	apm_gpu_check(s, apm_gpu_set_adapt(s->gpu, 1, (double) TARGET_ACCEPTANCE_RATE), "enabling ADAPT");
+#endif
+	/* RANDOMSWAP (reference src/parallel_tempering_interaction.c:47-65,130-131) needs nothing: called
+	 * with n_swap = 1 its extra uniform is always below 1.0 / n_swap, so it is the default swap rule
+	 * plus one discarded draw -- the same distribution under the engine's counter RNG */
 	d = s->chains[0]->data;
 	assert(d->tda == d->size2);
 	apm_gpu_check(s, apm_gpu_set_data(s->gpu, d->data, (long long) d->size1, (int) d->size2), "uploading the data table");

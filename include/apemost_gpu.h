@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define APM_GPU_ABI_VERSION 2
+#define APM_GPU_ABI_VERSION 3
 
 /* ---- error codes -------------------------------------------------------- */
 #define APM_OK          0
@@ -199,6 +199,13 @@ int apm_gpu_calibrate(apm_gpu * h, const unsigned char * select,
 		const apm_gpu_calib_cfg * cfg, int * status,
 		apm_gpu_calib_progress * progress, long long progress_capacity,
 		long long * n_progress);
+
+/* ---- adapt() as compiled with -DADAPT (reference src/parallel_tempering.c:282-302, called
+ * once per round before the swap, :404): a chain whose per-parameter accept + reject counter
+ * sums have reached 20000 scales all its step widths by 0.99 (accepts / rejects below
+ * target - 0.05) or 1 / 0.99 (above target + 0.05) and resets its counters beyond 100000.
+ * Off by default, like the reference. ------------------------------------------------------ */
+int apm_gpu_set_adapt(apm_gpu * h, int enabled, double target_acceptance_rate);
 
 /* ---- on-device accumulators: what analyse needs
  * without the text round trip.  Per chain: n = recorded steps, sum_dl =

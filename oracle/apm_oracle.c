@@ -407,6 +407,9 @@ struct orc_engine {
 	int n_cols;
 	mt_state mt;
 	u64 * swap_round; /* per ensemble: PHILOX swap-stream position */
+	int adapt;            /* -DADAPT, ref src/parallel_tempering.c:282-302 */
+	double adapt_target;  /* TARGET_ACCEPTANCE_RATE */
+	int random_swap;      /* -DRANDOMSWAP, ref src/parallel_tempering_interaction.c:130-131 */
 	/* trace of the last run */
 	double * tr_prob, *tr_dl, *tr_params;
 	long long tr_prob_rows, tr_param_rows;
@@ -737,6 +740,12 @@ static void tempering_interaction(orc_engine * e, int ens) {
 	if (n_beta == 1)
 		return;
 	if (e->cfg.rng_kind == ORC_RNG_MT19937) {
+		/* parallel_tempering_decide_swap_random(chains, n_beta, 1) :47-65: one more uniform is
+		 * drawn first and compared with 1.0 / n_swap = 1, which it is always below; the pair
+		 * (a, (a + 1) % n_beta) is (a, a + 1) because a <= n_beta - 2.  Hence RANDOMSWAP differs
+		 * from the default only by this draw. */
+		if (e->random_swap)
+			(void) mt_uniform(&e->mt);
 		u_pick = mt_uniform(&e->mt);
 	} else {
 		orc_philox_uniforms(e->cfg.seed, (unsigned) (e->cfg.ensemble_id_offset + ens),
@@ -793,9 +802,46 @@ static void tempering_interaction(orc_engine * e, int ens) {
 	}
 }
 
+/* ---- adapt() with -DADAPT: ref src/parallel_tempering.c:282-302 ---------
+ * once per round, before the swap: a constant small rescaling of all step widths of a chain
+ * from its per-parameter accept / reject counter sums (note: accepts / REJECTS) */
+static void adapt_chain(orc_engine * e, chain_t * c) {
+	const int n = e->cfg.n_par;
+	u64 sa = 0, sr = 0;
+	double ratio;
+	int i;
+	for (i = 0; i < n; i++) {
+		sa += c->pacc[i];
+		sr += c->prej[i];
+	}
+	if (sa + sr < 20000)
+		return;
+	ratio = sa * 1.0 / sr;
+	if (ratio < e->adapt_target - 0.05) {
+		for (i = 0; i < n; i++)
+			c->steps[i] *= 0.99;
+	} else if (ratio > e->adapt_target + 0.05) {
+		for (i = 0; i < n; i++)
+			c->steps[i] *= 1 / 0.99;
+	}
+	if (sa + sr > 100000)
+		reset_accept_rejects(e, c);
+}
+
 /* ===================================================================== */
 /* API                                                                    */
 /* ===================================================================== */
+
+int orc_set_adapt(orc_engine * e, int enabled, double target_acceptance_rate) {
+	e->adapt = enabled;
+	e->adapt_target = target_acceptance_rate;
+	return 0;
+}
+
+int orc_set_random_swap(orc_engine * e, int enabled) {
+	e->random_swap = enabled;
+	return 0;
+}
 
 int orc_create(orc_engine ** out, const orc_config * cfg) {
 	orc_engine * e;
@@ -1049,6 +1095,9 @@ int orc_run(orc_engine * e, long long n_rounds, int n_swap, const orc_trace_cfg 
 			for (subiter = 0; subiter < n_swap; subiter++)
 				sampler_substep(e, g, round * n_swap + subiter, &tr);
 		}
+		if (e->adapt) /* adapt(chains, n_beta, n_swap), ref src/parallel_tempering.c:404 */
+			for (g = 0; g < e->n_chains; g++)
+				adapt_chain(e, e->chains + g);
 		for (ens = 0; ens < e->cfg.n_ensembles; ens++)
 			tempering_interaction(e, ens);
 	}

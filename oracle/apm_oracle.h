@@ -126,6 +126,10 @@ int orc_read_trace(orc_engine * e, double * prob, double * prob_minus_prior,
 int orc_calibrate(orc_engine * e, const unsigned char * select,
 		const orc_calib_cfg * cfg, int * status, orc_calib_progress * progress,
 		long long progress_capacity, long long * n_progress);
+/* -DADAPT (ref src/parallel_tempering.c:282-302) and -DRANDOMSWAP
+ * (ref src/parallel_tempering_interaction.c:47-65,130-131) */
+int orc_set_adapt(orc_engine * e, int enabled, double target_acceptance_rate);
+int orc_set_random_swap(orc_engine * e, int enabled);
 int orc_reset_stats(orc_engine * e);
 int orc_get_stats(orc_engine * e, unsigned long long * n, double * sum_dl,
 		double * sum_params, double * sum_params_sq);

@@ -217,6 +217,14 @@ def all_phase_fixtures():
         "normal", [(20.0, 0.0, 60.0, "x", -1.0)], None, np.array([[0.0, 0.0], [1.0, 1.0]]),
         dict(N_BETA=3, BURN_IN_ITERATIONS=1000, MAX_ITERATIONS=4000, BETA_0=0.5, GSL_RNG_SEED=2),
         suffix="_pin2b", engine_opts=dict(beta_0=0.5))
+    # -DADAPT: long enough for the 1 % rescalings (counter sums >= 20000) and a counter reset
+    # (> 100000) to happen; -DRANDOMSWAP: one more uniform per round
+    fx["c1_adapt_phases"] = phases_fixture(
+        "simplesin", C1_ROWS, "testlc.dat", None, dict(small, MAX_ITERATIONS=30000, GSL_RNG_SEED=13),
+        ccflags_extra="-DADAPT", suffix="_pin_adapt", engine_opts=dict(adapt=0.5))
+    fx["c1_randomswap_phases"] = phases_fixture(
+        "simplesin", C1_ROWS, "testlc.dat", None, dict(small, GSL_RNG_SEED=17),
+        ccflags_extra="-DRANDOMSWAP", suffix="_pin_rswap", engine_opts=dict(random_swap=1))
     return fx
 
 

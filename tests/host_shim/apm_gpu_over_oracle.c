@@ -49,8 +49,15 @@ int apm_gpu_create(apm_gpu ** handle, const apm_gpu_config * cfg) {
 		free(h);
 		return APM_EINVAL;
 	}
+	/* -DRANDOMSWAP changes nothing but the position in the global MT19937 stream (one more draw
+	 * per round); the product ABI has no such notion, so the test tells the oracle directly */
+	if (getenv("APM_TEST_RANDOMSWAP") != NULL)
+		orc_set_random_swap(h->e, 1);
 	*handle = h;
 	return APM_OK;
+}
+int apm_gpu_set_adapt(apm_gpu * h, int enabled, double target_acceptance_rate) {
+	return orc_set_adapt(h->e, enabled, target_acceptance_rate);
 }
 int apm_gpu_destroy(apm_gpu * h) {
 	if (h != NULL) {

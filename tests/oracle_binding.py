@@ -72,6 +72,9 @@ class Oracle(EngineBase):
             cfg.model_const[i] = v
         super().__init__(lib, cfg, n_ensembles, n_beta, n_par)
 
+    def set_random_swap(self, enabled=True):
+        self._check(self._lib.orc_set_random_swap(self._h, int(bool(enabled))))
+
     def mt_uniform(self):
         return self._lib.orc_mt_uniform(self._h)
 

@@ -116,6 +116,25 @@ def test_eval_exe_matches_reference_fixture(tmp_path):
         np.testing.assert_allclose(out[:, 1], np.array(fx["prior"], dtype=float), rtol=1e-12, atol=1e-300)
 
 
+def test_benchmark_exe_reproduces_and_matches_fixture(tmp_path):
+    """benchmark_<model>.exe (reference apps/benchmark_main.c): n + p evaluations at the params
+    file's start values, every one bit-identical to the first; the printed prob against the
+    reference's eval fixture (its first vector is the start vector)"""
+    fx = json.load(open(os.path.join(GOLDEN, "eval_simplesin.json")))
+    exe = make("benchmark_simplesin.exe", "-DN_BETA=1", str(tmp_path / "bin"))
+    wd = str(tmp_path / "wd")
+    os.makedirs(wd)
+    write_params_file(os.path.join(wd, "params"), [tuple(r) for r in fx["rows"]])
+    write_data_file(os.path.join(wd, "data"), np.array(fx["data"], dtype=float).reshape(-1, fx["n_cols"]))
+    r = subprocess.run([exe, "1000", "9000"], cwd=wd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    m = re.search(r"^10000 model evaluations in .* prob = (\S+)$", r.stdout, flags=re.M)
+    assert m, r.stdout
+    assert abs(float(m.group(1)) / float(fx["prob"][0]) - 1) < 1e-12
+    r = subprocess.run([exe], cwd=wd, capture_output=True, text=True)
+    assert r.returncode == 1 and "SYNOPSIS" in r.stderr
+
+
 def test_several_ensembles_side_by_side(tmp_path):
     """N_ENSEMBLES=3: one working directory per ensemble; ensemble 0 (chain ids 0..n_beta-1,
     ensemble id 0) repeats the single-ensemble run exactly, the others differ"""

@@ -191,6 +191,37 @@ def test_run_trajectory_equals_oracle(capi, name, kw, quirks, path):
 
 
 @pytest.mark.parametrize("path", PATHS)
+def test_adapt_trajectory_equals_oracle(capi, path):
+    """-DADAPT (reference src/parallel_tempering.c:282-302): once the counter sums reach 20000 the
+    step widths move by 1 % per round, beyond 100000 the counters are reset; the oracle's adapt is
+    byte-pinned to the reference build by tests/golden/c1_adapt_phases.json"""
+    fx = load("c1_adapt_phases")
+    rows = [tuple(r) for r in fx["rows"]]
+    n_par, n_beta, n_ens = len(rows), fx["config"]["N_BETA"], 2
+    data = np.loadtxt(os.path.join(GOLDEN, fx["data_file"]))
+    cal = np.array(fx["phases"]["calibrate_rest"].split(), dtype=float).reshape(n_beta, 1 + 2 * n_par)
+    res = []
+    for eng in _pair(capi, fx["model"], n_ens, n_beta, n_par=n_par, seed=29, path=path):
+        eng.set_data(data)
+        pt_flow.setup_chains(eng, rows)
+        pt_flow.apply_calibration(eng, 0, np.tile(cal[:, 0], n_ens), np.tile(cal[:, 1:1 + n_par], (n_ens, 1)),
+                                  np.tile(cal[:, 1 + n_par:], (n_ens, 1)))
+        # start the counters just below the two thresholds so that a short run crosses both
+        n = n_ens * n_beta
+        pa = np.full((n, n_par), 2600, dtype=np.uint64)
+        pa[n_beta:] = 13000
+        eng.set_chains(0, n, params_accepts=pa, params_rejects=(pa * 0.9).astype(np.uint64))
+        eng.set_adapt(True, 0.5)
+        eng.run(12, 50, prob_every=1, params_chains=1)
+        res.append((eng.read_trace(), eng.get_chains()))
+    (tr_g, st_g), (tr_c, st_c) = res
+    _compare_state(st_g, st_c)
+    np.testing.assert_allclose(tr_g["prob"], tr_c["prob"], rtol=RTOL_TRAJ)
+    assert not np.allclose(st_g["steps"][:n_beta], cal[:, 1:1 + n_par]), "adapt must have rescaled the steps"
+    assert (st_g["params_accepts"][n_beta:] < 13000).all(), "the counters of ensemble 1 must have been reset"
+
+
+@pytest.mark.parametrize("path", PATHS)
 def test_run_continues_across_calls(capi, path):
     """two runs of 4 rounds == one run of 8 rounds (state, RNG position and swap stream persist)"""
     fx = load("c1_phases")

@@ -23,7 +23,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 HOST = os.path.join(ROOT, "apemost_b200", "host")
 BUILD = os.path.join(ROOT, "oracle", "_build")
-FIXTURES = ["c1_phases", "c1_circular_phases", "c1_logistic_phases", "c1_uniform_phases", "c4_phases", "c2_phases"]
+FIXTURES = ["c1_phases", "c1_circular_phases", "c1_logistic_phases", "c1_uniform_phases", "c4_phases", "c2_phases",
+            "c1_adapt_phases", "c1_randomswap_phases"]
 MODEL_IDS = {"simplesin": 0, "simplesin5": 1, "normal": 2, "pulse_vrot": 3, "simplesin2": 4, "pulse": 5}
 
 
@@ -61,6 +62,8 @@ def test_host_layer_files_byte_identical_to_reference(name, tmp_path):
         import numpy as np
         write_data_file(os.path.join(wd, "data"), np.array(fx["data"], dtype=float).reshape(-1, fx["n_cols"]))
     env = dict(os.environ, GSL_RNG_SEED=str(cfg["GSL_RNG_SEED"]), APM_TEST_ORACLE_RNG="mt19937")
+    if "-DRANDOMSWAP" in fx["ccflags_extra"]:
+        env["APM_TEST_RANDOMSWAP"] = "1"
     for phase in ("calibrate_first", "calibrate_rest", "run"):
         subprocess.run([exe, phase], cwd=wd, env=env, check=True, capture_output=True)
         assert open(os.path.join(wd, "calibration_results")).read() == fx["phases"][phase], phase

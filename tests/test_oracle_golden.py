@@ -112,7 +112,7 @@ def test_evidence_rectangle_rule():
 
 
 PHASE_FIXTURES = ["c1_phases", "c1_circular_phases", "c1_logistic_phases", "c1_uniform_phases",
-                  "c4_phases", "c2_phases"]
+                  "c4_phases", "c2_phases", "c1_adapt_phases", "c1_randomswap_phases"]
 
 
 def _fixture_data(fx):
@@ -139,6 +139,10 @@ def test_phases_byte_identical_to_reference(name, tmp_path):
                    rng=RNG_MT19937, proposal=opts.get("proposal", 0),
                    circular_mask=opts.get("circular_mask", 0))
         e.set_data(data)
+        if opts.get("adapt"):        # -DADAPT
+            e.set_adapt(True, opts["adapt"])
+        if opts.get("random_swap"):  # -DRANDOMSWAP
+            e.set_random_swap(True)
         return e
 
     def cal_file():
