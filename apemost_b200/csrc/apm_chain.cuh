@@ -158,6 +158,42 @@ APM_D void chain_propose(const DevState & S, int g, int kind) {
 	S.pend[g] = kind;
 }
 
+// ---- random draws of a step, computed ahead of the step (cluster path) --------------------
+// A chain's draws depend on (seed, chain id, step counter, purpose, coordinate, attempt) only,
+// so while a group's warps evaluate the likelihood of the pending proposal one warp can already
+// compute (a) log(u) of that step's accept test and (b) the first-attempt jump of every
+// coordinate of the NEXT step (counter + 1).  The values are bit-identical to what
+// chain_finalize / propose_coordinate would compute later; they just leave the critical path.
+// out[0 .. n-1] = jumps, out[n] = log(u); lanes 0..n of one warp.
+APM_D void chain_precompute_draws(const DevState & S, int g, int lane, double * out) {
+	const int n = S.n_par;
+	const uint32_t id = chain_rng_id(S, g);
+	const u64 ctr = S.rng_ctr[g];
+	double u0, u1;
+	if (lane < n) {
+		philox_uniforms(S.seed, id, ctr + 1, PURPOSE_JUMP, (uint32_t) lane, 0, u0, u1);
+		out[lane] = jump_from_uniforms(S.proposal, S.steps[(size_t) g * n + lane], u0, u1);
+	} else if (lane == n) {
+		philox_uniforms(S.seed, id, ctr, PURPOSE_ACCEPT, 0, 0, u0, u1);
+		out[n] = log(u0);
+	}
+}
+
+// chain_propose for a full step with the first-attempt jumps at hand (lanes 0..n-1 of a warp);
+// a coordinate whose first attempt leaves the bounds takes the regular path (redraw / wrap)
+APM_D void chain_propose_from_jumps(const DevState & S, int g, int lane, const double * jumps) {
+	const int n = S.n_par;
+	if (lane < n) {
+		const double old = S.params[(size_t) g * n + lane];
+		double v = old + jumps[lane];
+		if (v > S.pmax[lane] || v < S.pmin[lane])
+			v = propose_coordinate(S, g, S.rng_ctr[g], lane, old, S.steps[(size_t) g * n + lane]);
+		S.prop[(size_t) g * n + lane] = v;
+	}
+	if (lane == 0)
+		S.pend[g] = n;
+}
+
 // mcmc_check_best: reference src/mcmc_calculate.c:35-41
 APM_D void chain_check_best(const DevState & S, int g) {
 	if (S.prob[g] > S.prob_best[g]) {
@@ -187,8 +223,10 @@ APM_D void chain_reset_accept_rejects(const DevState & S, int g) {
 // The second half of markov_chain_step / markov_chain_step_for (reference
 // src/markov_chain.c:369-386, 317-333) once the model's running sum for the proposal
 // is known: set_prior/set_prob, check_accept (:282-311), bookkeeping.
+// `pre_logu`, when given, is log(u0) of this step's accept draw, computed ahead of time by another
+// warp from the same counter (the draw depends on the chain's id and step counter only).
 template<class M>
-APM_D void chain_finalize(const DevState & S, int g, double sum) {
+APM_D void chain_finalize(const DevState & S, int g, double sum, const double * pre_logu = nullptr) {
 	const int n = S.n_par;
 	const int kind = S.pend[g];
 	const double * q = S.prop + (size_t) g * n;
@@ -206,9 +244,15 @@ APM_D void chain_finalize(const DevState & S, int g, double sum) {
 		accepted = 1;
 	else {
 		// get_next_alog_urandom: reference src/mcmc_gettersetter.c:307-309
-		double u0, u1;
-		philox_uniforms(S.seed, chain_rng_id(S, g), S.rng_ctr[g], PURPOSE_ACCEPT, 0, 0, u0, u1);
-		accepted = log(u0) < (prob_new - prob_old) ? 1 : 0;
+		double logu;
+		if (pre_logu != nullptr) {
+			logu = *pre_logu;
+		} else {
+			double u0, u1;
+			philox_uniforms(S.seed, chain_rng_id(S, g), S.rng_ctr[g], PURPOSE_ACCEPT, 0, 0, u0, u1);
+			logu = log(u0);
+		}
+		accepted = logu < (prob_new - prob_old) ? 1 : 0;
 	}
 	if (accepted) {
 		S.prob[g] = prob_new;
@@ -256,8 +300,8 @@ APM_D void chain_record(const DevState & S, int g, long long step_index) {
 		int slot = -1;
 		if (S.tr_params_chains == 2)
 			slot = g;
-		else if (S.tr_params_chains == 1 && g % S.n_beta == 0)
-			slot = g / S.n_beta;
+		else if (S.tr_params_chains == 1 && S.k_offset + g % S.n_beta == 0)
+			slot = g / S.n_beta; // rung 0 of the whole ladder (k_offset != 0: a block of a split ladder)
 		if (slot >= 0)
 			for (int i = 0; i < n; i++)
 				S.tr_params[((size_t) step_index * S.tr_dumped + slot) * n + i] =
@@ -270,6 +314,107 @@ APM_D void chain_record(const DevState & S, int g, long long step_index) {
 		S.stat_sum_p[(size_t) g * n + i] += v;
 		S.stat_sum_p2[(size_t) g * n + i] += v * v;
 	}
+}
+
+// ---- warp-cooperative forms of chain_finalize / chain_record (fused and cluster paths) ------
+// The same state transitions, element for element, with the per-parameter work spread over
+// lanes 0..n-1 of the calling warp and the scalar work on lane 0, so that the serial tail of a
+// step is a few dozen instructions instead of several hundred.  `sum` and `pre_logu` need to be
+// valid on lane 0 only.  All 32 lanes must call.
+template<class M>
+APM_D void chain_finalize_warp(const DevState & S, int g, double sum, const double * pre_logu, int lane) {
+	const int n = S.n_par;
+	const int kind = S.pend[g];
+	const double * q = S.prop + (size_t) g * n;
+	double * p = S.params + (size_t) g * n;
+	int accepted = 0;
+	if (lane == 0) {
+		const double prob_old = S.prob[g];
+		const double prior_old = S.prior[g];
+		double prior_new = prior_old;
+		if (M::HAS_PRIOR)
+			prior_new = M::prior(q, n, S.model_const);
+		const double prob_new = M::finish(S.beta[g], sum, prior_new, q, S.model_const);
+		if (prob_new == prob_old)
+			accepted = 1;
+		else if (prob_new > prob_old)
+			accepted = 1;
+		else {
+			double logu;
+			if (pre_logu != nullptr) {
+				logu = *pre_logu;
+			} else {
+				double u0, u1;
+				philox_uniforms(S.seed, chain_rng_id(S, g), S.rng_ctr[g], PURPOSE_ACCEPT, 0, 0, u0, u1);
+				logu = log(u0);
+			}
+			accepted = logu < (prob_new - prob_old) ? 1 : 0;
+		}
+		if (accepted) {
+			S.prob[g] = prob_new;
+			S.prior[g] = prior_new;
+			if (kind == n)
+				S.accept[g]++;
+		} else {
+			if (S.quirks & 2u)
+				S.prior[g] = prior_new;
+			if (kind == n)
+				S.reject[g]++;
+		}
+	}
+	accepted = __shfl_sync(0xffffffffu, accepted, 0);
+	if (lane < n && (kind == n || kind == lane)) {
+		if (accepted) {
+			p[lane] = q[lane];
+			S.pacc[(size_t) g * n + lane]++;
+		} else {
+			S.prej[(size_t) g * n + lane]++;
+		}
+	}
+	__syncwarp();
+	if (lane == 0) {
+		S.rng_ctr[g]++;
+		S.pend[g] = PEND_NONE;
+	}
+	__syncwarp();
+}
+
+APM_D void chain_record_warp(const DevState & S, int g, long long step_index, int lane) {
+	const int n = S.n_par;
+	const double prob = S.prob[g], dl = S.prob[g] - S.prior[g];
+	const bool better = prob > S.prob_best[g]; // mcmc_check_best
+	const double v = lane < n ? S.params[(size_t) g * n + lane] : 0.0;
+	__syncwarp();
+	if (better) {
+		if (lane == 0)
+			S.prob_best[g] = prob;
+		if (lane < n)
+			S.params_best[(size_t) g * n + lane] = v;
+	}
+	if (lane == 0) {
+		S.n_iter[g]++;
+		if (S.tr_prob_every > 0 && S.tr_prob != nullptr && step_index % S.tr_prob_every == 0) {
+			long long row = step_index / S.tr_prob_every;
+			S.tr_prob[row * S.n_chains + g] = prob;
+			S.tr_dl[row * S.n_chains + g] = dl;
+		}
+		S.stat_n[g]++;
+		S.stat_sum_dl[g] += dl;
+	}
+	if (lane < n) {
+		if (S.tr_params != nullptr) {
+			int slot = -1;
+			if (S.tr_params_chains == 2)
+				slot = g;
+			else if (S.tr_params_chains == 1 && S.k_offset + g % S.n_beta == 0)
+				slot = g / S.n_beta;
+			if (slot >= 0)
+				S.tr_params[((size_t) step_index * S.tr_dumped + slot) * n + lane] = v;
+		}
+		S.stat_sum_p[(size_t) g * n + lane] += v;
+		S.stat_sum_p2[(size_t) g * n + lane] += v * v;
+	}
+	__syncwarp();
 }
 
 // adapt() as compiled with -DADAPT (reference src/parallel_tempering.c:282-302): once per

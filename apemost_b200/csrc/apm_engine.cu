@@ -176,6 +176,7 @@ static int configure_kernels(apm_gpu * h) {
 	const int fused_smem = (int) FUSED_SMEM_LIMIT;
 	CU(cudaFuncSetAttribute(fused_run_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
 	CU(cudaFuncSetAttribute(fused_calibrate_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
+	CU(cudaFuncSetAttribute(cluster_run_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
 	return APM_OK;
 }
 
@@ -677,13 +678,47 @@ extern "C" int apm_gpu_eval(apm_gpu * h, int n, const double * params, const dou
 template<class M> static int model_has_data_t(apm_gpu *) { return M::HAS_DATA ? 1 : 0; }
 static int model_has_data(apm_gpu * h) { DISPATCH(h->cfg.model_id, model_has_data_t, h) }
 
-static int choose_path(apm_gpu * h, int * path) {
+// cluster geometry for a run: CTAs per ensemble (0 = the cluster path does not apply)
+static int cluster_size_for(const apm_gpu * h, bool has_data) {
+	if (!has_data || h->comm || h->cfg.n_beta < 2)
+		return 0;
+	int want = CLUSTER_MAX;
+	if (const char * t = getenv("APM_CLUSTER")) // experiments: force a cluster size (0 = never)
+		want = atoi(t);
+	for (int cl = CLUSTER_MAX; cl >= 2; cl >>= 1) {
+		if (cl > want || cl > h->cfg.n_beta)
+			continue;
+		if ((long long) h->cfg.n_ensembles * cl > h->sm_count)
+			continue; // more CTAs than SMs: the fused kernel's one CTA per ensemble is the better deal
+		const int gmax = (h->cfg.n_beta + cl - 1) / cl;
+		if (gmax > FUSED_MAX_WARPS)
+			continue;
+		const int wc = gmax <= 8 ? FUSED_MAX_WARPS / gmax : 1; // named barriers 1..8 for the groups
+		if (cluster_smem_bytes(h->n_rows, gmax, wc, h->cfg.n_par) > FUSED_SMEM_LIMIT)
+			continue;
+		return cl;
+	}
+	return 0;
+}
+
+static int choose_path(apm_gpu * h, int * path, bool for_run = false) {
 	const int has_data = model_has_data(h);
 	if (has_data < 0)
 		return has_data;
 	const size_t need = fused_table_bytes(has_data ? h->n_rows : 0) + fused_state_bytes(h->cfg.n_beta, h->cfg.n_par);
 	const bool fits = need <= FUSED_SMEM_LIMIT && (!has_data || h->n_rows < (1ll << 24));
-	if (h->cfg.path == APM_PATH_FUSED) {
+	const bool rows_ok = !has_data || h->n_rows < (1ll << 24);
+	const int cl = for_run && rows_ok ? cluster_size_for(h, has_data != 0) : 0;
+	int want = h->cfg.path;
+	if (want == APM_PATH_CLUSTER && !for_run)
+		want = fits ? APM_PATH_FUSED : APM_PATH_TILED; // calibration: chains do not interact, no cluster needed
+	if (want == APM_PATH_CLUSTER) {
+		if (cl == 0)
+			return fail(h, APM_EINVAL, "the cluster path needs a data model, 2 <= cluster size <= n_beta, "
+					"n_ensembles x cluster size <= %d SMs, the table in shared memory and no multi-GPU sharding",
+					h->sm_count);
+		*path = APM_PATH_CLUSTER;
+	} else if (want == APM_PATH_FUSED) {
 		if (h->comm)
 			return fail(h, APM_EINVAL, "the fused path cannot be used with a data-sharded likelihood");
 		if (!fits)
@@ -691,10 +726,10 @@ static int choose_path(apm_gpu * h, int * path) {
 					"%lld rows x %d chains need %lld bytes > %lld", h->n_rows, h->cfg.n_beta, (long long) need,
 					(long long) FUSED_SMEM_LIMIT);
 		*path = APM_PATH_FUSED;
-	} else if (h->cfg.path == APM_PATH_TILED) {
+	} else if (want == APM_PATH_TILED) {
 		*path = APM_PATH_TILED;
 	} else {
-		*path = (fits && !h->comm) ? APM_PATH_FUSED : APM_PATH_TILED;
+		*path = cl > 0 ? APM_PATH_CLUSTER : ((fits && !h->comm) ? APM_PATH_FUSED : APM_PATH_TILED);
 	}
 	return APM_OK;
 }
@@ -735,6 +770,56 @@ static int run_fused_t(apm_gpu * h, long long n_rounds, int n_swap) {
 	h->last_ll_ms = 0;
 	h->last_ll_launches = 0;
 	h->last_path = APM_PATH_FUSED;
+	return APM_OK;
+}
+
+template<class M>
+static int run_cluster_t(apm_gpu * h, long long n_rounds, int n_swap) {
+	if (!M::HAS_DATA)
+		return fail(h, APM_EINVAL, "the cluster path is for models with data");
+	ClusterArgs ca;
+	int threads = 0;
+	size_t smem_unused = 0;
+	fused_geometry(h, true, &threads, &smem_unused, &ca.f);
+	ca.f.n_rounds = n_rounds;
+	ca.f.n_swap = n_swap;
+	ca.cl = cluster_size_for(h, true);
+	if (ca.cl < 2)
+		return fail(h, APM_ESTATE, "no cluster geometry");
+	ca.gmax = (h->cfg.n_beta + ca.cl - 1) / ca.cl;
+	ca.wc = ca.gmax <= 8 ? FUSED_MAX_WARPS / ca.gmax : 1;
+	cudaLaunchConfig_t lc;
+	memset(&lc, 0, sizeof(lc));
+	lc.gridDim = dim3((unsigned) (h->cfg.n_ensembles * ca.cl));
+	lc.blockDim = dim3((unsigned) (32 * ca.wc * ca.gmax));
+	lc.dynamicSmemBytes = cluster_smem_bytes(h->n_rows, ca.gmax, ca.wc, h->cfg.n_par);
+	lc.stream = h->stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = (unsigned) ca.cl;
+	attr[0].val.clusterDim.y = 1;
+	attr[0].val.clusterDim.z = 1;
+	lc.attrs = attr;
+	lc.numAttrs = 1;
+	int max_clusters = 0;
+	CU(cudaOccupancyMaxActiveClusters(&max_clusters, cluster_run_kernel<M>, &lc));
+	if (max_clusters < 1)
+		return fail(h, APM_ECUDA, "a cluster of %d CTAs x %u threads x %zu bytes cannot be scheduled", ca.cl,
+				lc.blockDim.x, lc.dynamicSmemBytes);
+	h->ev_used = 0;
+	cudaEvent_t t0 = next_event(h), t1 = next_event(h);
+	CU(cudaEventRecord(t0, h->stream));
+	CU(cudaLaunchKernelEx(&lc, cluster_run_kernel<M>, h->S, ca));
+	h->launches++;
+	CU(cudaEventRecord(t1, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	CU(cudaGetLastError());
+	float tot = 0;
+	cudaEventElapsedTime(&tot, t0, t1);
+	h->last_total_ms = tot;
+	h->last_ll_ms = 0;
+	h->last_ll_launches = 0;
+	h->last_path = APM_PATH_CLUSTER;
 	return APM_OK;
 }
 
@@ -838,9 +923,12 @@ extern "C" int apm_gpu_run(apm_gpu * h, long long n_rounds, int n_swap, const ap
 	if (n_rounds == 0)
 		return APM_OK;
 	int path = APM_PATH_TILED;
-	rc = choose_path(h, &path);
+	rc = choose_path(h, &path, true);
 	if (rc != APM_OK)
 		return rc;
+	if (path == APM_PATH_CLUSTER) {
+		DISPATCH(h->cfg.model_id, run_cluster_t, h, n_rounds, n_swap)
+	}
 	if (path == APM_PATH_FUSED) {
 		DISPATCH(h->cfg.model_id, run_fused_t, h, n_rounds, n_swap)
 	}

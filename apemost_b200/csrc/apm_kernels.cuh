@@ -22,6 +22,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include "apm_chain.cuh"
 
 namespace apm {
@@ -477,12 +478,14 @@ __device__ __forceinline__ const double2 * fused_stage_table(const FusedArgs & a
 	return sdata;
 }
 
-// copy ensemble `ens` into shared memory; the returned DevState addresses the copies with
-// chain index = position in the ensemble
-__device__ inline DevState fused_localize(const DevState & S, int ens, unsigned char * mem) {
+// copy rungs [k0, k0 + nb) of ensemble `ens` into shared memory (the whole ensemble: k0 = 0, nb =
+// S.n_beta); the returned DevState addresses the copies with chain index = position in the block
+// and carries the ladder-split fields (n_beta_total, k_offset) that make chain ids, swap pairs
+// and trace slots those of the whole ladder
+__device__ inline DevState fused_localize_block(const DevState & S, int ens, int k0, int nb, unsigned char * mem) {
 	DevState L = S;
-	const int nb = S.n_beta, n = S.n_par;
-	const size_t base = (size_t) ens * nb;
+	const int n = S.n_par;
+	const size_t base = (size_t) ens * S.n_beta + k0;
 	size_t off = 0;
 #define X(name, type, width) { \
 		type * p = reinterpret_cast<type *>(mem + off); \
@@ -515,8 +518,12 @@ __device__ inline DevState fused_localize(const DevState & S, int ens, unsigned 
 		L.pend = p;
 	}
 	L.n_ens = 1;
+	L.n_beta = nb;
+	L.n_beta_total = S.n_beta_total;
+	L.id_stride = S.id_stride;
+	L.k_offset = S.k_offset + k0;
 	L.g_base = S.g_base + (int) base;
-	L.chain_id_offset = S.chain_id_offset + (int) base;
+	L.chain_id_offset = S.chain_id_offset + ens * S.id_stride;
 	L.ensemble_id_offset = S.ensemble_id_offset + ens;
 	if (S.tr_prob != nullptr) {
 		L.tr_prob = S.tr_prob + base;
@@ -528,9 +535,15 @@ __device__ inline DevState fused_localize(const DevState & S, int ens, unsigned 
 	return L;
 }
 
-__device__ inline void fused_writeback(const DevState & S, const DevState & L, int ens) {
-	const int nb = S.n_beta, n = S.n_par;
-	const size_t base = (size_t) ens * nb;
+__device__ inline DevState fused_localize(const DevState & S, int ens, unsigned char * mem) {
+	return fused_localize_block(S, ens, 0, S.n_beta, mem);
+}
+
+// L = what fused_localize_block returned for (ens, k0); copies its L.n_beta chains back
+__device__ inline void fused_writeback_block(const DevState & S, const DevState & L, int ens, int k0,
+		bool write_swap_round) {
+	const int nb = L.n_beta, n = S.n_par;
+	const size_t base = (size_t) ens * S.n_beta + k0;
 	__syncthreads();
 #define X(name, type, width) \
 		for (int i = threadIdx.x; i < nb * (width); i += blockDim.x) \
@@ -544,10 +557,14 @@ __device__ inline void fused_writeback(const DevState & S, const DevState & L, i
 		for (int i = threadIdx.x; i < nb * W; i += blockDim.x)
 			dst[i] = src[i];
 	}
-	if (threadIdx.x == 0)
+	if (threadIdx.x == 0 && write_swap_round)
 		S.swap_round[ens] = L.swap_round[0];
 	for (int i = threadIdx.x; i < nb; i += blockDim.x)
 		S.pend[base + i] = L.pend[i];
+}
+
+__device__ inline void fused_writeback(const DevState & S, const DevState & L, int ens) {
+	fused_writeback_block(S, L, ens, 0, true);
 }
 
 // sum over the table of the model's row terms for chain g's pending proposal; every lane
@@ -614,11 +631,8 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_run_kernel(cons
 				const bool last_of_round = sub + 1 == a.n_swap;
 				for (int k = warp; k < nb; k += n_warps) {
 					const double sum = fused_loglik<M>(L, k, sdata, a.n_rows, xub, lane);
-					if (lane == 0) {
-						chain_finalize<M>(L, k, M::sum0(L.prop + (size_t) k * n) + sum);
-						chain_record(L, k, step);
-					}
-					__syncwarp();
+					chain_finalize_warp<M>(L, k, M::sum0(L.prop + (size_t) k * n) + sum, nullptr, lane);
+					chain_record_warp(L, k, step, lane);
 					if (!last_of_round)
 						chain_propose_warp(L, k, n, lane);
 				}
@@ -663,6 +677,217 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_run_kernel(cons
 		}
 	}
 	fused_writeback(S, L, ens);
+}
+
+// ------------------------------------------------------------------ cluster path
+// The fused path with one ensemble spread over a thread-block CLUSTER of CL CTAs (CL SMs), for
+// runs with fewer ensembles than SMs (config C1: ONE 20-rung ensemble): CTA r of the cluster
+// holds rungs [nb r / CL, nb (r + 1) / CL) -- the ladder split of DESIGN.md section 6, inside
+// one GPC instead of across GPUs -- and a group of WC warps works on each of its chains (rows
+// strided over the group's lanes, fp64 butterfly per warp, the warps' sums added in index order
+// by the group's leader, which then finalises the step and draws the next proposal).
+//   * the table is fetched from global memory ONCE per cluster: CTA 0 issues TMA bulk copies
+//     with .multicast::cluster, which land at the same shared-memory offset of every CTA and
+//     complete on every CTA's own mbarrier;
+//   * once per round the CTAs publish the swap-relevant state of their first and last rung
+//     ("pack", LADDER_PACK doubles) in their shared memory, barrier.cluster, and read their
+//     neighbours' packs through distributed shared memory: ensemble_swap decides a pair that
+//     straddles two CTAs identically on both, each updating the chain it owns -- the very code
+//     path of the multi-GPU ladder split, so results equal the other paths' chain for chain.
+constexpr int CLUSTER_MAX = 8; // portable cluster size
+
+__host__ __device__ inline int cluster_block_lo(int nb, int cl, int r) { return (int) ((long long) nb * r / cl); }
+
+struct ClusterArgs {
+	FusedArgs f;
+	int cl;      // CTAs per ensemble = cluster size
+	int gmax;    // chains per CTA (upper bound): ceil(nb / cl)
+	int wc;      // warps per chain
+};
+
+__host__ __device__ inline size_t cluster_smem_bytes(long long n_rows, int gmax, int wc, int n_par) {
+	return fused_table_bytes(n_rows) + fused_state_bytes(gmax, n_par)
+			+ sizeof(double) * (2 * LADDER_PACK(n_par) + (size_t) gmax * wc + (size_t) gmax * (n_par + 1));
+}
+
+__device__ __forceinline__ void group_bar(int id, int n_threads) {
+	asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n_threads) : "memory");
+}
+
+__device__ __forceinline__ void tma_bulk_g2s_multicast(void * dst_smem, const void * src_gmem, uint32_t bytes,
+		uint64_t * bar, uint16_t cta_mask) {
+	asm volatile(
+			"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+			:: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+	uint32_t r;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+	return r;
+}
+// barrier.cluster.arrive.release + barrier.cluster.wait.acquire over all threads of the cluster
+__device__ __forceinline__ void cluster_sync_all() {
+	cooperative_groups::this_cluster().sync();
+}
+// generic (distributed shared memory) address of `p`, a shared-memory address of this CTA, in
+// CTA `rank` of the cluster (mapa)
+__device__ __forceinline__ const double * cluster_map(double * p, uint32_t rank) {
+	return cooperative_groups::this_cluster().map_shared_rank(p, rank);
+}
+
+// the group's share of chain g's sum: lanes gl, gl + GL, ... of the table; every lane of a warp
+// returns the warp's total
+template<class M>
+__device__ __forceinline__ double group_loglik(const DevState & S, int g, const double2 * sdata, int n_rows,
+		double xub, int gl, int GL) {
+	typename M::Prep q;
+	M::prep(q, S.prop + (size_t) g * S.n_par, S.n_par, S.model_const);
+	double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+	int i = gl;
+	if (M::fast_ok(q, xub)) {
+		for (; i + 3 * GL < n_rows; i += 4 * GL) {
+			const double2 r0 = sdata[i], r1 = sdata[i + GL], r2 = sdata[i + 2 * GL], r3 = sdata[i + 3 * GL];
+			a0 = M::accum_fast(a0, q, r0.x, r0.y);
+			a1 = M::accum_fast(a1, q, r1.x, r1.y);
+			a2 = M::accum_fast(a2, q, r2.x, r2.y);
+			a3 = M::accum_fast(a3, q, r3.x, r3.y);
+		}
+		for (; i < n_rows; i += GL) {
+			const double2 r = sdata[i];
+			a0 = M::accum_fast(a0, q, r.x, r.y);
+		}
+	} else {
+		for (; i < n_rows; i += GL) {
+			const double2 r = sdata[i];
+			a0 = M::accum(a0, q, r.x, r.y);
+		}
+	}
+	return warp_sum((a0 + a1) + (a2 + a3));
+}
+
+template<class M>
+__global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) cluster_run_kernel(const DevState S, const ClusterArgs ca) {
+	extern __shared__ __align__(128) unsigned char fused_smem[];
+	const FusedArgs & a = ca.f;
+	const int CL = ca.cl, WC = ca.wc;
+	const uint32_t rank = cluster_ctarank();
+	const int ens = blockIdx.x / CL;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int nb_all = S.n_beta, n = S.n_par;
+	const int k0 = cluster_block_lo(nb_all, CL, rank), nloc = cluster_block_lo(nb_all, CL, rank + 1) - k0;
+
+	// ---- the table: one multicast fetch per cluster
+	double2 * sdata = reinterpret_cast<double2 *>(fused_smem);
+	uint64_t * bar = reinterpret_cast<uint64_t *>(fused_smem + fused_table_bytes(a.n_rows) - 16);
+	const uint32_t total = (uint32_t) a.n_rows * sizeof(double2);
+	if (tid == 0) {
+		mbar_init(bar, 1);
+		mbar_fence_init();
+		mbar_arrive_expect_tx(bar, total);
+	}
+	cluster_sync_all(); // every CTA's barrier is armed before the copies that complete on it start
+	if (rank == 0 && tid == 0) {
+		for (uint32_t off = 0; off < total; off += 32768u)
+			tma_bulk_g2s_multicast(reinterpret_cast<unsigned char *>(sdata) + off,
+					reinterpret_cast<const unsigned char *>(a.data) + off, min(32768u, total - off), bar,
+					(uint16_t) ((1u << CL) - 1u));
+	}
+	mbar_wait(bar, 0);
+
+	// ---- this CTA's block of the ensemble, resident in shared memory
+	unsigned char * mem = fused_smem + fused_table_bytes(a.n_rows);
+	const DevState L = fused_localize_block(S, ens, k0, nloc, mem);
+	double * pack_first = reinterpret_cast<double *>(mem + fused_state_bytes(ca.gmax, n));
+	double * pack_last = pack_first + LADDER_PACK(n);
+	double * red = pack_last + LADDER_PACK(n); // [gmax][WC]
+	const double * pack_prev = rank > 0 ? cluster_map(pack_last, rank - 1) : nullptr;
+	const double * pack_next = rank + 1 < (uint32_t) CL ? cluster_map(pack_first, rank + 1) : nullptr;
+
+	double * pre = red + (size_t) ca.gmax * WC; // [gmax][n + 1]: next step's jumps, this step's log(u)
+	const int c = warp / WC, wi = warp - c * WC; // chain of this warp's group, warp within the group
+	const bool active = c < nloc;
+	// with two or more warps per chain the group's last warp computes the step's random draws
+	// while the others are in the likelihood; it also takes a share of the rows when the table is
+	// long enough for that to pay
+	const bool rng_warp = WC > 1 && wi == WC - 1;
+	const bool rng_rows = a.n_rows / (WC * 32) >= 16;
+	const int LW = (WC > 1 && !rng_rows) ? WC - 1 : WC; // warps of the group that walk the table
+	const int GL = LW * 32, gl = wi * 32 + lane;
+	const int GT = WC * 32;                              // threads of the group (named barrier)
+	double * my_pre = pre + (size_t) c * (n + 1);
+	const double xub = *a.xabsmax;
+	long long step = 0;
+	if (active && wi == 0)
+		chain_propose_warp(L, c, n, lane);
+	__syncthreads();
+	for (long long round = 0; round < a.n_rounds; round++) {
+		if (active) {
+			for (int sub = 0; sub < a.n_swap; sub++, step++) {
+				double sum = 0.0;
+				if (rng_warp) {
+					// off the critical path: the bookkeeping of the step just finalised (best,
+					// n_iter, trace rows, accumulators), then this step's random draws
+					if (sub > 0)
+						chain_record_warp(L, c, step - 1, lane);
+					chain_precompute_draws(L, c, lane, my_pre);
+				}
+				if (wi < LW)
+					sum = group_loglik<M>(L, c, sdata, a.n_rows, xub, gl, GL);
+				if (WC > 1) {
+					if (lane == 0 && wi < LW)
+						red[c * WC + wi] = sum;
+					group_bar(1 + c, GT);
+				}
+				if (wi == 0) {
+					if (WC > 1 && lane == 0) {
+						sum = red[c * WC];
+						for (int w = 1; w < LW; w++)
+							sum += red[c * WC + w];
+					}
+					chain_finalize_warp<M>(L, c, M::sum0(L.prop + (size_t) c * n) + sum, WC > 1 ? my_pre + n : nullptr,
+							lane);
+					if (WC == 1)
+						chain_record_warp(L, c, step, lane);
+					if (sub + 1 < a.n_swap) {
+						if (WC > 1)
+							chain_propose_from_jumps(L, c, lane, my_pre);
+						else
+							chain_propose_warp(L, c, n, lane);
+					}
+				}
+				if (WC > 1)
+					group_bar(1 + c, GT); // the next proposal is visible to the whole group
+			}
+			if (rng_warp)
+				chain_record_warp(L, c, step - 1, lane); // the round's last step
+		} else {
+			step += a.n_swap;
+		}
+		// ---- round end: adapt, publish the boundary rungs, swap with the neighbours' packs at hand
+		__syncthreads();
+		if (L.adapt && tid < nloc)
+			chain_adapt(L, tid);
+		if (tid < 2) {
+			const int g = tid == 0 ? 0 : nloc - 1;
+			double * p = tid == 0 ? pack_first : pack_last;
+			p[0] = L.prob[g];
+			p[1] = L.beta[g];
+			p[2] = L.prior[g];
+			p[3] = L.prob_best[g];
+			for (int i = 0; i < n; i++) {
+				p[4 + i] = L.params[(size_t) g * n + i];
+				p[4 + n + i] = L.params_best[(size_t) g * n + i];
+			}
+		}
+		cluster_sync_all();
+		if (tid == 0)
+			ensemble_swap(L, 0, pack_prev, pack_next);
+		cluster_sync_all(); // the neighbours have read this CTA's packs; the swap is visible to the CTA
+		if (round + 1 < a.n_rounds && active && wi == 0)
+			chain_propose_warp(L, c, n, lane);
+		__syncthreads();
+	}
+	fused_writeback_block(S, L, ens, k0, rank == 0);
 }
 
 // markov_chain_calibrate of every selected chain, start to finish in one launch: the per-chain

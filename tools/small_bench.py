@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Chain-steps/s of the small configurations of BASELINE.json (C1 simplesin on the reference's
-own light curve, C2 normal / 64 chains, C4 pulse_vrot) on both kernel paths, beside the CPU oracle.
+own light curve, C2 normal / 64 chains, C4 pulse_vrot) on the three kernel paths, beside the CPU oracle.
   python tools/small_bench.py            (on the GPU box) -> gpurun_out/small_bench.json"""
 import json
 import os
@@ -47,6 +47,7 @@ def time_engine(eng, rows, data, beta, steps, params, n_ens, rounds, n_swap):
 def main():
     out = {}
     for label, name, n_ens, n_beta in [("C1 simplesin testlc.dat 1x20", "c1_phases", 1, 20),
+                                       ("C1 simplesin testlc.dat 8x20", "c1_phases", 8, 20),
                                        ("C1 simplesin testlc.dat 64x20", "c1_phases", 64, 20),
                                        ("C2 normal 1x64", "c2_phases", 1, 64),
                                        ("C2 normal 64x64", "c2_phases", 64, 64),
@@ -55,7 +56,9 @@ def main():
         model, rows, data, beta, steps, params = case(name, n_ens, n_beta)
         n_swap = max(1, 2000 // n_beta)
         res = {}
-        for pname, path in (("tiled", 1), ("fused", 2)):
+        for pname, path in (("tiled", 1), ("fused", 2), ("cluster", 3)):
+            if path == 3 and model == "normal":
+                continue  # data-free: nothing to spread over a cluster
             e = capi.Engine(model, n_ens, n_beta, n_par=len(rows), seed=1, path=path)
             res[pname] = time_engine(e, rows, data, beta, steps, params, n_ens, 20 if path == 1 else 200, n_swap)
             e.close()
