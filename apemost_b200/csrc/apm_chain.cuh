@@ -112,34 +112,33 @@ APM_D uint32_t chain_rng_id(const DevState & S, int g) {
 }
 
 // ---- proposal: reference src/markov_chain.c:226-270 (do_step_for) ------------------------
-APM_D double propose_coordinate(const DevState & S, int g, u64 ctr, int i, double old_value,
-		double step) {
-	const double mx = S.pmax[i], mn = S.pmin[i];
-	const uint32_t id = chain_rng_id(S, g);
+// Kept out of line: Philox + log + sqrt + cos, called from several places of the fused / cluster
+// kernels, would otherwise be inlined into (and bloat) their step loops.
+__device__ __noinline__ double propose_coordinate_core(u64 seed, uint32_t id, u64 ctr, int i, double old_value,
+		double step, int proposal, bool wrap, double mn, double mx) {
 	unsigned attempt = 0;
 	double u0, u1, new_value;
-	if (S.circular_mask == 0) {
-		// CIRCULAR_PARAMS == 0: redraw until inside the bounds (:235-240)
-		do {
-			philox_uniforms(S.seed, id, ctr, PURPOSE_JUMP, (uint32_t) i, attempt++, u0, u1);
-			new_value = old_value + jump_from_uniforms(S.proposal, step, u0, u1);
-		} while (new_value > mx || new_value < mn);
-	} else {
-		// (:241-262)
-		philox_uniforms(S.seed, id, ctr, PURPOSE_JUMP, (uint32_t) i, attempt++, u0, u1);
-		new_value = old_value + jump_from_uniforms(S.proposal, step, u0, u1);
-		if (new_value > mx || new_value < mn) {
-			if (S.circular_mask & (1u << i)) {
-				new_value = mn + mod_double(new_value - mn, mx - mn);
-			} else {
-				do {
-					philox_uniforms(S.seed, id, ctr, PURPOSE_JUMP, (uint32_t) i, attempt++, u0, u1);
-					new_value = old_value + jump_from_uniforms(S.proposal, step, u0, u1);
-				} while (new_value > mx || new_value < mn);
-			}
+	philox_uniforms(seed, id, ctr, PURPOSE_JUMP, (uint32_t) i, attempt++, u0, u1);
+	new_value = old_value + jump_from_uniforms(proposal, step, u0, u1);
+	if (new_value > mx || new_value < mn) {
+		if (wrap) {
+			// CIRCULAR_PARAMS lists this parameter (:257-260)
+			new_value = mn + mod_double(new_value - mn, mx - mn);
+		} else {
+			// redraw until inside the bounds (:235-240; :241-262 for the unlisted parameters)
+			do {
+				philox_uniforms(seed, id, ctr, PURPOSE_JUMP, (uint32_t) i, attempt++, u0, u1);
+				new_value = old_value + jump_from_uniforms(proposal, step, u0, u1);
+			} while (new_value > mx || new_value < mn);
 		}
 	}
 	return new_value;
+}
+
+APM_D double propose_coordinate(const DevState & S, int g, u64 ctr, int i, double old_value,
+		double step) {
+	return propose_coordinate_core(S.seed, chain_rng_id(S, g), ctr, i, old_value, step, S.proposal,
+			(S.circular_mask >> i) & 1u, S.pmin[i], S.pmax[i]);
 }
 
 // do_step (:272-277) / do_step_for for the pending kind; writes S.prop[g]
@@ -156,42 +155,6 @@ APM_D void chain_propose(const DevState & S, int g, int kind) {
 			q[i] = p[i];
 	}
 	S.pend[g] = kind;
-}
-
-// ---- random draws of a step, computed ahead of the step (cluster path) --------------------
-// A chain's draws depend on (seed, chain id, step counter, purpose, coordinate, attempt) only,
-// so while a group's warps evaluate the likelihood of the pending proposal one warp can already
-// compute (a) log(u) of that step's accept test and (b) the first-attempt jump of every
-// coordinate of the NEXT step (counter + 1).  The values are bit-identical to what
-// chain_finalize / propose_coordinate would compute later; they just leave the critical path.
-// out[0 .. n-1] = jumps, out[n] = log(u); lanes 0..n of one warp.
-APM_D void chain_precompute_draws(const DevState & S, int g, int lane, double * out) {
-	const int n = S.n_par;
-	const uint32_t id = chain_rng_id(S, g);
-	const u64 ctr = S.rng_ctr[g];
-	double u0, u1;
-	if (lane < n) {
-		philox_uniforms(S.seed, id, ctr + 1, PURPOSE_JUMP, (uint32_t) lane, 0, u0, u1);
-		out[lane] = jump_from_uniforms(S.proposal, S.steps[(size_t) g * n + lane], u0, u1);
-	} else if (lane == n) {
-		philox_uniforms(S.seed, id, ctr, PURPOSE_ACCEPT, 0, 0, u0, u1);
-		out[n] = log(u0);
-	}
-}
-
-// chain_propose for a full step with the first-attempt jumps at hand (lanes 0..n-1 of a warp);
-// a coordinate whose first attempt leaves the bounds takes the regular path (redraw / wrap)
-APM_D void chain_propose_from_jumps(const DevState & S, int g, int lane, const double * jumps) {
-	const int n = S.n_par;
-	if (lane < n) {
-		const double old = S.params[(size_t) g * n + lane];
-		double v = old + jumps[lane];
-		if (v > S.pmax[lane] || v < S.pmin[lane])
-			v = propose_coordinate(S, g, S.rng_ctr[g], lane, old, S.steps[(size_t) g * n + lane]);
-		S.prop[(size_t) g * n + lane] = v;
-	}
-	if (lane == 0)
-		S.pend[g] = n;
 }
 
 // mcmc_check_best: reference src/mcmc_calculate.c:35-41
@@ -380,28 +343,14 @@ APM_D void chain_finalize_warp(const DevState & S, int g, double sum, const doub
 }
 
 APM_D void chain_record_warp(const DevState & S, int g, long long step_index, int lane) {
-	const int n = S.n_par;
+	const int n = S.n_par; // <= APM_MAX_PAR = 16, so lanes n .. n + 3 exist
 	const double prob = S.prob[g], dl = S.prob[g] - S.prior[g];
 	const bool better = prob > S.prob_best[g]; // mcmc_check_best
 	const double v = lane < n ? S.params[(size_t) g * n + lane] : 0.0;
 	__syncwarp();
-	if (better) {
-		if (lane == 0)
-			S.prob_best[g] = prob;
-		if (lane < n)
-			S.params_best[(size_t) g * n + lane] = v;
-	}
-	if (lane == 0) {
-		S.n_iter[g]++;
-		if (S.tr_prob_every > 0 && S.tr_prob != nullptr && step_index % S.tr_prob_every == 0) {
-			long long row = step_index / S.tr_prob_every;
-			S.tr_prob[row * S.n_chains + g] = prob;
-			S.tr_dl[row * S.n_chains + g] = dl;
-		}
-		S.stat_n[g]++;
-		S.stat_sum_dl[g] += dl;
-	}
 	if (lane < n) {
+		if (better)
+			S.params_best[(size_t) g * n + lane] = v;
 		if (S.tr_params != nullptr) {
 			int slot = -1;
 			if (S.tr_params_chains == 2)
@@ -413,8 +362,77 @@ APM_D void chain_record_warp(const DevState & S, int g, long long step_index, in
 		}
 		S.stat_sum_p[(size_t) g * n + lane] += v;
 		S.stat_sum_p2[(size_t) g * n + lane] += v * v;
+	} else if (lane == n) {
+		if (better)
+			S.prob_best[g] = prob;
+		S.n_iter[g]++;
+	} else if (lane == n + 1) {
+		S.stat_n[g]++;
+	} else if (lane == n + 2) {
+		S.stat_sum_dl[g] += dl;
+	} else if (lane == n + 3) {
+		if (S.tr_prob_every > 0 && S.tr_prob != nullptr && step_index % S.tr_prob_every == 0) {
+			long long row = step_index / S.tr_prob_every;
+			S.tr_prob[row * S.n_chains + g] = prob;
+			S.tr_dl[row * S.n_chains + g] = dl;
+		}
 	}
 	__syncwarp();
+}
+
+// the state transition of a full step whose outcome is already known (cluster path: every warp
+// of a chain's group takes the accept decision redundantly in registers, one warp writes it
+// down): what chain_finalize does after the decision.  prop = this lane's proposed coordinate.
+APM_D void chain_apply_step_warp(const DevState & S, int g, int accepted, double prob_new, double prior_new,
+		double prop, int lane) {
+	const int n = S.n_par;
+	if (lane < n) {
+		if (accepted) {
+			S.params[(size_t) g * n + lane] = prop;
+			S.pacc[(size_t) g * n + lane]++;
+		} else {
+			S.prej[(size_t) g * n + lane]++;
+		}
+	} else if (lane == n) {
+		if (accepted) {
+			S.prob[g] = prob_new;
+			S.prior[g] = prior_new;
+		} else if (S.quirks & 2u) {
+			S.prior[g] = prior_new;
+		}
+	} else if (lane == n + 1) {
+		if (accepted)
+			S.accept[g]++;
+		else
+			S.reject[g]++;
+	} else if (lane == n + 2) {
+		S.rng_ctr[g]++;
+	}
+	__syncwarp();
+}
+
+// K steps' worth of a chain's random draws in one go, lane-parallel: lane j * (n + 1) + d computes,
+// for step counter ctr0 + j, the first-attempt jump of coordinate d (d < n) or log(u) of the accept
+// test (d == n).  out[j * (n + 1) + d].  Same values as propose_coordinate / chain_finalize draw.
+APM_D void chain_draw_batch(const DevState & S, int g, u64 ctr0, int K, int lane, double * out) {
+	const int n = S.n_par;
+	const int j = lane / (n + 1), d = lane - j * (n + 1);
+	if (j >= K)
+		return;
+	const uint32_t id = chain_rng_id(S, g);
+	const bool is_jump = d < n;
+	double u0, u1;
+	philox_uniforms(S.seed, id, ctr0 + (u64) j, is_jump ? PURPOSE_JUMP : PURPOSE_ACCEPT, is_jump ? (uint32_t) d : 0u, 0,
+			u0, u1);
+	if (S.proposal == 0) {
+		const double lg = log(u0);
+		double r = lg;
+		if (is_jump) // = jump_from_uniforms(0, sigma, u0, u1), the same operations in the same order
+			r = S.steps[(size_t) g * n + d] * (sqrt(-2.0 * lg) * cos(2.0 * 3.14159265358979323846 * u1));
+		out[lane] = r;
+	} else {
+		out[lane] = is_jump ? jump_from_uniforms(S.proposal, S.steps[(size_t) g * n + d], u0, u1) : log(u0);
+	}
 }
 
 // adapt() as compiled with -DADAPT (reference src/parallel_tempering.c:282-302): once per

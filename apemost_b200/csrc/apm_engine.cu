@@ -778,6 +778,13 @@ static int run_cluster_t(apm_gpu * h, long long n_rounds, int n_swap) {
 	if (!M::HAS_DATA)
 		return fail(h, APM_EINVAL, "the cluster path is for models with data");
 	ClusterArgs ca;
+	ca.timing = nullptr;
+#ifdef APM_CLUSTER_TIMING
+	long long * d_timing = nullptr;
+	CU(cudaMalloc((void **) &d_timing, 16 * 8 * sizeof(long long)));
+	CU(cudaMemset(d_timing, 0, 16 * 8 * sizeof(long long)));
+	ca.timing = d_timing;
+#endif
 	int threads = 0;
 	size_t smem_unused = 0;
 	fused_geometry(h, true, &threads, &smem_unused, &ca.f);
@@ -820,6 +827,20 @@ static int run_cluster_t(apm_gpu * h, long long n_rounds, int n_swap) {
 	h->last_ll_ms = 0;
 	h->last_ll_launches = 0;
 	h->last_path = APM_PATH_CLUSTER;
+#ifdef APM_CLUSTER_TIMING
+	{
+		long long t[16 * 8];
+		CU(cudaMemcpy(t, d_timing, sizeof(t), cudaMemcpyDeviceToHost));
+		cudaFree(d_timing);
+		const double steps = (double) n_rounds * n_swap;
+		fprintf(stderr, "cluster timing, CTA 0 (cl %d, gmax %d, wc %d), cycles per step: warp: loop + deferred barrier "
+				"wait | own work (rows / bookkeeping + draws) | barrier | decision + next proposal\n", ca.cl, ca.gmax, ca.wc);
+		for (int w = 0; w < ca.wc * ca.gmax; w++)
+			fprintf(stderr, "  warp %2d (chain %d, %s): %7.0f %7.0f %7.0f %7.0f\n", w, w / ca.wc,
+					ca.wc > 1 && w % ca.wc == ca.wc - 1 ? "service" : "rows   ",
+					t[w * 8 + 0] / steps, t[w * 8 + 1] / steps, t[w * 8 + 2] / steps, t[w * 8 + 3] / steps);
+	}
+#endif
 	return APM_OK;
 }
 

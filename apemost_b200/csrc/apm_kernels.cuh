@@ -683,31 +683,43 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_run_kernel(cons
 // The fused path with one ensemble spread over a thread-block CLUSTER of CL CTAs (CL SMs), for
 // runs with fewer ensembles than SMs (config C1: ONE 20-rung ensemble): CTA r of the cluster
 // holds rungs [nb r / CL, nb (r + 1) / CL) -- the ladder split of DESIGN.md section 6, inside
-// one GPC instead of across GPUs -- and a group of WC warps works on each of its chains (rows
-// strided over the group's lanes, fp64 butterfly per warp, the warps' sums added in index order
-// by the group's leader, which then finalises the step and draws the next proposal).
+// one GPC instead of across GPUs -- and a group of WC warps works on each of its chains.
 //   * the table is fetched from global memory ONCE per cluster: CTA 0 issues TMA bulk copies
 //     with .multicast::cluster, which land at the same shared-memory offset of every CTA and
 //     complete on every CTA's own mbarrier;
+//   * a Metropolis step is latency-bound (rows -> sum -> accept -> next proposal -> rows), so the
+//     group keeps everything that is not on that chain of dependencies off it: WC - 1 warps walk
+//     the table (rows strided over their lanes, fp64 butterfly per warp, ONE named barrier per
+//     step); then EVERY warp adds the warps' sums in index order and takes the accept decision
+//     and forms the next proposal redundantly in registers (lane i holds coordinate i) -- the
+//     same instructions on the same inputs, hence the same bits in every warp -- so nobody waits
+//     for a leader; the group's last warp, which walks no rows, writes the outcome into the
+//     chain state (counters, best, trace rows, accumulators) one step behind, and draws the
+//     random numbers of the next K = 32 / (n_par + 1) steps in one lane-parallel batch (a
+//     chain's draws depend on its id and step counter only);
 //   * once per round the CTAs publish the swap-relevant state of their first and last rung
 //     ("pack", LADDER_PACK doubles) in their shared memory, barrier.cluster, and read their
 //     neighbours' packs through distributed shared memory: ensemble_swap decides a pair that
 //     straddles two CTAs identically on both, each updating the chain it owns -- the very code
 //     path of the multi-GPU ladder split, so results equal the other paths' chain for chain.
-constexpr int CLUSTER_MAX = 8; // portable cluster size
+constexpr int CLUSTER_MAX = 8; // the portable cluster size (16 was measured: +10 % for one ensemble, -40 % for eight)
 
 __host__ __device__ inline int cluster_block_lo(int nb, int cl, int r) { return (int) ((long long) nb * r / cl); }
 
 struct ClusterArgs {
+	long long * timing; // -DAPM_CLUSTER_TIMING builds: [16 warps][8] cycle sums of CTA 0 (tools/prof_small.py)
 	FusedArgs f;
 	int cl;      // CTAs per ensemble = cluster size
 	int gmax;    // chains per CTA (upper bound): ceil(nb / cl)
 	int wc;      // warps per chain
 };
 
+constexpr int CLUSTER_DRAW_RING = 4; // batches of draws in flight per chain
 __host__ __device__ inline size_t cluster_smem_bytes(long long n_rows, int gmax, int wc, int n_par) {
+	// packs (2) + per chain: warp sums [2][wc], draws [RING][32], per-warp proposal copies [wc][n_par]
 	return fused_table_bytes(n_rows) + fused_state_bytes(gmax, n_par)
-			+ sizeof(double) * (2 * LADDER_PACK(n_par) + (size_t) gmax * wc + (size_t) gmax * (n_par + 1));
+			+ sizeof(double) * (2 * LADDER_PACK(n_par)
+					+ (size_t) gmax * (2 * wc + CLUSTER_DRAW_RING * 32 + (size_t) wc * n_par));
 }
 
 __device__ __forceinline__ void group_bar(int id, int n_threads) {
@@ -738,10 +750,10 @@ __device__ __forceinline__ const double * cluster_map(double * p, uint32_t rank)
 // the group's share of chain g's sum: lanes gl, gl + GL, ... of the table; every lane of a warp
 // returns the warp's total
 template<class M>
-__device__ __forceinline__ double group_loglik(const DevState & S, int g, const double2 * sdata, int n_rows,
-		double xub, int gl, int GL) {
+__device__ __forceinline__ double group_loglik(const DevState & S, const double * prop, const double2 * sdata,
+		int n_rows, double xub, int gl, int GL) {
 	typename M::Prep q;
-	M::prep(q, S.prop + (size_t) g * S.n_par, S.n_par, S.model_const);
+	M::prep(q, prop, S.n_par, S.model_const);
 	double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 	int i = gl;
 	if (M::fast_ok(q, xub)) {
@@ -752,9 +764,17 @@ __device__ __forceinline__ double group_loglik(const DevState & S, int g, const 
 			a2 = M::accum_fast(a2, q, r2.x, r2.y);
 			a3 = M::accum_fast(a3, q, r3.x, r3.y);
 		}
-		for (; i < n_rows; i += GL) {
-			const double2 r = sdata[i];
-			a0 = M::accum_fast(a0, q, r.x, r.y);
+		// up to three rows left for this lane: evaluated side by side (a row's evaluation is one
+		// long dependency chain), each into the accumulator it would have gone to above
+		if (i < n_rows) {
+			const bool v1 = i + GL < n_rows, v2 = i + 2 * GL < n_rows;
+			const double2 r0 = sdata[i], r1 = sdata[v1 ? i + GL : i], r2 = sdata[v2 ? i + 2 * GL : i];
+			const double b0 = M::accum_fast(a0, q, r0.x, r0.y);
+			const double b1 = M::accum_fast(a1, q, r1.x, r1.y);
+			const double b2 = M::accum_fast(a2, q, r2.x, r2.y);
+			a0 = b0;
+			a1 = v1 ? b1 : a1;
+			a2 = v2 ? b2 : a2;
 		}
 	} else {
 		for (; i < n_rows; i += GL) {
@@ -765,9 +785,22 @@ __device__ __forceinline__ double group_loglik(const DevState & S, int g, const 
 	return warp_sum((a0 + a1) + (a2 + a3));
 }
 
+#ifdef APM_CLUSTER_TIMING
+#define APM_TICK(k) do { long long t_now; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_now) :: "memory"); \
+		t_sum[k] += t_now - t_last; t_last = t_now; } while (0)
+// the same after `val` has been computed (the clock read cannot be scheduled ahead of it)
+#define APM_TICK_AFTER(k, val) do { asm volatile("" :: "d"(val) : "memory"); APM_TICK(k); } while (0)
+#else
+#define APM_TICK(k) do { } while (0)
+#define APM_TICK_AFTER(k, val) do { } while (0)
+#endif
+
 template<class M>
 __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) cluster_run_kernel(const DevState S, const ClusterArgs ca) {
 	extern __shared__ __align__(128) unsigned char fused_smem[];
+#ifdef APM_CLUSTER_TIMING
+	long long t_sum[4] = { 0, 0, 0, 0 }, t_last = clock64();
+#endif
 	const FusedArgs & a = ca.f;
 	const int CL = ca.cl, WC = ca.wc;
 	const uint32_t rank = cluster_ctarank();
@@ -795,71 +828,160 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) cluster_run_kernel(co
 	mbar_wait(bar, 0);
 
 	// ---- this CTA's block of the ensemble, resident in shared memory
+	// (the localized DevState -- some forty pointers -- lives in shared memory, not in every thread's
+	// registers: the row loop needs the registers for independent row evaluations in flight)
 	unsigned char * mem = fused_smem + fused_table_bytes(a.n_rows);
-	const DevState L = fused_localize_block(S, ens, k0, nloc, mem);
+	__shared__ DevState L_shared;
+	{
+		const DevState L_tmp = fused_localize_block(S, ens, k0, nloc, mem);
+		if (tid == 0)
+			L_shared = L_tmp;
+		__syncthreads();
+	}
+	const DevState & L = L_shared;
 	double * pack_first = reinterpret_cast<double *>(mem + fused_state_bytes(ca.gmax, n));
 	double * pack_last = pack_first + LADDER_PACK(n);
-	double * red = pack_last + LADDER_PACK(n); // [gmax][WC]
+	double * red = pack_last + LADDER_PACK(n); // per-chain work areas, see cluster_smem_bytes
 	const double * pack_prev = rank > 0 ? cluster_map(pack_last, rank - 1) : nullptr;
 	const double * pack_next = rank + 1 < (uint32_t) CL ? cluster_map(pack_first, rank + 1) : nullptr;
 
-	double * pre = red + (size_t) ca.gmax * WC; // [gmax][n + 1]: next step's jumps, this step's log(u)
 	const int c = warp / WC, wi = warp - c * WC; // chain of this warp's group, warp within the group
 	const bool active = c < nloc;
-	// with two or more warps per chain the group's last warp computes the step's random draws
-	// while the others are in the likelihood; it also takes a share of the rows when the table is
-	// long enough for that to pay
-	const bool rng_warp = WC > 1 && wi == WC - 1;
-	const bool rng_rows = a.n_rows / (WC * 32) >= 16;
-	const int LW = (WC > 1 && !rng_rows) ? WC - 1 : WC; // warps of the group that walk the table
+	double * sums = red + (size_t) c * 2 * WC;                                      // [2][WC]
+	double * draws = red + (size_t) ca.gmax * 2 * WC + (size_t) c * CLUSTER_DRAW_RING * 32; // [RING][32]
+	double * wprop = red + (size_t) ca.gmax * (2 * WC + CLUSTER_DRAW_RING * 32) + ((size_t) c * WC + wi) * n; // [n]
+	const int LW = WC > 1 ? WC - 1 : 1;    // warps of the group that walk the table
+	const bool service = WC > 1 && wi == WC - 1;
 	const int GL = LW * 32, gl = wi * 32 + lane;
-	const int GT = WC * 32;                              // threads of the group (named barrier)
-	double * my_pre = pre + (size_t) c * (n + 1);
+	const int GT = WC * 32;                // threads of the group (named barrier)
+	const int K = 32 / (n + 1);            // steps per batch of draws (n <= 16: K >= 1)
 	const double xub = *a.xabsmax;
+	const double lo = lane < n ? L.pmin[lane] : 0.0, hi = lane < n ? L.pmax[lane] : 0.0;
 	long long step = 0;
 	if (active && wi == 0)
 		chain_propose_warp(L, c, n, lane);
 	__syncthreads();
 	for (long long round = 0; round < a.n_rounds; round++) {
-		if (active) {
+		if (active && WC == 1) {
+			// one warp per chain: the fused path's step, on this CTA's block of the ladder
 			for (int sub = 0; sub < a.n_swap; sub++, step++) {
-				double sum = 0.0;
-				if (rng_warp) {
-					// off the critical path: the bookkeeping of the step just finalised (best,
-					// n_iter, trace rows, accumulators), then this step's random draws
-					if (sub > 0)
-						chain_record_warp(L, c, step - 1, lane);
-					chain_precompute_draws(L, c, lane, my_pre);
-				}
-				if (wi < LW)
-					sum = group_loglik<M>(L, c, sdata, a.n_rows, xub, gl, GL);
-				if (WC > 1) {
-					if (lane == 0 && wi < LW)
-						red[c * WC + wi] = sum;
-					group_bar(1 + c, GT);
-				}
-				if (wi == 0) {
-					if (WC > 1 && lane == 0) {
-						sum = red[c * WC];
-						for (int w = 1; w < LW; w++)
-							sum += red[c * WC + w];
-					}
-					chain_finalize_warp<M>(L, c, M::sum0(L.prop + (size_t) c * n) + sum, WC > 1 ? my_pre + n : nullptr,
-							lane);
-					if (WC == 1)
-						chain_record_warp(L, c, step, lane);
-					if (sub + 1 < a.n_swap) {
-						if (WC > 1)
-							chain_propose_from_jumps(L, c, lane, my_pre);
-						else
-							chain_propose_warp(L, c, n, lane);
-					}
-				}
-				if (WC > 1)
-					group_bar(1 + c, GT); // the next proposal is visible to the whole group
+				const double sum = group_loglik<M>(L, L.prop + (size_t) c * n, sdata, a.n_rows, xub, gl, GL);
+				chain_finalize_warp<M>(L, c, M::sum0(L.prop + (size_t) c * n) + sum, nullptr, lane);
+				chain_record_warp(L, c, step, lane);
+				if (sub + 1 < a.n_swap)
+					chain_propose_warp(L, c, n, lane);
 			}
-			if (rng_warp)
-				chain_record_warp(L, c, step - 1, lane); // the round's last step
+		} else if (active) {
+			// the chain's state as of the round's start, replicated in the registers of every warp
+			const u64 ctr0 = L.rng_ctr[c];
+			const double beta = L.beta[c];
+			const double stepw = lane < n ? L.steps[(size_t) c * n + lane] : 0.0;
+			double cur = lane < n ? L.params[(size_t) c * n + lane] : 0.0;
+			double prop = lane < n ? L.prop[(size_t) c * n + lane] : 0.0;
+			double prob_cur = L.prob[c], prior_cur = L.prior[c];
+			const double mc[4] = { L.model_const[0], L.model_const[1], L.model_const[2], L.model_const[3] };
+			const unsigned quirks = L.quirks;
+			int accepted = 0;
+			double prob_new = 0.0, prior_new = 0.0;
+			// position of step `sub`'s draws in the ring: batch sub / K, entry sub % K (kept incrementally)
+			int ring_b = 0, ring_j = 0;
+
+			// markov_chain_step's second half for step `sub` -- the same instructions in every warp of
+			// the group -- and the next proposal (do_step): first attempt from the batch of draws,
+			// the rare out-of-bounds rest as usual.  Leaves (accepted, prob_new, prior_new) of this
+			// step and updates (cur, prob_cur, prior_cur, prop).
+			auto decide = [&](int sub, double & prop_done) {
+				const int par = sub & 1;
+				double sum = sums[par * WC];
+				for (int w = 1; w < LW; w++)
+					sum += sums[par * WC + w];
+				prior_new = prior_cur;
+				if (M::HAS_PRIOR)
+					prior_new = M::prior(wprop, n, mc);
+				prob_new = M::finish(beta, M::sum0(wprop) + sum, prior_new, wprop, mc);
+				const double * dr = draws + ring_b * 32 + ring_j * (n + 1);
+				if (prob_new == prob_cur)
+					accepted = 1;
+				else if (prob_new > prob_cur)
+					accepted = 1;
+				else
+					accepted = dr[n] < (prob_new - prob_cur) ? 1 : 0;
+				prop_done = prop;
+				if (accepted) {
+					cur = prop;
+					prob_cur = prob_new;
+					prior_cur = prior_new;
+				} else if (quirks & 2u) {
+					prior_cur = prior_new;
+				}
+				if (++ring_j == K) {
+					ring_j = 0;
+					ring_b = (ring_b + 1) % CLUSTER_DRAW_RING;
+				}
+				if (sub + 1 < a.n_swap && lane < n) {
+					double v = cur + draws[ring_b * 32 + ring_j * (n + 1) + lane];
+					if (v > hi || v < lo)
+						v = propose_coordinate(L, c, ctr0 + (u64) (sub + 1), lane, cur, stepw);
+					prop = v;
+				}
+			};
+
+			if (service) {
+				// a private copy of the state's addresses: the bookkeeping below is chains of
+				// read-modify-writes, which must not wait for the pointers to be re-read after every store
+				const DevState Lr = L;
+				int pend_acc = 0;
+				double pend_prob = 0.0, pend_prior = 0.0, pend_prop = 0.0;
+				int next_batch_at = K - 1, next_batch = 1; // batch b is drawn at the start of step b K - 1
+				for (int sub = 0; sub < a.n_swap; sub++, step++) {
+					APM_TICK(0);
+					if (sub > 0) { // write down step sub - 1
+						chain_apply_step_warp(Lr, c, pend_acc, pend_prob, pend_prior, pend_prop, lane);
+						chain_record_warp(Lr, c, step - 1, lane);
+					}
+					if (sub == 0)
+						chain_draw_batch(Lr, c, ctr0, K, lane, draws);
+					if (sub == next_batch_at) {
+						if (sub + 1 < a.n_swap)
+							chain_draw_batch(Lr, c, ctr0 + (u64) next_batch * K, K, lane,
+									draws + (next_batch % CLUSTER_DRAW_RING) * 32);
+						next_batch_at += K;
+						next_batch++;
+					}
+					if (lane < n)
+						wprop[lane] = prop;
+					__syncwarp();
+					APM_TICK(1);
+					group_bar(1 + c, GT);
+					APM_TICK(2);
+					decide(sub, pend_prop);
+					pend_acc = accepted;
+					pend_prob = prob_new;
+					pend_prior = prior_new;
+					APM_TICK_AFTER(3, prop);
+				}
+				// the round's last step
+				chain_apply_step_warp(Lr, c, pend_acc, pend_prob, pend_prior, pend_prop, lane);
+				chain_record_warp(Lr, c, step - 1, lane);
+				if (lane == 0)
+					Lr.pend[c] = PEND_NONE;
+			} else {
+				double unused;
+				for (int sub = 0; sub < a.n_swap; sub++, step++) {
+					APM_TICK(0);
+					if (lane < n)
+						wprop[lane] = prop;
+					__syncwarp();
+					const double part = group_loglik<M>(L, wprop, sdata, a.n_rows, xub, gl, GL);
+					if (lane == 0)
+						sums[(sub & 1) * WC + wi] = part;
+					APM_TICK_AFTER(1, part);
+					group_bar(1 + c, GT);
+					APM_TICK(2);
+					decide(sub, unused);
+					APM_TICK_AFTER(3, prop);
+				}
+			}
 		} else {
 			step += a.n_swap;
 		}
@@ -887,6 +1009,11 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) cluster_run_kernel(co
 			chain_propose_warp(L, c, n, lane);
 		__syncthreads();
 	}
+#ifdef APM_CLUSTER_TIMING
+	if (ca.timing != nullptr && blockIdx.x == 0 && lane == 0)
+		for (int k = 0; k < 4; k++)
+			ca.timing[warp * 8 + k] = t_sum[k];
+#endif
 	fused_writeback_block(S, L, ens, k0, rank == 0);
 }
 
