@@ -9,6 +9,7 @@
  * Everything read from or written to disk goes through the chain structs, so the files are
  * produced by the same formatting code paths as in the reference.
  */
+#include <pthread.h>
 #include <signal.h>
 #include <time.h>
 #include "apm_session.h"
@@ -502,6 +503,48 @@ static void on_sigusr(int signalnr) {
 	dump_requested = 1;
 }
 
+/* ------------------------------------------------------------------ dump writer
+ * The per-iteration text of run_sampler() (reference src/parallel_tempering.c:396-401,
+ * src/mcmc_dump.c:79-88) for one engine call's trace.  At GPU step rates formatting it is the
+ * slow part of `run` (two "%e" conversions per chain and iteration), so (a) every file is written
+ * by one thread of an OpenMP team -- a file's bytes and their order do not depend on the team --
+ * and (b) the job runs on a helper thread while the engine computes the next call's trace into
+ * the other buffer. */
+typedef struct {
+	const apm_session * s;
+	FILE ** prob_files;
+	const double * t_prob, * t_dl, * t_par;
+	long long n_prob_rows, n_par_rows;
+	int n_dumped, params_chains;
+} write_job;
+
+static void * write_trace(void * arg) {
+	const write_job * w = (const write_job *) arg;
+	const apm_session * s = w->s;
+	const int n_chains = s->n_chains, n_par = s->n_par, n_beta = s->n_beta;
+	int k;
+#pragma omp parallel for schedule(dynamic, 1)
+	for (k = 0; k < n_chains + w->n_dumped * n_par; k++) {
+		long long r;
+		if (k < n_chains) {
+			/* prob-chain<k>.dump: "prob, prob - prior" of every chain */
+			FILE * f = w->prob_files[k];
+			for (r = 0; r < w->n_prob_rows; r++)
+				fprintf(f, "%6e\t%6e\n", w->t_prob[r * n_chains + k], w->t_dl[r * n_chains + k]);
+		} else {
+			/* <name>-chain-<i>.prob.dump: one parameter of one dumped chain */
+			const int i = (k - n_chains) / n_par, j = (k - n_chains) % n_par;
+			const mcmc * m = w->params_chains == 2 ? s->chains[i] : s->chains[i * n_beta];
+			FILE * f = m->files != NULL ? m->files[j] : NULL;
+			if (f == NULL)
+				continue;
+			for (r = 0; r < w->n_par_rows; r++)
+				fprintf(f, DUMP_FORMAT "\n", w->t_par[((size_t) r * w->n_dumped + i) * n_par + j]);
+		}
+	}
+	return NULL;
+}
+
 static void report(apm_session * s) {
 	int e, i;
 	printf("printing chain parameters: \n");
@@ -572,10 +615,13 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 	apm_gpu_trace_cfg trace;
 	unsigned long iter, interval_rounds;
 	long long max_rows, call_cap = 1;
-	double * t_prob = NULL, *t_dl = NULL, *t_par = NULL;
-	size_t t_cap = 0;
+	double * t_prob[2] = { NULL, NULL }, *t_dl[2] = { NULL, NULL }, *t_par[2] = { NULL, NULL };
+	size_t t_cap[2] = { 0, 0 };
+	write_job job;
+	pthread_t writer;
+	int writer_active = 0, cur = 0;
 	char name[64];
-	int e, i, j, n_dumped;
+	int e, i, n_dumped;
 
 #ifdef DUMP_ALL_CHAINS
 	trace.params_chains = 2;
@@ -647,7 +693,7 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 		 * about half a second of device time, so that signals are honoured promptly */
 		const unsigned long done_rounds = iter / n_swap;
 		long long rounds = (long long) (interval_rounds - done_rounds % interval_rounds);
-		long long n_prob_rows = 0, n_par_rows = 0, r;
+		long long n_prob_rows = 0, n_par_rows = 0;
 		struct timespec t0, t1;
 		double secs;
 		size_t need;
@@ -663,15 +709,15 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 		clock_gettime(CLOCK_MONOTONIC, &t0);
 		apm_gpu_check(s, apm_gpu_run(s->gpu, rounds, n_swap, &trace), "sampling");
 		need = (size_t) rounds * n_swap;
-		if (need > t_cap) {
-			free(t_prob); free(t_dl); free(t_par);
-			t_cap = need;
-			t_prob = (double *) malloc(t_cap * n_chains * sizeof(double));
-			t_dl = (double *) malloc(t_cap * n_chains * sizeof(double));
-			t_par = (double *) malloc(t_cap * n_dumped * n_par * sizeof(double));
-			assert(t_prob != NULL && t_dl != NULL && t_par != NULL);
+		if (need > t_cap[cur]) { /* (buffer `cur` is idle: its writer was joined one call ago) */
+			free(t_prob[cur]); free(t_dl[cur]); free(t_par[cur]);
+			t_cap[cur] = need;
+			t_prob[cur] = (double *) malloc(need * n_chains * sizeof(double));
+			t_dl[cur] = (double *) malloc(need * n_chains * sizeof(double));
+			t_par[cur] = (double *) malloc(need * n_dumped * n_par * sizeof(double) + 8);
+			assert(t_prob[cur] != NULL && t_dl[cur] != NULL && t_par[cur] != NULL);
 		}
-		apm_gpu_check(s, apm_gpu_read_trace(s->gpu, t_prob, t_dl, t_par, &n_prob_rows, &n_par_rows),
+		apm_gpu_check(s, apm_gpu_read_trace(s->gpu, t_prob[cur], t_dl[cur], t_par[cur], &n_prob_rows, &n_par_rows),
 				"reading the trace");
 		clock_gettime(CLOCK_MONOTONIC, &t1);
 		secs = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
@@ -680,25 +726,25 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 		else if (secs > 1.0 && call_cap > 1)
 			call_cap /= 2;
 
-		/* the per-iteration text of run_sampler(): prob-chain<k>.dump gets "prob, prob - prior"
-		 * of every chain, the parameter dumps get the dumped chains' vectors */
-		for (i = 0; i < n_chains; i++) {
-			FILE * f = prob_files[i];
-			for (r = 0; r < n_prob_rows; r++)
-				fprintf(f, "%6e\t%6e\n", t_prob[r * n_chains + i], t_dl[r * n_chains + i]);
+		/* hand the trace to the writer; the previous job (other buffer, same files) must be done */
+		if (writer_active)
+			pthread_join(writer, NULL);
+		job.s = s;
+		job.prob_files = prob_files;
+		job.t_prob = t_prob[cur];
+		job.t_dl = t_dl[cur];
+		job.t_par = t_par[cur];
+		job.n_prob_rows = n_prob_rows;
+		job.n_par_rows = n_par_rows;
+		job.n_dumped = n_dumped;
+		job.params_chains = trace.params_chains;
+		if (pthread_create(&writer, NULL, write_trace, &job) == 0) {
+			writer_active = 1;
+		} else {
+			writer_active = 0;
+			write_trace(&job);
 		}
-		for (i = 0; i < n_dumped; i++) {
-			const mcmc * m = trace.params_chains == 2 ? s->chains[i] : s->chains[i * n_beta];
-			if (m->files == NULL)
-				continue;
-			for (j = 0; j < n_par; j++) {
-				FILE * f = m->files[j];
-				if (f == NULL)
-					continue;
-				for (r = 0; r < n_par_rows; r++)
-					fprintf(f, DUMP_FORMAT "\n", t_par[((size_t) r * n_dumped + i) * n_par + j]);
-			}
-		}
+		cur ^= 1;
 		iter += (unsigned long) rounds * n_swap;
 
 		if (iter % PRINT_PROB_INTERVAL == 0) { /* dump() */
@@ -707,6 +753,10 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 			if (dump_requested) {
 				report(s);
 				dump_requested = 0;
+				if (writer_active) {
+					pthread_join(writer, NULL);
+					writer_active = 0;
+				}
 				for (i = 0; i < n_chains; i++)
 					fflush(prob_files[i]);
 			}
@@ -724,6 +774,8 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 			fflush(stdout);
 		}
 	}
+	if (writer_active)
+		pthread_join(writer, NULL);
 	apm_session_pull(s, 0, n_chains);
 	for (e = 0; e < n_ens; e++)
 		fclose(accept_files[e]);
@@ -732,6 +784,12 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 	printf("handled %lu iterations on %d chains\n", iter, n_chains);
 	report(s);
 	write_run_statistics(s);
-	free(t_prob); free(t_dl); free(t_par); free(prob_files); free(accept_files);
+	for (i = 0; i < 2; i++) {
+		free(t_prob[i]);
+		free(t_dl[i]);
+		free(t_par[i]);
+	}
+	free(prob_files);
+	free(accept_files);
 	apm_session_close(s);
 }

@@ -36,7 +36,7 @@ def build_host_over_oracle(name, model, ccflags):
                                            "apm_analyse.c")]
     src += [os.path.join(ROOT, "apemost_b200", "compat", "gsl", "gsl_compat.c"),
             os.path.join(ROOT, "tests", "host_shim", "apm_gpu_over_oracle.c")]
-    cmd = ["gcc", "-O2", "-std=gnu99", "-I", os.path.join(HOST, "include"), "-I", os.path.join(ROOT, "include"),
+    cmd = ["gcc", "-O2", "-std=gnu99", "-fopenmp", "-pthread", "-I", os.path.join(HOST, "include"), "-I", os.path.join(ROOT, "include"),
            "-I", os.path.join(ROOT, "apemost_b200", "compat"), "-I", os.path.join(ROOT, "oracle"),
            f"-DAPM_MODEL_ID={MODEL_IDS[model]}", f'-DAPM_MODEL_NAME="{model}"', *ccflags, *src,
            os.path.join(BUILD, "liboracle.so"), f"-Wl,-rpath,{BUILD}", "-lm", "-lgomp", "-o", exe]
