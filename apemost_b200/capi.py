@@ -238,6 +238,15 @@ class EngineBase:
                 for p in prog[:min(nprog.value, progress_capacity)]]
         return status, rows
 
+    # -- steps with an accept log (assess_acceptance_rate's inner loop) -------------
+    def steps(self, kind, n_steps, select=None):
+        log = np.zeros((n_steps, self.n_chains), dtype=np.uint8)
+        sel = None if select is None else np.ascontiguousarray(select, dtype=np.uint8)
+        f = self._fn("steps")
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]
+        self._check(f(self._h, None if sel is None else sel.ctypes.data, int(kind), int(n_steps), log.ctypes.data))
+        return log
+
     # -- -DADAPT -------------------------------------------------------------------
     def set_adapt(self, enabled=True, target_acceptance_rate=0.5):
         f = self._fn("set_adapt")

@@ -17,7 +17,8 @@ typedef unsigned long long u64;
 
 // calibration state machine phases (markov_chain_calibrate = burn_in + _orig)
 enum {
-	CAL_IDLE = 0, CAL_BURN_A = 1, CAL_BURN_B = 2, CAL_SINGLE = 3, CAL_FULL = 4, CAL_DONE = 5
+	CAL_IDLE = 0, CAL_BURN_A = 1, CAL_BURN_B = 2, CAL_SINGLE = 3, CAL_FULL = 4, CAL_DONE = 5,
+	CAL_STEPS = 6 // apm_gpu_steps: a fixed number of steps of one kind, accept log kept
 };
 
 struct CalState {
@@ -30,6 +31,9 @@ struct CalState {
 	u64 iter;
 	double rat_limit;
 	double saved_steps[APM_MAX_PAR];
+	// CAL_STEPS
+	long long steps_left, steps_done;
+	u64 last_count;
 };
 
 struct CalibCfgDev {
@@ -42,6 +46,10 @@ struct CalibCfgDev {
 	int skip_calibrate;
 	int iter_readjust;
 	int no_rescaling_limit;
+	// apm_gpu_steps (steps_n > 0): steps_n x { step of kind steps_kind; mcmc_check_best } instead of a
+	// calibration; steps_kind = parameter index (markov_chain_step_for) or n_par (markov_chain_step)
+	int steps_kind;
+	long long steps_n;
 };
 
 struct ProgressRow {
@@ -95,6 +103,7 @@ struct DevState {
 	long long progress_cap;
 	unsigned long long * progress_n;
 	int * n_active;    // chains still calibrating (device counter)
+	unsigned char * alog; // apm_gpu_steps: [steps][n_chains] 1 = the step was accepted
 	// compacted list of the chains whose proposal is pending (calibration: the likelihood
 	// kernel only visits these).  Two buffers / counters used alternately: the control kernel
 	// of step s fills [w] for the next likelihood launch and clears [1 - w].
@@ -593,12 +602,26 @@ APM_D void cal_burn_midpoint(const DevState & S, int g, const CalibCfgDev & cfg)
 	}
 }
 
+// the counter whose change tells whether a step of `kind` was accepted: this is how
+// assess_acceptance_rate keeps its log (reference src/markov_chain.c:146-172)
+APM_D u64 steps_counter(const DevState & S, int g, int kind) {
+	return kind == S.n_par ? S.accept[g] : S.pacc[(size_t) g * S.n_par + kind];
+}
+
 APM_D void cal_begin(const DevState & S, int g, const CalibCfgDev & cfg) {
 	CalState & c = S.cal[g];
 	const int n = S.n_par;
 	c.status = 0;
 	c.iter = 0;
 	c.sub = 0;
+	if (cfg.steps_n > 0) {
+		c.phase = CAL_STEPS;
+		c.sub = cfg.steps_kind;
+		c.steps_left = cfg.steps_n;
+		c.steps_done = 0;
+		c.last_count = steps_counter(S, g, cfg.steps_kind);
+		return;
+	}
 	for (int i = 0; i < n; i++) {
 		c.saved_steps[i] = S.steps[(size_t) g * n + i];                 // markov_chain.c:38
 		S.steps[(size_t) g * n + i] = (S.pmax[i] - S.pmin[i]) * 0.1;    // :39-41
@@ -618,6 +641,7 @@ APM_D int cal_next_kind(const DevState & S, int g) {
 	case CAL_FULL:
 		return S.n_par;
 	case CAL_SINGLE:
+	case CAL_STEPS:
 		return c.sub;
 	default:
 		return PEND_NONE;
@@ -630,6 +654,17 @@ APM_D void cal_after_step(const DevState & S, int g, const CalibCfgDev & cfg) {
 	const int iter_readjust = cfg.iter_readjust > 0 ? cfg.iter_readjust : 200;
 	const int no_rescaling_limit = cfg.no_rescaling_limit > 0 ? cfg.no_rescaling_limit : 15;
 	switch (c.phase) {
+	case CAL_STEPS: {
+		chain_check_best(S, g);
+		const u64 now = steps_counter(S, g, c.sub);
+		if (S.alog != nullptr)
+			S.alog[(size_t) c.steps_done * S.n_chains + S.g_base + g] = now != c.last_count ? 1 : 0;
+		c.last_count = now;
+		c.steps_done++;
+		if (--c.steps_left == 0)
+			cal_finish(S, g, 0);
+		return;
+	}
 	case CAL_BURN_A:
 	case CAL_BURN_B: {
 		// blocks of 200 full steps, mcmc_check_best once per block (markov_chain.c:46-57,61-72)

@@ -980,9 +980,12 @@ extern "C" int apm_gpu_read_trace(apm_gpu * h, double * prob, double * dl, doubl
 
 // ------------------------------------------------------------------ calibrate
 template<class M>
-static int calibrate_t(apm_gpu * h, const apm_gpu_calib_cfg * cfg, int * status, int n_selected) {
+static int calibrate_t(apm_gpu * h, const apm_gpu_calib_cfg * cfg, int * status, int n_selected, int steps_kind,
+		long long steps_n) {
 	AdvArgs a;
 	memset(&a, 0, sizeof(a));
+	a.cal.steps_kind = steps_kind; // steps_n > 0: apm_gpu_steps, not a calibration
+	a.cal.steps_n = steps_n;
 	a.cal.burn_in_iterations = cfg->burn_in_iterations;
 	a.cal.desired_acceptance_rate = cfg->desired_acceptance_rate;
 	a.cal.max_ar_deviation = cfg->max_ar_deviation;
@@ -1021,7 +1024,7 @@ static int calibrate_t(apm_gpu * h, const apm_gpu_calib_cfg * cfg, int * status,
 		h->launches++;
 	}
 	int active = n_selected;
-	const int block = 200;
+	const int block = steps_n > 0 ? (int) std::min<long long>(steps_n, 200) : 200;
 	long long step = 0;
 	while (active > 0) {
 		int rc = replan(h, active); // the row splits follow the number of chains left
@@ -1094,7 +1097,7 @@ extern "C" int apm_gpu_calibrate(apm_gpu * h, const unsigned char * select, cons
 	int n_selected = 0;
 	for (unsigned char c : sel)
 		n_selected += c != 0;
-	auto go = [&]() -> int { DISPATCH(h->cfg.model_id, calibrate_t, h, cfg, status, n_selected) };
+	auto go = [&]() -> int { DISPATCH(h->cfg.model_id, calibrate_t, h, cfg, status, n_selected, 0, 0) };
 	int rc = go();
 	if (rc != APM_OK && rc != APM_ECALIB)
 		return rc;
@@ -1114,6 +1117,48 @@ extern "C" int apm_gpu_calibrate(apm_gpu * h, const unsigned char * select, cons
 			return x.param < y.param;
 		});
 	}
+	return rc;
+}
+
+// ------------------------------------------------------------------ steps with an accept log
+extern "C" int apm_gpu_steps(apm_gpu * h, const unsigned char * select, int kind, long long n_steps,
+		unsigned char * accepted) {
+	if (!h || n_steps < 0 || kind < 0 || kind > h->cfg.n_par)
+		return APM_EINVAL;
+	if (!h->have_data || !h->have_bounds)
+		return fail(h, APM_ESTATE, "apm_gpu_set_data and apm_gpu_set_bounds must be called first");
+	if (n_steps == 0)
+		return APM_OK;
+	CU(cudaSetDevice(h->cfg.device));
+	std::vector<unsigned char> sel(h->n_chains, 1);
+	if (select)
+		memcpy(sel.data(), select, h->n_chains);
+	CU(cudaMemcpy(h->d_select, sel.data(), h->n_chains, cudaMemcpyHostToDevice));
+	CU(cudaMemset(h->S.n_active, 0, sizeof(int)));
+	CU(cudaMemset(h->S.progress_n, 0, sizeof(unsigned long long)));
+	if (h->S.progress)
+		cudaFree(h->S.progress);
+	h->S.progress = nullptr;
+	h->S.progress_cap = 0;
+	int n_selected = 0;
+	for (unsigned char c : sel)
+		n_selected += c != 0;
+	const size_t log_bytes = (size_t) n_steps * h->n_chains;
+	unsigned char * d_log = nullptr;
+	CU(cudaMalloc((void **) &d_log, log_bytes));
+	CU(cudaMemset(d_log, 0, log_bytes));
+	h->S.alog = d_log;
+	apm_gpu_calib_cfg cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	auto go = [&]() -> int { DISPATCH(h->cfg.model_id, calibrate_t, h, &cfg, nullptr, n_selected, kind, n_steps) };
+	int rc = go();
+	h->S.alog = nullptr;
+	cudaError_t e = cudaSuccess;
+	if (rc == APM_OK && accepted)
+		e = cudaMemcpy(accepted, d_log, log_bytes, cudaMemcpyDeviceToHost);
+	cudaFree(d_log);
+	if (e != cudaSuccess)
+		return fail(h, APM_ECUDA, "reading the accept log failed: %s", cudaGetErrorString(e));
 	return rc;
 }
 

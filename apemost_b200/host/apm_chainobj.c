@@ -224,6 +224,20 @@ void set_params_best(mcmc * m, const gsl_vector * v) { gsl_vector_memcpy(m->para
 gsl_vector * get_steps(const mcmc * m) { return m->params_step; }
 double get_steps_for(const mcmc * m, const unsigned int i) { return gsl_vector_get(m->params_step, i); }
 void set_steps_for(mcmc * m, const double v, const unsigned int i) { gsl_vector_set(m->params_step, i, v); }
+/* reference src/mcmc_gettersetter.c:263-266 */
+double get_steps_for_normalized(const mcmc * m, const unsigned int i) {
+	return get_steps_for(m, i) / (get_params_max_for(m, i) - get_params_min_for(m, i));
+}
+/* reference src/mcmc_gettersetter.c:119-127 */
+void reset_accept_rejects(mcmc * m) {
+	unsigned int i;
+	for (i = 0; i < get_n_par(m); i++) {
+		m->params_accepts[i] = 0;
+		m->params_rejects[i] = 0;
+	}
+	m->reject = 0;
+	m->accept = 0;
+}
 gsl_vector * get_params_min(const mcmc * m) { return m->params_min; }
 gsl_vector * get_params_max(const mcmc * m) { return m->params_max; }
 double get_params_min_for(const mcmc * m, const unsigned int i) { return gsl_vector_get(m->params_min, i); }

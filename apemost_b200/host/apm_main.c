@@ -147,6 +147,11 @@ void check(void) {
 #else
 	printf("off\n");
 #endif
+#ifdef CALIBRATE_ALTERNATE
+	printf("\tCALIBRATE_ALTERNATE: on (assess_acceptance_rate + markov_chain_calibrate_alt)\n");
+#else
+	printf("\tCALIBRATE_ALTERNATE: off (markov_chain_calibrate_orig)\n");
+#endif
 #ifdef ADAPT
 	printf("\tADAPT: on (1%% step width rescaling per round once 20000 moves are counted)\n");
 #else

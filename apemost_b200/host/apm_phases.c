@@ -320,6 +320,35 @@ static void calibrate_selected(apm_session * s, const unsigned char * select, in
 	long long cap = 0, n_rows = 0;
 	apm_gpu_calib_progress * rows = NULL;
 	int g, rc, n_sel = 0;
+#if defined(CALIBRATE_QUADRATIC) || defined(CALIBRATE_MULTILIN)
+#error "of the alternate calibrators only CALIBRATE_ALTERNATE is built (apm_calibrate_alt.c)"
+#endif
+#ifdef CALIBRATE_ALTERNATE
+	if (!skip) {
+		/* markov_chain_calibrate = burn_in + markov_chain_calibrate_alt, one chain after the other
+		 * like the reference's loop (src/parallel_tempering.c:173-197 with one thread) */
+		unsigned char * one = (unsigned char *) calloc(s->n_chains, 1);
+		for (g = 0; g < s->n_chains; g++) {
+			if (!select[g])
+				continue;
+			one[g] = 1;
+			calib_config(&cfg, 1 /* burn_in only */);
+			apm_gpu_check(s, apm_gpu_calibrate(s->gpu, one, &cfg, NULL, NULL, 0, NULL), "burn-in");
+			one[g] = 0;
+			apm_session_pull(s, g, 1);
+			apm_set_output_dir(s->ens_first + g / s->n_beta);
+			apm_calibrate_alt(s, g, TARGET_ACCEPTANCE_RATE, MAX_AR_DEVIATION, ITER_LIMIT);
+		}
+		apm_set_output_dir(-1);
+		free(one);
+		free(status);
+		if (rows_out != NULL) {
+			*rows_out = NULL; /* calibration_progress.data has been written by the calibrator itself */
+			*n_rows_out = 0;
+		}
+		return;
+	}
+#endif
 	calib_config(&cfg, skip);
 	for (g = 0; g < s->n_chains; g++)
 		n_sel += select[g] != 0;
@@ -367,7 +396,8 @@ void calibrate_first(void) {
 	apm_session_pull(s, 0, s->n_chains);
 	for (e = 0; e < s->n_ens; e++) {
 		apm_set_output_dir(s->ens_first + e);
-		apm_write_calibration_progress(rows, n_rows, which[e]);
+		if (rows != NULL)
+			apm_write_calibration_progress(rows, n_rows, which[e]);
 		write_calibrations_file(apm_ensemble(s, e), 1);
 		write_params_file(apm_ensemble(s, e)[0]);
 	}

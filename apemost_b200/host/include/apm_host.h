@@ -172,6 +172,8 @@ void set_params_best(mcmc * m, const gsl_vector * v);
 gsl_vector * get_steps(const mcmc * m);
 double get_steps_for(const mcmc * m, const unsigned int i);
 void set_steps_for(mcmc * m, const double v, const unsigned int i);
+double get_steps_for_normalized(const mcmc * m, const unsigned int i); /* step / (max - min) */
+void reset_accept_rejects(mcmc * m);
 gsl_vector * get_params_min(const mcmc * m);
 gsl_vector * get_params_max(const mcmc * m);
 double get_params_min_for(const mcmc * m, const unsigned int i);

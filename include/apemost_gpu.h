@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define APM_GPU_ABI_VERSION 3
+#define APM_GPU_ABI_VERSION 4
 
 /* ---- error codes -------------------------------------------------------- */
 #define APM_OK          0
@@ -203,6 +203,15 @@ int apm_gpu_calibrate(apm_gpu * h, const unsigned char * select,
 		const apm_gpu_calib_cfg * cfg, int * status,
 		apm_gpu_calib_progress * progress, long long progress_capacity,
 		long long * n_progress);
+
+/* ---- n_steps x { markov_chain_step_for(kind) -- or markov_chain_step if kind == n_par --;
+ * mcmc_check_best } for the selected chains (NULL = all), in lockstep: the inner loop of
+ * assess_acceptance_rate (reference src/markov_chain.c:143-172), on which the alternate
+ * calibrators are built (src/markov_chain_calibrate.c:33-1037).  accepted[step * n_chains + g]
+ * receives 1 where chain g's step was accepted (what assess_acceptance_rate keeps in its bit
+ * field), 0 otherwise and for chains not selected. --------------------------------------- */
+int apm_gpu_steps(apm_gpu * h, const unsigned char * select, int kind,
+		long long n_steps, unsigned char * accepted /*[n_steps][n_chains]*/);
 
 /* ---- adapt() as compiled with -DADAPT (reference src/parallel_tempering.c:282-302, called
  * once per round before the swap, :404): a chain whose per-parameter accept + reject counter

@@ -1149,6 +1149,37 @@ int orc_calibrate(orc_engine * e, const unsigned char * select, const orc_calib_
 	return any_failed ? -6 : 0;
 }
 
+/* n_steps x { markov_chain_step_for(kind) or markov_chain_step; mcmc_check_best } with the accept
+ * log assess_acceptance_rate keeps: ref src/markov_chain.c:143-172.  Chain after chain (each chain
+ * does all its steps before the next starts), which in MT19937 mode is the reference's draw order
+ * when one chain is selected. */
+int orc_steps(orc_engine * e, const unsigned char * select, int kind, long long n_steps,
+		unsigned char * accepted) {
+	const int n = e->cfg.n_par;
+	int g;
+	long long i;
+	if (kind < 0 || kind > n || n_steps < 0)
+		return -1;
+	if (accepted)
+		memset(accepted, 0, (size_t) n_steps * e->n_chains);
+	for (g = 0; g < e->n_chains; g++) {
+		chain_t * c = e->chains + g;
+		if (select != NULL && !select[g])
+			continue;
+		for (i = 0; i < n_steps; i++) {
+			const u64 before = kind == n ? c->accept : c->pacc[kind];
+			if (kind == n)
+				markov_chain_step(e, g, c);
+			else
+				markov_chain_step_for(e, g, c, (unsigned) kind);
+			mcmc_check_best(e, c);
+			if (accepted)
+				accepted[(size_t) i * e->n_chains + g] = (kind == n ? c->accept : c->pacc[kind]) != before;
+		}
+	}
+	return 0;
+}
+
 int orc_reset_stats(orc_engine * e) {
 	int g;
 	for (g = 0; g < e->n_chains; g++) {

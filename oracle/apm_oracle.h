@@ -126,6 +126,9 @@ int orc_read_trace(orc_engine * e, double * prob, double * prob_minus_prior,
 int orc_calibrate(orc_engine * e, const unsigned char * select,
 		const orc_calib_cfg * cfg, int * status, orc_calib_progress * progress,
 		long long progress_capacity, long long * n_progress);
+/* the inner loop of assess_acceptance_rate (ref src/markov_chain.c:143-172); mirrors apm_gpu_steps */
+int orc_steps(orc_engine * e, const unsigned char * select, int kind, long long n_steps,
+		unsigned char * accepted);
 /* -DADAPT (ref src/parallel_tempering.c:282-302) and -DRANDOMSWAP
  * (ref src/parallel_tempering_interaction.c:47-65,130-131) */
 int orc_set_adapt(orc_engine * e, int enabled, double target_acceptance_rate);

@@ -225,6 +225,15 @@ def all_phase_fixtures():
     fx["c1_randomswap_phases"] = phases_fixture(
         "simplesin", C1_ROWS, "testlc.dat", None, dict(small, GSL_RNG_SEED=17),
         ccflags_extra="-DRANDOMSWAP", suffix="_pin_rswap", engine_opts=dict(random_swap=1))
+    # -DCALIBRATE_ALTERNATE: assess_acceptance_rate + markov_chain_calibrate_alt replace _orig
+    # (pins the host layer's apm_calibrate_alt.c through tests/test_host_cpu.py).  The reference's
+    # alternate calibrator often gives up on the hot chains ("iteration limit reached", exit 1), so
+    # the fixture calibrates chains 0 and 1 with it and only burns the others in
+    # (-DSKIP_CALIBRATE_ALLCHAINS), with a seed for which it converges.
+    fx["c1_altcal_phases"] = phases_fixture(
+        "simplesin", C1_ROWS, "testlc.dat", None, dict(small, GSL_RNG_SEED=23),
+        ccflags_extra="-DCALIBRATE_ALTERNATE -DSKIP_CALIBRATE_ALLCHAINS", suffix="_pin_altskip",
+        engine_opts=dict(host_only=1))
     return fx
 
 

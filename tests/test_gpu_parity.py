@@ -409,6 +409,36 @@ def test_calibration_selection_and_failure_status(capi, path):
     _compare_state(res[0][1], res[1][1])
 
 
+@pytest.mark.parametrize("path", PATHS)
+def test_steps_accept_log_equals_oracle(capi, path):
+    """apm_gpu_steps: n x { markov_chain_step_for / markov_chain_step ; mcmc_check_best } with the accept
+    log assess_acceptance_rate keeps (reference src/markov_chain.c:143-172): the log is equal bit for
+    bit, the chains' state to 1e-9, for single-parameter and full steps, on a selection of chains"""
+    fx = load("c1_phases")
+    rows = [tuple(r) for r in fx["rows"]]
+    n_par, n_beta, n_ens = len(rows), fx["config"]["N_BETA"], 2
+    data = np.loadtxt(os.path.join(GOLDEN, fx["data_file"]))
+    cal = np.array(fx["phases"]["calibrate_rest"].split(), dtype=float).reshape(n_beta, 1 + 2 * n_par)
+    res = []
+    for eng in _pair(capi, fx["model"], n_ens, n_beta, n_par=n_par, seed=37, path=path):
+        eng.set_data(data)
+        pt_flow.setup_chains(eng, rows)
+        pt_flow.apply_calibration(eng, 0, np.tile(cal[:, 0], n_ens), np.tile(cal[:, 1:1 + n_par], (n_ens, 1)),
+                                  np.tile(cal[:, 1 + n_par:], (n_ens, 1)))
+        st = eng.get_chains(fields=("params", "beta"))
+        prob, prior = eng.eval(st["params"], st["beta"])
+        eng.set_chains(0, n_ens * n_beta, prob=prob, prior=prior)
+        sel = np.zeros(n_ens * n_beta, dtype=np.uint8)
+        sel[[0, 3, 5]] = 1
+        logs = [eng.steps(1, 40, select=sel), eng.steps(n_par, 333, select=sel), eng.steps(0, 7)]
+        res.append((logs, eng.get_chains()))
+    (lg, st_g), (lc, st_c) = res
+    for a, b in zip(lg, lc):
+        np.testing.assert_array_equal(a, b)
+    assert lg[0][:, [1, 2, 4, 6, 7]].sum() == 0 and 0 < lg[1][:, 0].mean() < 1
+    _compare_state(st_g, st_c)
+
+
 # ---------------------------------------------------------------- statistical parity with the reference
 def test_evidence_and_posterior_match_reference_statistics(capi):
     """Second half of 'correctness' (north_star): with different RNG streams the engine's
