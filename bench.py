@@ -21,9 +21,12 @@ Metropolis steps actually executed (rejected ones included, swaps excluded).
 Multi-GPU (torchrun, one rank per GPU): independent ensembles are sharded over the ranks, no
 data-path collective, weak scaling (4096 chains per GPU).
 
---impl reference times the reference's CPU implementation on the host cores.  The unmodified
-reference cannot build apps/simplesin5.c, so this arm runs the CPU port of it
-(oracle/apm_oracle.c, byte-identical to the reference build on the models that do compile).
+--impl reference times the reference's own CPU implementation on the host cores: the reference
+engine (src/*.c, OpenMP over chains) with apps/simplesin5.c, whose two stale lines (SURVEY.md D1:
+it does not compile as shipped) are fixed by sed at build time -- oracle/_ref/simplesin5fix_b64_*.exe,
+built in the container by `make -C oracle refbench`, travels to the GPU box prebuilt.  Where those
+binaries are absent the arm falls back to the CPU port (oracle/apm_oracle.c, byte-identical to
+the reference build on the models that do compile; kind "port").
 """
 import argparse
 import json
@@ -138,6 +141,64 @@ def cpu_oracle_rate(data, seconds=15.0, n_threads=None):
     return rate, cores, sample, dt / steps * 1e3
 
 
+REF_EXE = os.path.join(ROOT, "oracle", "_ref", "simplesin5fix_b64_it%d.exe")
+REF_ITERS = (31, 124)   # 1 and 4 rounds of n_swap = 31 iterations (oracle/Makefile refbench)
+
+
+def reference_exe_rate(data, n_threads=None):
+    """chain-steps/s of the REFERENCE ITSELF on this box's cores: its own engine (src/*.c, OpenMP
+    over the chains of one 64-rung ladder) with apps/simplesin5.c (two stale lines fixed by sed,
+    SURVEY.md D1), built in the container as oracle/_ref/simplesin5fix_b64_it<N>.exe.  `run` is
+    executed from the same calibration_results our arm starts from, for 31 and for 124 iterations;
+    the difference removes process start-up and the parsing of the 1M-row data file.  Steps are
+    counted from the lines of prob-chain<k>.dump, because the OpenMP build's shared loop counter
+    makes it execute fewer steps than it reports.  None if the binaries are absent."""
+    import shutil
+    import tempfile
+    exes = [REF_EXE % it for it in REF_ITERS]
+    if not all(os.path.exists(e) for e in exes):
+        return None
+    cores = n_threads or os.cpu_count() or 1
+    st = chain_state(1, N_BETA, 99)
+    wd = tempfile.mkdtemp(prefix="apm_ref_")
+    try:
+        names = ["amplitude", "frequency", "phase", "offset"]
+        with open(os.path.join(wd, "params"), "w") as f:
+            for j in range(N_PAR):
+                f.write("%r\t%r\t%r\t%s\t%r\n" % (float(TRUTH[j]), float(LO[j]), float(HI[j]), names[j],
+                                                  float(st["steps"][0, j])))
+        np.savetxt(os.path.join(wd, "data"), data, fmt="%.17e", delimiter="\t")
+        with open(os.path.join(wd, "calibration_results"), "w") as f:
+            for k in range(N_BETA):
+                vals = [st["beta"][k], *st["steps"][k], *st["params"][k]]
+                f.write("\t".join("%.15e" % v for v in vals) + "\n")
+        env = dict(os.environ, OMP_NUM_THREADS=str(cores), GSL_RNG_SEED="1")
+        meas = []
+        for exe in exes:
+            for fn in os.listdir(wd):
+                if fn.endswith(".dump"):
+                    os.remove(os.path.join(wd, fn))
+            t0 = time.perf_counter()
+            r = subprocess.run([exe, "run"], cwd=wd, env=env, capture_output=True, text=True)
+            dt = time.perf_counter() - t0
+            if r.returncode != 0:
+                return None
+            lines = 0
+            for k in range(N_BETA):
+                with open(os.path.join(wd, "prob-chain%d.dump" % k), "rb") as f:
+                    lines += sum(1 for _ in f)
+            meas.append((dt, lines))
+        (t_a, n_a), (t_b, n_b) = meas
+        rate = (n_b - n_a) / (t_b - t_a)
+        sample = (f"reference build (src/*.c + apps/simplesin5.c, -DN_BETA={N_BETA}), `run` on the full {N_ROWS}-row "
+                  f"table with {cores} OpenMP threads: {n_b - n_a} chain-steps counted from the dump files in "
+                  f"{t_b - t_a:.1f} s ({REF_ITERS[1]}-iteration run minus {REF_ITERS[0]}-iteration run; "
+                  f"{N_BETA * (REF_ITERS[1] - REF_ITERS[0])} were requested)")
+        return rate, cores, sample, (t_b - t_a) / max(n_b - n_a, 1) * 1e3 * N_BETA
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+
+
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of one likelihood launch, from the newest
     committed `ncu --set full` summary under profiles/ (tools/ncu_summary.py); None if absent"""
@@ -178,6 +239,21 @@ def main():
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
+            return 0
+        real = reference_exe_rate(data)
+        if real is not None:
+            # the reference itself (one measurement covers the K "steps": each is the same bounded
+            # sample of the workload, and the run is minutes of CPU time already)
+            v, cores, sample, ms = real
+            line = {"impl": "reference", "metric": "chain-steps/sec", "value": v, "unit": "chain-steps/s",
+                    "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms * N_SWAP * N_ENS,
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                    "data": "synthetic", "config": config,
+                    "cpu_baseline": {"value": v, "unit": "chain-steps/s", "cores": cores, "kind": "reference",
+                                     "sample": sample},
+                    "e2e": {"value": v, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    "gpu_launches": 0}
+            print(json.dumps(line))
             return 0
         subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"], check=True)
         rates = []
