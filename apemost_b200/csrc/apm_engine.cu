@@ -140,19 +140,26 @@ static cudaError_t dalloc(T ** p, size_t n) {
 	case APM_MODEL_NORMAL: return FN<ModelNormal>(__VA_ARGS__); \
 	case APM_MODEL_PULSE_VROT: return FN<ModelPulseVrot>(__VA_ARGS__); \
 	case APM_MODEL_PULSE: return FN<ModelPulse>(__VA_ARGS__); \
+	case APM_MODEL_BERNOULLI: return FN<ModelBernoulli>(__VA_ARGS__); \
 	APM_USER_CASE(FN, __VA_ARGS__) \
 	default: return fail(h, APM_EINVAL, "unknown model id %d", model_id); }
 
 template<class M> static int model_npar_t(apm_gpu *) { return M::NPAR; }
-template<class M> static int model_ncols_t(apm_gpu *) { return M::HAS_DATA ? M::NCOLS : 0; }
+template<class M> static int model_ncols_t(apm_gpu *) { return M::HAS_DATA ? M::NCOLS : 0; } // -1: one per parameter
+template<class M> static int model_row_w_t(apm_gpu *) { return M::ROW_W; }
+template<class M> static int model_chunk_rows_t(apm_gpu *) { return ll_chunk<M>(); }
 static int model_npar(apm_gpu * h, int id) { DISPATCH(id, model_npar_t, h) }
 static int model_ncols(apm_gpu * h, int id) { DISPATCH(id, model_ncols_t, h) }
+static int model_row_w(apm_gpu * h, int id) { DISPATCH(id, model_row_w_t, h) }
+static int model_chunk_rows(apm_gpu * h, int id) { DISPATCH(id, model_chunk_rows_t, h) }
 
 extern "C" int apm_gpu_model_n_par(int model_id) {
 	int r = model_npar(nullptr, model_id);
 	return r < 0 ? 0 : r;
 }
 extern "C" int apm_gpu_model_n_cols(int model_id) {
+	if (model_id == APM_MODEL_BERNOULLI)
+		return -1; // one column per parameter
 	int r = model_ncols(nullptr, model_id);
 	return r < 0 ? 0 : r;
 }
@@ -197,6 +204,8 @@ extern "C" int apm_gpu_create(apm_gpu ** out, const apm_gpu_config * cfg) {
 				cfg->n_par);
 	if (cfg->model_id == APM_MODEL_PULSE && (cfg->n_par < 4 || (cfg->n_par - 2) % 2 != 0))
 		return fail(h, APM_EINVAL, "pulse needs n_par = 2 + 2k");
+	if (cfg->model_id == APM_MODEL_BERNOULLI && (cfg->n_par < 2 || cfg->n_par > 4))
+		return fail(h, APM_EINVAL, "bernoulli: n_par = number of data columns, 2 to 4 on the device");
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
 		cudaGetLastError();
@@ -390,36 +399,46 @@ extern "C" int apm_gpu_set_data(apm_gpu * h, const double * rowmajor, long long 
 	if (!h)
 		return APM_EINVAL;
 	CU(cudaSetDevice(h->cfg.device));
-	const int need = model_ncols(h, h->cfg.model_id);
-	if (need < 0)
+	int need = model_ncols(h, h->cfg.model_id);
+	if (need < -1)
 		return need;
+	if (need == -1)
+		need = h->cfg.n_par; // one column per parameter (bernoulli)
+	const int row_w = model_row_w(h, h->cfg.model_id);       // doubles per row on the device
+	const int chunk_rows = model_chunk_rows(h, h->cfg.model_id);
+	if (row_w < 0 || chunk_rows < 0)
+		return row_w < 0 ? row_w : chunk_rows;
 	if (need > 0 && (rowmajor == nullptr || n_rows < 1))
 		return fail(h, APM_EINVAL, "this model needs a data table");
 	if (need > 0 && n_cols < need)
 		return fail(h, APM_EINVAL, "model reads %d data columns, table has %d", need, n_cols);
-	if (need > 2)
-		return fail(h, APM_EINVAL, "models reading more than 2 columns are not supported yet");
+	if (need > row_w)
+		return fail(h, APM_EINVAL, "models reading more than %d columns are not supported", row_w);
 	h->n_rows = n_rows;
 	h->n_cols = n_cols;
 	h->n_chunks = 0;
 	if (need > 0) {
-		// device layout: [rows padded to a whole number of chunks][2], i.e. the gsl_matrix
-		// row-major layout for two columns (tda = 2); wider tables are narrowed on upload
-		h->n_chunks = (int) ((n_rows + LL_CHUNK - 1) / LL_CHUNK);
-		const size_t padded = (size_t) h->n_chunks * LL_CHUNK;
-		CU(ensure_cap(&h->d_data, &h->data_cap, padded * 2));
-		if (padded > (size_t) n_rows) // zero the padding rows of the last chunk
-			CU(cudaMemsetAsync(h->d_data + (size_t) n_rows * 2, 0, (padded - (size_t) n_rows) * 2 * sizeof(double),
-					h->stream));
-		if (n_cols == 2) {
-			CU(cudaMemcpyAsync(h->d_data, rowmajor, (size_t) n_rows * 2 * sizeof(double),
+		// device layout: [rows padded to a whole number of chunks][row_w]: for two columns the
+		// gsl_matrix row-major layout (tda = 2); wider tables are narrowed to the columns the model
+		// reads, narrower rows (3 columns in a 4-wide row) are padded with zeros
+		h->n_chunks = (int) ((n_rows + chunk_rows - 1) / chunk_rows);
+		const size_t padded = (size_t) h->n_chunks * chunk_rows;
+		const int take = std::min(n_cols, row_w);
+		CU(ensure_cap(&h->d_data, &h->data_cap, padded * row_w));
+		if (take < row_w) // zero everything: the padding columns and the padding rows
+			CU(cudaMemsetAsync(h->d_data, 0, padded * row_w * sizeof(double), h->stream));
+		else if (padded > (size_t) n_rows) // zero the padding rows of the last chunk
+			CU(cudaMemsetAsync(h->d_data + (size_t) n_rows * row_w, 0,
+					(padded - (size_t) n_rows) * row_w * sizeof(double), h->stream));
+		if (n_cols == row_w) {
+			CU(cudaMemcpyAsync(h->d_data, rowmajor, (size_t) n_rows * row_w * sizeof(double),
 					cudaMemcpyHostToDevice, h->stream));
 		} else {
-			CU(cudaMemcpy2DAsync(h->d_data, 2 * sizeof(double), rowmajor, (size_t) n_cols * sizeof(double),
-					2 * sizeof(double), (size_t) n_rows, cudaMemcpyHostToDevice, h->stream));
+			CU(cudaMemcpy2DAsync(h->d_data, row_w * sizeof(double), rowmajor, (size_t) n_cols * sizeof(double),
+					take * sizeof(double), (size_t) n_rows, cudaMemcpyHostToDevice, h->stream));
 		}
 		CU(cudaMemsetAsync(h->d_xabsmax, 0, sizeof(unsigned long long), h->stream));
-		absmax_col0_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_data, n_rows, h->d_xabsmax);
+		absmax_col0_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(h->d_data, n_rows, row_w, h->d_xabsmax);
 		h->launches++;
 		CU(cudaStreamSynchronize(h->stream));
 	}
@@ -694,7 +713,8 @@ static int cluster_size_for(const apm_gpu * h, bool has_data) {
 		if (gmax > FUSED_MAX_WARPS)
 			continue;
 		const int wc = gmax <= 8 ? FUSED_MAX_WARPS / gmax : 1; // named barriers 1..8 for the groups
-		if (cluster_smem_bytes(h->n_rows, gmax, wc, h->cfg.n_par) > FUSED_SMEM_LIMIT)
+		const long long n_slots = h->n_rows * (model_row_w(const_cast<apm_gpu *>(h), h->cfg.model_id) / 2);
+		if (cluster_smem_bytes(n_slots, gmax, wc, h->cfg.n_par) > FUSED_SMEM_LIMIT)
 			continue;
 		return cl;
 	}
@@ -705,7 +725,8 @@ static int choose_path(apm_gpu * h, int * path, bool for_run = false) {
 	const int has_data = model_has_data(h);
 	if (has_data < 0)
 		return has_data;
-	const size_t need = fused_table_bytes(has_data ? h->n_rows : 0) + fused_state_bytes(h->cfg.n_beta, h->cfg.n_par);
+	const long long n_slots = has_data ? h->n_rows * (model_row_w(h, h->cfg.model_id) / 2) : 0; // 16-byte units
+	const size_t need = fused_table_bytes(n_slots) + fused_state_bytes(h->cfg.n_beta, h->cfg.n_par);
 	const bool fits = need <= FUSED_SMEM_LIMIT && (!has_data || h->n_rows < (1ll << 24));
 	const bool rows_ok = !has_data || h->n_rows < (1ll << 24);
 	const int cl = for_run && rows_ok ? cluster_size_for(h, has_data != 0) : 0;
@@ -741,7 +762,8 @@ static void fused_geometry(const apm_gpu * h, bool has_data, int * threads, size
 	} else {        // a thread per chain
 		*threads = std::min(FUSED_MAX_WARPS * 32, 32 * ((h->cfg.n_beta + 31) / 32));
 	}
-	*smem = fused_table_bytes(has_data ? h->n_rows : 0) + fused_state_bytes(h->cfg.n_beta, h->cfg.n_par);
+	*smem = fused_table_bytes(has_data ? h->n_rows * (model_row_w(const_cast<apm_gpu *>(h), h->cfg.model_id) / 2) : 0)
+			+ fused_state_bytes(h->cfg.n_beta, h->cfg.n_par);
 	memset(a, 0, sizeof(*a));
 	a->data = has_data ? h->d_data : nullptr;
 	a->n_rows = has_data ? (int) h->n_rows : 0;
@@ -799,7 +821,7 @@ static int run_cluster_t(apm_gpu * h, long long n_rounds, int n_swap) {
 	memset(&lc, 0, sizeof(lc));
 	lc.gridDim = dim3((unsigned) (h->cfg.n_ensembles * ca.cl));
 	lc.blockDim = dim3((unsigned) (32 * ca.wc * ca.gmax));
-	lc.dynamicSmemBytes = cluster_smem_bytes(h->n_rows, ca.gmax, ca.wc, h->cfg.n_par);
+	lc.dynamicSmemBytes = cluster_smem_bytes(h->n_rows * (M::ROW_W / 2), ca.gmax, ca.wc, h->cfg.n_par);
 	lc.stream = h->stream;
 	cudaLaunchAttribute attr[1];
 	attr[0].id = cudaLaunchAttributeClusterDimension;

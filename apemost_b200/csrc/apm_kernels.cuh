@@ -67,6 +67,30 @@ __device__ __forceinline__ double warp_sum(double v) {
 	return v;
 }
 
+// ------------------------------------------------------------------ table rows
+// A table row on the device is M::ROW_W doubles: 2 (double2: the gsl_matrix layout of a two-column
+// file) or 4 (double4: models reading three or four columns, padded with zeros).  Everything
+// that stages rows is written for `Row<M>` and 16 * ROW_W / 2 bytes per row.
+template<int W> struct RowT;
+template<> struct RowT<2> { typedef double2 type; };
+template<> struct RowT<4> { typedef double4 type; };
+template<class M> using Row = typename RowT<M::ROW_W>::type;
+
+template<class M>
+__device__ __forceinline__ double row_accum(double acc, const typename M::Prep & q, const Row<M> & r) {
+	if constexpr (M::ROW_W == 2)
+		return M::accum(acc, q, r.x, r.y);
+	else
+		return M::accum(acc, q, r);
+}
+template<class M>
+__device__ __forceinline__ double row_accum_fast(double acc, const typename M::Prep & q, const Row<M> & r) {
+	if constexpr (M::ROW_W == 2)
+		return M::accum_fast(acc, q, r.x, r.y);
+	else
+		return M::accum_fast(acc, q, r);
+}
+
 // ------------------------------------------------------------------ tiled likelihood
 // tuning knobs (overridable at build time for kernel sweeps: tools/kernel_sweep.py)
 #ifndef APM_LL_THREADS
@@ -84,13 +108,16 @@ __device__ __forceinline__ double warp_sum(double v) {
 constexpr int LL_THREADS = APM_LL_THREADS;
 constexpr int LL_WARPS = LL_THREADS / 32;
 constexpr int LL_RPT = APM_LL_RPT;              // rows per thread per chunk
-constexpr int LL_CHUNK = LL_THREADS * LL_RPT;   // rows per TMA chunk (4096 rows = 64 KB)
+constexpr int LL_CHUNK = LL_THREADS * LL_RPT;   // two-column rows per TMA chunk (4096 rows = 64 KB)
+// rows per thread / per chunk for a model: a chunk is always LL_CHUNK * 16 bytes
+template<class M> __host__ __device__ constexpr int ll_rpt() { return LL_RPT * 2 / M::ROW_W; }
+template<class M> __host__ __device__ constexpr int ll_chunk() { return LL_THREADS * ll_rpt<M>(); }
 constexpr int LL_STAGES = APM_LL_STAGES;
 constexpr int LL_UNROLL = APM_LL_UNROLL;          // inner iterations unrolled together
 constexpr int LL_MAX_C = 8;                     // upper bound of M::LL_C (chains per work item)
 
 struct LLArgs {
-	const double * data;    // [n_rows_padded][2], padded with zeros to a multiple of LL_CHUNK
+	const double * data;    // [n_rows_padded][ROW_W], padded with zeros to a multiple of the chunk
 	long long n_rows;
 	const double * prop;    // [n_slots][n_par] parameter vectors to evaluate
 	const int * act_idx;    // optional compacted list of the slots to evaluate (NULL = all n_slots)
@@ -124,10 +151,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t * bar) {
 template<class M>
 __global__ void __launch_bounds__(LL_THREADS, 1) loglik_tiled_kernel(const LLArgs a) {
 	constexpr int C = M::LL_C, U = M::LL_U;
-	static_assert(C <= LL_MAX_C && LL_RPT % U == 0, "tile shape");
+	constexpr int RPT = ll_rpt<M>(), CHUNK = ll_chunk<M>(); // rows per thread per chunk, rows per chunk
+	static_assert(C <= LL_MAX_C && RPT % U == 0, "tile shape");
 	extern __shared__ __align__(128) unsigned char ll_smem[];
-	double2 * sdata = reinterpret_cast<double2 *>(ll_smem);                  // [STAGES][CHUNK]
-	double * sacc = reinterpret_cast<double *>(sdata + LL_STAGES * LL_CHUNK); // [MAX_C][THREADS]
+	Row<M> * sdata = reinterpret_cast<Row<M> *>(ll_smem);                  // [STAGES][CHUNK]
+	double * sacc = reinterpret_cast<double *>(sdata + LL_STAGES * CHUNK); // [MAX_C][THREADS]
 	uint64_t * full = reinterpret_cast<uint64_t *>(sacc + LL_MAX_C * LL_THREADS); // [STAGES]
 	uint64_t * empty = full + LL_STAGES;                                     // [STAGES]
 
@@ -146,7 +174,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) loglik_tiled_kernel(const LLArg
 	const int n_ctiles = (n_act + C - 1) / C;
 	const int n_items = n_ctiles * a.n_splits; // < 2^31, checked by the host
 	const double xub = *a.xabsmax;
-	constexpr uint32_t CHUNK_BYTES = LL_CHUNK * sizeof(double2);
+	constexpr uint32_t CHUNK_BYTES = CHUNK * sizeof(Row<M>);
 
 	// ---- producer (thread 0): walks this CTA's items chunk by chunk, LL_STAGES - 1 ahead
 	int p_item = blockIdx.x;
@@ -161,7 +189,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) loglik_tiled_kernel(const LLArg
 		if (p_n >= LL_STAGES) // chunk p_n - LL_STAGES must have been read by every warp
 			mbar_wait(&empty[st], ((p_n / LL_STAGES) + 1u) & 1u);
 		mbar_arrive_expect_tx(&full[st], CHUNK_BYTES);
-		tma_bulk_g2s(sdata + st * LL_CHUNK, a.data + (size_t) (k0 + p_k) * LL_CHUNK * 2, CHUNK_BYTES,
+		tma_bulk_g2s(sdata + st * CHUNK, a.data + (size_t) (k0 + p_k) * CHUNK * M::ROW_W, CHUNK_BYTES,
 				&full[st]);
 		p_n++;
 		if (++p_k == nk) {
@@ -203,14 +231,14 @@ __global__ void __launch_bounds__(LL_THREADS, 1) loglik_tiled_kernel(const LLArg
 			mbar_wait(&full[st], (it / LL_STAGES) & 1u);
 			if (tid == 0)
 				produce(); // chunk it + STAGES - 1 goes where chunk it - 1 was
-			const double2 * srow = sdata + st * LL_CHUNK + tid;
-			const long long row0 = (long long) (k0 + k) * LL_CHUNK;
-			const int n_valid = (int) min((long long) LL_CHUNK, a.n_rows - row0);
-			if (fast && n_valid == LL_CHUNK) {
+			const Row<M> * srow = sdata + st * CHUNK + tid;
+			const long long row0 = (long long) (k0 + k) * CHUNK;
+			const int n_valid = (int) min((long long) CHUNK, a.n_rows - row0);
+			if (fast && n_valid == CHUNK) {
 				// branch-free path: every row of the chunk is real and inside the fast range
 #pragma unroll LL_UNROLL
-				for (int j = 0; j < LL_RPT; j += U) {
-					double2 r[U];
+				for (int j = 0; j < RPT; j += U) {
+					Row<M> r[U];
 #pragma unroll
 					for (int u = 0; u < U; u++)
 						r[u] = srow[(j + u) * LL_THREADS];
@@ -218,28 +246,28 @@ __global__ void __launch_bounds__(LL_THREADS, 1) loglik_tiled_kernel(const LLArg
 					for (int c = 0; c < C; c++)
 #pragma unroll
 						for (int u = 0; u < U; u++)
-							acc[c][u] = M::accum_fast(acc[c][u], q[c], r[u].x, r[u].y);
+							acc[c][u] = row_accum_fast<M>(acc[c][u], q[c], r[u]);
 				}
 			} else if (fast) {
 				// ragged last chunk: padding rows masked out
 #pragma unroll 1
-				for (int j = 0; j < LL_RPT; j++) {
-					const double2 r = srow[j * LL_THREADS];
+				for (int j = 0; j < RPT; j++) {
+					const Row<M> r = srow[j * LL_THREADS];
 					if (j * LL_THREADS + tid < n_valid) {
 #pragma unroll
 						for (int c = 0; c < C; c++)
-							acc[c][0] = M::accum_fast(acc[c][0], q[c], r.x, r.y);
+							acc[c][0] = row_accum_fast<M>(acc[c][0], q[c], r);
 					}
 				}
 			} else {
 				// some chain of the tile is outside the fast sine's range: exact path
 #pragma unroll 1
-				for (int j = 0; j < LL_RPT; j++) {
-					const double2 r = srow[j * LL_THREADS];
+				for (int j = 0; j < RPT; j++) {
+					const Row<M> r = srow[j * LL_THREADS];
 					if (j * LL_THREADS + tid < n_valid) {
 #pragma unroll
 						for (int c = 0; c < C; c++)
-							acc[c][0] = M::accum(acc[c][0], q[c], r.x, r.y);
+							acc[c][0] = row_accum<M>(acc[c][0], q[c], r);
 					}
 				}
 			}
@@ -283,11 +311,11 @@ constexpr int LL_PARTS = 1;
 // max |x| over the table (first column): bound for the per-item fast-sine range check.
 // |double| ordering == unsigned ordering of the bit pattern; NaN compares above everything,
 // which switches the fast path off.
-__global__ void absmax_col0_kernel(const double * data, long long n_rows, unsigned long long * out) {
+__global__ void absmax_col0_kernel(const double * data, long long n_rows, int row_w, unsigned long long * out) {
 	unsigned long long m = 0;
 	for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < n_rows;
 			i += (long long) gridDim.x * blockDim.x) {
-		unsigned long long b = (unsigned long long) __double_as_longlong(data[2 * i]) & 0x7fffffffffffffffull;
+		unsigned long long b = (unsigned long long) __double_as_longlong(data[(size_t) row_w * i]) & 0x7fffffffffffffffull;
 		m = b > m ? b : m;
 	}
 #pragma unroll
@@ -442,8 +470,9 @@ __host__ __device__ inline size_t fused_state_bytes(int n_beta, int n_par) {
 	const size_t per_chain = 8 * (size_t) (8 * n_par + 11) + sizeof(CalState) + sizeof(int);
 	return (per_chain * n_beta + 8 /* swap_round */ + 15) & ~(size_t) 15;
 }
-__host__ __device__ inline size_t fused_table_bytes(long long n_rows) {
-	return (((size_t) n_rows * 16 + 127) & ~(size_t) 127) + 16 /* mbarrier */;
+// (n_slots = table rows x ROW_W / 2: 16-byte units)
+__host__ __device__ inline size_t fused_table_bytes(long long n_slots) {
+	return (((size_t) n_slots * 16 + 127) & ~(size_t) 127) + 16 /* mbarrier */;
 }
 
 struct FusedArgs {
@@ -456,15 +485,16 @@ struct FusedArgs {
 	const unsigned char * select;
 };
 
-__device__ __forceinline__ const double2 * fused_stage_table(const FusedArgs & a, unsigned char * smem) {
-	double2 * sdata = reinterpret_cast<double2 *>(smem);
-	uint64_t * bar = reinterpret_cast<uint64_t *>(smem + fused_table_bytes(a.n_rows) - 16);
+template<class M>
+__device__ __forceinline__ const Row<M> * fused_stage_table(const FusedArgs & a, unsigned char * smem) {
+	Row<M> * sdata = reinterpret_cast<Row<M> *>(smem);
+	uint64_t * bar = reinterpret_cast<uint64_t *>(smem + fused_table_bytes((long long) a.n_rows * (M::ROW_W / 2)) - 16);
 	if (a.n_rows > 0) {
 		if (threadIdx.x == 0) {
 			mbar_init(bar, 1);
 			mbar_fence_init();
 			// bulk copies of at most 32 KB each, all completing on the one barrier
-			const uint32_t total = (uint32_t) a.n_rows * sizeof(double2);
+			const uint32_t total = (uint32_t) a.n_rows * sizeof(Row<M>);
 			mbar_arrive_expect_tx(bar, total);
 			for (uint32_t off = 0; off < total; off += 32768u) {
 				const uint32_t n = min(32768u, total - off);
@@ -570,7 +600,7 @@ __device__ inline void fused_writeback(const DevState & S, const DevState & L, i
 // sum over the table of the model's row terms for chain g's pending proposal; every lane
 // returns the same bits (butterfly of commutative adds)
 template<class M>
-__device__ __forceinline__ double fused_loglik(const DevState & S, int g, const double2 * sdata, int n_rows,
+__device__ __forceinline__ double fused_loglik(const DevState & S, int g, const Row<M> * sdata, int n_rows,
 		double xub, int lane) {
 	if (!M::HAS_DATA)
 		return 0.0;
@@ -580,20 +610,20 @@ __device__ __forceinline__ double fused_loglik(const DevState & S, int g, const 
 	int i = lane;
 	if (M::fast_ok(q, xub)) {
 		for (; i + 96 < n_rows; i += 128) {
-			const double2 r0 = sdata[i], r1 = sdata[i + 32], r2 = sdata[i + 64], r3 = sdata[i + 96];
-			a0 = M::accum_fast(a0, q, r0.x, r0.y);
-			a1 = M::accum_fast(a1, q, r1.x, r1.y);
-			a2 = M::accum_fast(a2, q, r2.x, r2.y);
-			a3 = M::accum_fast(a3, q, r3.x, r3.y);
+			const Row<M> r0 = sdata[i], r1 = sdata[i + 32], r2 = sdata[i + 64], r3 = sdata[i + 96];
+			a0 = row_accum_fast<M>(a0, q, r0);
+			a1 = row_accum_fast<M>(a1, q, r1);
+			a2 = row_accum_fast<M>(a2, q, r2);
+			a3 = row_accum_fast<M>(a3, q, r3);
 		}
 		for (; i < n_rows; i += 32) {
-			const double2 r = sdata[i];
-			a0 = M::accum_fast(a0, q, r.x, r.y);
+			const Row<M> r = sdata[i];
+			a0 = row_accum_fast<M>(a0, q, r);
 		}
 	} else {
 		for (; i < n_rows; i += 32) {
-			const double2 r = sdata[i];
-			a0 = M::accum(a0, q, r.x, r.y);
+			const Row<M> r = sdata[i];
+			a0 = row_accum<M>(a0, q, r);
 		}
 	}
 	return warp_sum((a0 + a1) + (a2 + a3));
@@ -616,9 +646,9 @@ __device__ __forceinline__ void chain_propose_warp(const DevState & S, int g, in
 template<class M>
 __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_run_kernel(const DevState S, const FusedArgs a) {
 	extern __shared__ __align__(128) unsigned char fused_smem[];
-	const double2 * sdata = fused_stage_table(a, fused_smem);
+	const Row<M> * sdata = fused_stage_table<M>(a, fused_smem);
 	const int ens = blockIdx.x;
-	const DevState L = fused_localize(S, ens, fused_smem + fused_table_bytes(a.n_rows));
+	const DevState L = fused_localize(S, ens, fused_smem + fused_table_bytes((long long) a.n_rows * (M::ROW_W / 2)));
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
 	const int nb = L.n_beta, n = L.n_par;
 	const double xub = M::HAS_DATA ? *a.xabsmax : 0.0;
@@ -715,9 +745,9 @@ struct ClusterArgs {
 };
 
 constexpr int CLUSTER_DRAW_RING = 4; // batches of draws in flight per chain
-__host__ __device__ inline size_t cluster_smem_bytes(long long n_rows, int gmax, int wc, int n_par) {
+__host__ __device__ inline size_t cluster_smem_bytes(long long n_slots, int gmax, int wc, int n_par) {
 	// packs (2) + per chain: warp sums [2][wc], draws [RING][32], per-warp proposal copies [wc][n_par]
-	return fused_table_bytes(n_rows) + fused_state_bytes(gmax, n_par)
+	return fused_table_bytes(n_slots) + fused_state_bytes(gmax, n_par)
 			+ sizeof(double) * (2 * LADDER_PACK(n_par)
 					+ (size_t) gmax * (2 * wc + CLUSTER_DRAW_RING * 32 + (size_t) wc * n_par));
 }
@@ -750,7 +780,7 @@ __device__ __forceinline__ const double * cluster_map(double * p, uint32_t rank)
 // the group's share of chain g's sum: lanes gl, gl + GL, ... of the table; every lane of a warp
 // returns the warp's total
 template<class M>
-__device__ __forceinline__ double group_loglik(const DevState & S, const double * prop, const double2 * sdata,
+__device__ __forceinline__ double group_loglik(const DevState & S, const double * prop, const Row<M> * sdata,
 		int n_rows, double xub, int gl, int GL) {
 	typename M::Prep q;
 	M::prep(q, prop, S.n_par, S.model_const);
@@ -758,28 +788,28 @@ __device__ __forceinline__ double group_loglik(const DevState & S, const double 
 	int i = gl;
 	if (M::fast_ok(q, xub)) {
 		for (; i + 3 * GL < n_rows; i += 4 * GL) {
-			const double2 r0 = sdata[i], r1 = sdata[i + GL], r2 = sdata[i + 2 * GL], r3 = sdata[i + 3 * GL];
-			a0 = M::accum_fast(a0, q, r0.x, r0.y);
-			a1 = M::accum_fast(a1, q, r1.x, r1.y);
-			a2 = M::accum_fast(a2, q, r2.x, r2.y);
-			a3 = M::accum_fast(a3, q, r3.x, r3.y);
+			const Row<M> r0 = sdata[i], r1 = sdata[i + GL], r2 = sdata[i + 2 * GL], r3 = sdata[i + 3 * GL];
+			a0 = row_accum_fast<M>(a0, q, r0);
+			a1 = row_accum_fast<M>(a1, q, r1);
+			a2 = row_accum_fast<M>(a2, q, r2);
+			a3 = row_accum_fast<M>(a3, q, r3);
 		}
 		// up to three rows left for this lane: evaluated side by side (a row's evaluation is one
 		// long dependency chain), each into the accumulator it would have gone to above
 		if (i < n_rows) {
 			const bool v1 = i + GL < n_rows, v2 = i + 2 * GL < n_rows;
-			const double2 r0 = sdata[i], r1 = sdata[v1 ? i + GL : i], r2 = sdata[v2 ? i + 2 * GL : i];
-			const double b0 = M::accum_fast(a0, q, r0.x, r0.y);
-			const double b1 = M::accum_fast(a1, q, r1.x, r1.y);
-			const double b2 = M::accum_fast(a2, q, r2.x, r2.y);
+			const Row<M> r0 = sdata[i], r1 = sdata[v1 ? i + GL : i], r2 = sdata[v2 ? i + 2 * GL : i];
+			const double b0 = row_accum_fast<M>(a0, q, r0);
+			const double b1 = row_accum_fast<M>(a1, q, r1);
+			const double b2 = row_accum_fast<M>(a2, q, r2);
 			a0 = b0;
 			a1 = v1 ? b1 : a1;
 			a2 = v2 ? b2 : a2;
 		}
 	} else {
 		for (; i < n_rows; i += GL) {
-			const double2 r = sdata[i];
-			a0 = M::accum(a0, q, r.x, r.y);
+			const Row<M> r = sdata[i];
+			a0 = row_accum<M>(a0, q, r);
 		}
 	}
 	return warp_sum((a0 + a1) + (a2 + a3));
@@ -810,9 +840,10 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) cluster_run_kernel(co
 	const int k0 = cluster_block_lo(nb_all, CL, rank), nloc = cluster_block_lo(nb_all, CL, rank + 1) - k0;
 
 	// ---- the table: one multicast fetch per cluster
-	double2 * sdata = reinterpret_cast<double2 *>(fused_smem);
-	uint64_t * bar = reinterpret_cast<uint64_t *>(fused_smem + fused_table_bytes(a.n_rows) - 16);
-	const uint32_t total = (uint32_t) a.n_rows * sizeof(double2);
+	const long long n_slots = (long long) a.n_rows * (M::ROW_W / 2);
+	Row<M> * sdata = reinterpret_cast<Row<M> *>(fused_smem);
+	uint64_t * bar = reinterpret_cast<uint64_t *>(fused_smem + fused_table_bytes(n_slots) - 16);
+	const uint32_t total = (uint32_t) a.n_rows * sizeof(Row<M>);
 	if (tid == 0) {
 		mbar_init(bar, 1);
 		mbar_fence_init();
@@ -830,7 +861,7 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) cluster_run_kernel(co
 	// ---- this CTA's block of the ensemble, resident in shared memory
 	// (the localized DevState -- some forty pointers -- lives in shared memory, not in every thread's
 	// registers: the row loop needs the registers for independent row evaluations in flight)
-	unsigned char * mem = fused_smem + fused_table_bytes(a.n_rows);
+	unsigned char * mem = fused_smem + fused_table_bytes(n_slots);
 	__shared__ DevState L_shared;
 	{
 		const DevState L_tmp = fused_localize_block(S, ens, k0, nloc, mem);
@@ -1023,9 +1054,9 @@ template<class M>
 __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_calibrate_kernel(const DevState S,
 		const FusedArgs a) {
 	extern __shared__ __align__(128) unsigned char fused_smem[];
-	const double2 * sdata = fused_stage_table(a, fused_smem);
+	const Row<M> * sdata = fused_stage_table<M>(a, fused_smem);
 	const int ens = blockIdx.x;
-	const DevState L = fused_localize(S, ens, fused_smem + fused_table_bytes(a.n_rows));
+	const DevState L = fused_localize(S, ens, fused_smem + fused_table_bytes((long long) a.n_rows * (M::ROW_W / 2)));
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
 	const int nb = L.n_beta, n = L.n_par;
 	const size_t base = (size_t) ens * nb;

@@ -6,7 +6,10 @@
 // templates over it, so a model costs nothing at run time:
 //
 //   NPAR        number of parameters (0 = decided at run time, n_par is passed in)
-//   NCOLS       data columns the model reads (the row-major table may not be narrower)
+//   NCOLS       data columns the model reads (the row-major table may not be narrower);
+//               -1 = one column per parameter (apps/bernoulli_example.c)
+//   ROW_W       doubles per table row on the device: 2 (accum gets the row as x, y) or 4 (models
+//               reading 3 or 4 columns; accum gets a double4, unused columns are zero)
 //   HAS_DATA    false for models that never touch m->data (apps/normal.c)
 //   HAS_PRIOR   whether calc_model calls set_prior()
 //   LL_C, LL_U  register tile of the likelihood kernel: chains per work item x rows per
@@ -51,6 +54,7 @@ struct ModelSimplesin {
 	static constexpr int LL_C = APM_LL_C, LL_U = APM_LL_U;
 	static constexpr int NPAR = 4, NCOLS = 2;
 	static constexpr bool HAS_DATA = true, HAS_PRIOR = false;
+	static constexpr int ROW_W = 2;
 	struct Prep {
 		double amplitude, frequency, phase, offset;
 	};
@@ -87,6 +91,7 @@ struct ModelSimplesin5 {
 	static constexpr int LL_C = APM_LL_C, LL_U = APM_LL_U;
 	static constexpr int NPAR = 4, NCOLS = 2;
 	static constexpr bool HAS_DATA = true, HAS_PRIOR = false;
+	static constexpr int ROW_W = 2;
 	struct Prep {
 		double a, w, ph, off;
 	};
@@ -122,6 +127,7 @@ struct ModelSimplesin2 {
 	static constexpr int LL_C = APM_LL_C, LL_U = APM_LL_U;
 	static constexpr int NPAR = 2, NCOLS = 2;
 	static constexpr bool HAS_DATA = true, HAS_PRIOR = false;
+	static constexpr int ROW_W = 2;
 	struct Prep {
 		double a, f;
 	};
@@ -155,6 +161,7 @@ struct ModelNormal {
 	static constexpr int LL_C = 1, LL_U = 1;
 	static constexpr int NPAR = 1, NCOLS = 0;
 	static constexpr bool HAS_DATA = false, HAS_PRIOR = false;
+	static constexpr int ROW_W = 2;
 	struct Prep {
 		double x;
 	};
@@ -191,6 +198,7 @@ struct ModelPulseVrot {
 	static constexpr int LL_C = 4, LL_U = 1;
 	static constexpr int NPAR = 7, NCOLS = 2;
 	static constexpr bool HAS_DATA = true, HAS_PRIOR = true;
+	static constexpr int ROW_W = 2;
 	struct Prep {
 		double lifetime, vrot, f1, h1, f2, h2;
 	};
@@ -237,6 +245,7 @@ struct ModelPulse {
 	static constexpr int LL_C = 2, LL_U = 1;
 	static constexpr int NPAR = 0, NCOLS = 2;
 	static constexpr bool HAS_DATA = true, HAS_PRIOR = true;
+	static constexpr int ROW_W = 2;
 	struct Prep {
 		double lifetime;
 		int n_modes;
@@ -276,6 +285,58 @@ struct ModelPulse {
 	}
 	APM_D static double finish(double beta, double sum, double prior, const double *, const double *) {
 		return prior + -beta * sum;
+	}
+};
+
+// ---- apps/bernoulli_example.c:9-51: logistic regression, column 0 = outcome (0 / 1), columns
+// 1 .. n_par - 1 = regressors, parameter 0 = intercept.  On the device: up to 4 columns.
+struct ModelBernoulli {
+	static constexpr int LL_C = 4, LL_U = 2;
+	static constexpr int NPAR = 0, NCOLS = -1;
+	static constexpr bool HAS_DATA = true, HAS_PRIOR = true;
+	static constexpr int ROW_W = 4;
+	struct Prep {
+		double p0, p1, p2, p3;
+		int n;
+	};
+	APM_D static void prep(Prep & q, const double * p, int n_par, const double *) {
+		q.n = n_par;
+		q.p0 = p[0];
+		q.p1 = n_par > 1 ? p[1] : 0.0;
+		q.p2 = n_par > 2 ? p[2] : 0.0;
+		q.p3 = n_par > 3 ? p[3] : 0.0;
+	}
+	APM_D static double accum(double acc, const Prep & q, const double4 & r) {
+		// eta = [1, x] . params, accumulated term by term (:29-33)
+		double eta = q.p0;
+		if (q.n > 1)
+			eta = add_rn(eta, mul_rn(r.y, q.p1));
+		if (q.n > 2)
+			eta = add_rn(eta, mul_rn(r.z, q.p2));
+		if (q.n > 3)
+			eta = add_rn(eta, mul_rn(r.w, q.p3));
+		double p_i;
+		if (eta > 0)
+			p_i = 1 / (1 + exp(-eta));               // (:35-36)
+		else
+			p_i = exp(eta) / (1 + exp(eta));         // (:37-38)
+		const double l_i = r.x == 0 ? log(1 - p_i) : log(p_i); // (:40-43)
+		return acc + l_i;
+	}
+	APM_D static double accum_fast(double acc, const Prep & q, const double4 & r) { return accum(acc, q, r); }
+	APM_D static bool fast_ok(const Prep &, double) { return true; }
+	APM_D static double sum0(const double *) { return 0.0; }
+	APM_D static double prior(const double * p, int n_par, const double * mc) {
+		const double sigma = mc[0] != 0 ? mc[0] : 2.0; // SIGMA (:7)
+		double prior = 0;
+		for (int j = 1; j < n_par; j++) { // j < m->data->size2 = n_par (:20-22, assert :25)
+			const double t = p[j] / sigma;
+			prior += -(t * t) / 2;
+		}
+		return prior;
+	}
+	APM_D static double finish(double beta, double sum, double prior, const double *, const double *) {
+		return prior + beta * sum; // (:46)
 	}
 };
 

@@ -8,6 +8,7 @@ struct UserModel {
 	static constexpr int LL_C = 2, LL_U = 2; // register tile: 2 chains x 2 rows in flight
 	static constexpr int NPAR = 0, NCOLS = 2; // 3K + 1 parameters, K decided by the params file
 	static constexpr bool HAS_DATA = true, HAS_PRIOR = false;
+	static constexpr int ROW_W = 2;             // table rows of 2 doubles: accum gets (x, y)
 	struct Prep {
 		int n_sines;
 		double a[MAX_SINES], f[MAX_SINES], ph[MAX_SINES], offset;

@@ -52,7 +52,8 @@ extern "C" {
 #define APM_MODEL_PULSE_VROT   3  /* reference apps/pulse_vrot.c:12-65 */
 #define APM_MODEL_SIMPLESIN2   4  /* reference apps/simplesin2.c */
 #define APM_MODEL_PULSE        5  /* reference apps/pulse.c */
-#define APM_MODEL_BERNOULLI    6  /* reference apps/bernoulli_example.c */
+#define APM_MODEL_BERNOULLI    6  /* reference apps/bernoulli_example.c:9-51 (n_par = data columns, 2..4) */
+#define APM_MODEL_BERNOULLI_EXAMPLE APM_MODEL_BERNOULLI
 #define APM_MODEL_USER         100 /* apps/<model>.cuh compiled in with -DAPM_USER_MODEL_HEADER */
 
 /* ---- proposal distribution: reference src/mcmc_gettersetter.c:290-306 ---- */
@@ -161,11 +162,12 @@ int apm_gpu_destroy(apm_gpu * handle);
 const char * apm_gpu_last_error(const apm_gpu * handle); /* handle may be NULL: last create error */
 int apm_gpu_abi_version(void);
 int apm_gpu_model_n_par(int model_id);   /* 0 = any */
-int apm_gpu_model_n_cols(int model_id);  /* 0 = data-free */
+int apm_gpu_model_n_cols(int model_id);  /* 0 = data-free, -1 = one column per parameter */
 
 /* ---- inputs -------------------------------------------------------------
  * set_data replaces mcmc_load_data + mcmc_reuse_data (src/mcmc_parser.c:97-146):
- * one table per device, shared read-only by every chain.  row_offset/n_rows_total
+ * one table per device, shared read-only by every chain.  The device keeps the columns the
+ * model reads (at most 4; two-column models: rows of 2 doubles = the gsl_matrix layout).  row_offset/n_rows_total
  * describe a contiguous shard of a larger table (data-sharded mode). */
 int apm_gpu_set_data(apm_gpu * h, const double * rowmajor, long long n_rows,
 		int n_cols);

@@ -100,7 +100,7 @@ def test_phases_on_gpu_equal_oracle_flow(name, tmp_path):
 def test_eval_exe_matches_reference_fixture(tmp_path):
     """eval_<model>.exe (reference apps/eval_main.c) answered by the GPU: 1e-12 against what the
     unmodified reference printed for the same parameter vectors"""
-    for model in ("simplesin", "pulse_vrot"):
+    for model in ("simplesin", "pulse_vrot", "bernoulli_example"):
         fx = json.load(open(os.path.join(GOLDEN, f"eval_{model}.json")))
         exe = make(f"eval_{model}.exe", "-DN_BETA=1", str(tmp_path / "bin"))
         wd = str(tmp_path / model)

@@ -55,13 +55,14 @@ def test_manual_known_answer(capi):
     assert prior[0] == 0.0
 
 
-@pytest.mark.parametrize("model", ["simplesin", "simplesin5", "simplesin2", "normal", "pulse_vrot", "pulse"])
+@pytest.mark.parametrize("model", ["simplesin", "simplesin5", "simplesin2", "normal", "pulse_vrot", "pulse",
+                                   "bernoulli_example"])
 def test_calc_model_matches_reference_fixture(capi, model):
     fx = load("eval_" + model)
     n_par = len(fx["rows"])
     data = np.array(fx["data"], dtype=float).reshape(-1, fx["n_cols"])
     params = np.array(fx["params"], dtype=float).reshape(-1, n_par)
-    e = capi.Engine(model, 1, 1, n_par=n_par)
+    e = capi.Engine(model.replace("_example", ""), 1, 1, n_par=n_par)
     e.set_data(data)
     prob, prior = e.eval(params)
     np.testing.assert_allclose(prob, np.array(fx["prob"], dtype=float), rtol=RTOL_LOGLIK)
@@ -191,6 +192,47 @@ def test_run_trajectory_equals_oracle(capi, name, kw, quirks, path):
     for k in ("sum_dl", "sum_params", "sum_params_sq"):
         np.testing.assert_allclose(ac_g[k], ac_c[k], rtol=RTOL_TRAJ)
     assert st_g["swapcount"].sum() > 0, "the test must exercise accepted swaps"
+
+
+def _logistic_table(n_rows, n_cols, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(n_rows, n_cols - 1))
+    w = np.array([0.5, -0.3, 0.8])[:n_cols - 1]
+    y = (rng.uniform(size=n_rows) < 1 / (1 + np.exp(-(0.1 + X @ w)))).astype(float)
+    return np.column_stack([y, X])
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("n_cols,n_rows", [(3, 700), (2, 333), (4, 5000)])
+def test_bernoulli_rows_of_four_doubles(capi, path, n_cols, n_rows):
+    """apps/bernoulli_example.c: a model reading 2..4 data columns (n_par = columns), i.e. table
+    rows of 4 doubles on the device; calc_model to 1e-12 and whole runs against the oracle on
+    every kernel path (5000 rows x 32 B does not fit the fused paths' shared memory twice over,
+    so that case is tiled only)"""
+    if n_rows * 32 > 150_000 and path != 1:
+        pytest.skip("table too large for the shared-memory paths")
+    data = _logistic_table(n_rows, n_cols, 7 * n_cols)
+    n_ens, n_beta, n_par = 2, 6, n_cols
+    n = n_ens * n_beta
+    rng = np.random.default_rng(n_cols)
+    lo, hi = np.full(n_par, -5.0), np.full(n_par, 5.0)
+    params = rng.normal(0, 0.3, (n, n_par))
+    beta = np.tile(np.linspace(1.0, 0.5, n_beta), n_ens)
+    steps = np.full((n, n_par), 0.15) * beta[:, None] ** -0.5
+    res = []
+    for eng in _pair(capi, "bernoulli", n_ens, n_beta, n_par=n_par, seed=53, path=path):
+        eng.set_data(data)
+        eng.set_bounds(lo, hi)
+        prob, prior = eng.eval(params, beta)
+        eng.set_chains(0, n, beta=beta, params=params, steps=steps, params_best=params, prob=prob, prior=prior)
+        eng.run(5, 20, prob_every=1, params_chains=1)
+        res.append((prob, prior, eng.read_trace(), eng.get_chains()))
+    (p_g, pr_g, tr_g, st_g), (p_c, pr_c, tr_c, st_c) = res
+    np.testing.assert_allclose(p_g, p_c, rtol=RTOL_LOGLIK)
+    np.testing.assert_allclose(pr_g, pr_c, rtol=RTOL_LOGLIK, atol=1e-300)
+    _compare_state(st_g, st_c)
+    np.testing.assert_allclose(tr_g["prob"], tr_c["prob"], rtol=RTOL_TRAJ)
+    assert st_g["swapcount"].sum() > 0 and 0.05 < st_g["accept"].sum() / (n * 100) < 0.95
 
 
 @pytest.mark.parametrize("path", PATHS)
@@ -440,17 +482,20 @@ def test_steps_accept_log_equals_oracle(capi, path):
 
 
 # ---------------------------------------------------------------- statistical parity with the reference
-def test_evidence_and_posterior_match_reference_statistics(capi):
+@pytest.mark.parametrize("name", ["c1_phases", "c4_phases"])
+def test_evidence_and_posterior_match_reference_statistics(capi, name):
     """Second half of 'correctness' (north_star): with different RNG streams the engine's
     posterior moments and thermodynamic-integration evidence must agree with the reference's.
     Protocol: same params file, same calibration_results (the reference's own, from
-    tests/golden/c1_phases.json), 24 independent engine ensembles x 3000 iterations vs the
-    reference's run recorded in the fixture and the oracle (pinned byte-for-byte to the reference)
-    over 24 seeds; tolerance 5 standard errors of the seed-to-seed scatter."""
-    fx = load("c1_phases")
+    the fixture), 24 independent engine ensembles x the fixture's iterations vs the reference's
+    run recorded in the fixture and the oracle (pinned byte-for-byte to the reference) over 24
+    seeds; tolerance 5 standard errors of the seed-to-seed scatter.  c1 = simplesin on the
+    reference's light curve; c4 = pulse_vrot, a model with a prior (the swap and revert quirks act)."""
+    fx = load(name)
     rows = [tuple(r) for r in fx["rows"]]
-    n_par, n_beta, n_ens, iters = 4, 4, 24, 3000
-    data = np.loadtxt(os.path.join(GOLDEN, fx["data_file"]))
+    n_par, n_beta, n_ens, iters = len(rows), fx["config"]["N_BETA"], 24, fx["config"]["MAX_ITERATIONS"]
+    data = (np.loadtxt(os.path.join(GOLDEN, fx["data_file"])) if fx["data_file"]
+            else np.array(fx["data"], dtype=float).reshape(-1, 2))
     cal = np.array(fx["phases"]["calibrate_rest"].split(), dtype=float).reshape(n_beta, 1 + 2 * n_par)
     n_swap = 2000 // n_beta
 
@@ -460,15 +505,15 @@ def test_evidence_and_posterior_match_reference_statistics(capi):
         pt_flow.apply_calibration(eng, 0, np.tile(cal[:, 0], n_ens), np.tile(cal[:, 1:1 + n_par], (n_ens, 1)),
                                   np.tile(cal[:, 1 + n_par:], (n_ens, 1)))
         eng.reset_stats()
-        eng.run(iters // n_swap, n_swap)
+        eng.run(-(-iters // n_swap), n_swap)
         s = eng.get_stats()
         mean_dl = (s["sum_dl"] / s["n"]).reshape(n_ens, n_beta)
         lnz = np.array([pt_flow.evidence(cal[:, 0], m) for m in mean_dl])
         mean_p = (s["sum_params"] / s["n"][:, None]).reshape(n_ens, n_beta, n_par)[:, 0, :]
         return lnz, mean_p
 
-    lnz_g, mp_g = run(capi.Engine("simplesin", n_ens, n_beta, seed=101))
-    lnz_c, mp_c = run(Oracle("simplesin", n_ens, n_beta, seed=202, rng=RNG_PHILOX))
+    lnz_g, mp_g = run(capi.Engine(fx["model"], n_ens, n_beta, n_par=n_par, seed=101))
+    lnz_c, mp_c = run(Oracle(fx["model"], n_ens, n_beta, n_par=n_par, seed=202, rng=RNG_PHILOX))
     se = np.sqrt(lnz_g.var(ddof=1) / n_ens + lnz_c.var(ddof=1) / n_ens)
     assert abs(lnz_g.mean() - lnz_c.mean()) < 5 * se, (lnz_g.mean(), lnz_c.mean(), se)
     # the reference's own single run (GSL MT19937 stream) must be a typical member
