@@ -30,7 +30,7 @@ MODELS = {
 PROPOSAL_GAUSSIAN, PROPOSAL_LOGISTIC, PROPOSAL_UNIFORM = 0, 1, 2
 QUIRK_STALE_PROB_ON_SWAP, QUIRK_STALE_PRIOR_ON_REJECT = 1, 2
 QUIRKS_REFERENCE = 3
-PATH_AUTO, PATH_TILED, PATH_FUSED, PATH_CLUSTER = 0, 1, 2, 3
+PATH_AUTO, PATH_TILED, PATH_FUSED, PATH_CLUSTER, PATH_GRID = 0, 1, 2, 3, 4
 E_CALIB = -6
 
 _u64 = C.c_ulonglong

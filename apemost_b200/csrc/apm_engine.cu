@@ -75,6 +75,8 @@ struct apm_gpu {
 	bool have_data = false, have_bounds = false;
 	// row-split plan for n_chains slots
 	int plan_splits = 0, plan_cps = 0;
+	double * d_grid_partials = nullptr, *d_grid_draws = nullptr; // grid path workspaces
+	size_t grid_partials_cap = 0, grid_draws_cap = 0;
 	size_t partial_cap = 0;
 	unsigned long long * d_xabsmax = nullptr; // bits of max |x| over the table
 	// trace (device)
@@ -184,6 +186,7 @@ static int configure_kernels(apm_gpu * h) {
 	CU(cudaFuncSetAttribute(fused_run_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
 	CU(cudaFuncSetAttribute(fused_calibrate_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
 	CU(cudaFuncSetAttribute(cluster_run_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
+	CU(cudaFuncSetAttribute(grid_run_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
 	return APM_OK;
 }
 
@@ -298,7 +301,7 @@ extern "C" int apm_gpu_destroy(apm_gpu * h) {
 			S.accept, S.reject, S.pacc, S.prej, S.n_iter, S.swapcount, S.rng_ctr, S.swap_round, S.pmin,
 			S.pmax, S.pend, S.partial, S.stat_n, S.stat_sum_dl, S.stat_sum_p, S.stat_sum_p2, S.cal,
 			S.progress, S.progress_n, S.n_active, S.act_idx, S.act_n, h->d_select, h->d_shard_sum,
-			h->d_pack_first, h->d_pack_last, h->d_pack_prev, h->d_pack_next,
+			h->d_pack_first, h->d_pack_last, h->d_pack_prev, h->d_pack_next, h->d_grid_partials, h->d_grid_draws,
 			h->d_xabsmax, h->d_data, h->d_tr_prob, h->d_tr_dl, h->d_tr_params };
 	for (void * p : ptrs)
 		if (p)
@@ -721,6 +724,21 @@ static int cluster_size_for(const apm_gpu * h, bool has_data) {
 	return 0;
 }
 
+// grid path: rows per CTA (0 = the path does not apply).  Worth it where a step of the tiled path is
+// dominated by launch gaps and fixed latencies (~28 us): up to ~3e7 row evaluations per step.
+static int grid_slice_rows(const apm_gpu * h, bool has_data) {
+	if (!has_data || h->comm || h->n_chains > GRID_MAX_CHAINS || h->n_rows < 1)
+		return 0;
+	if (getenv("APM_NO_GRID"))
+		return 0;
+	const int row_w = model_row_w(const_cast<apm_gpu *>(h), h->cfg.model_id);
+	const long long slice = (h->n_rows + h->sm_count - 1) / h->sm_count + 1;
+	const size_t need = (((size_t) slice * row_w * 8 + 127) & ~(size_t) 127) + 64 + grid_state_bytes(h->n_chains, h->cfg.n_par);
+	if (need > FUSED_SMEM_LIMIT)
+		return 0;
+	return (int) slice;
+}
+
 static int choose_path(apm_gpu * h, int * path, bool for_run = false) {
 	const int has_data = model_has_data(h);
 	if (has_data < 0)
@@ -730,10 +748,19 @@ static int choose_path(apm_gpu * h, int * path, bool for_run = false) {
 	const bool fits = need <= FUSED_SMEM_LIMIT && (!has_data || h->n_rows < (1ll << 24));
 	const bool rows_ok = !has_data || h->n_rows < (1ll << 24);
 	const int cl = for_run && rows_ok ? cluster_size_for(h, has_data != 0) : 0;
+	const int gslice = for_run ? grid_slice_rows(h, has_data != 0) : 0;
 	int want = h->cfg.path;
 	if (want == APM_PATH_CLUSTER && !for_run)
 		want = fits ? APM_PATH_FUSED : APM_PATH_TILED; // calibration: chains do not interact, no cluster needed
-	if (want == APM_PATH_CLUSTER) {
+	if (want == APM_PATH_GRID && !for_run)
+		want = APM_PATH_TILED;
+	if (want == APM_PATH_GRID) {
+		if (gslice == 0)
+			return fail(h, APM_EINVAL, "the grid path needs a data model, at most %d chains, a slice of the table "
+					"(rows / %d SMs) plus the chains' state in shared memory and no multi-GPU sharding",
+					GRID_MAX_CHAINS, h->sm_count);
+		*path = APM_PATH_GRID;
+	} else if (want == APM_PATH_CLUSTER) {
 		if (cl == 0)
 			return fail(h, APM_EINVAL, "the cluster path needs a data model, 2 <= cluster size <= n_beta, "
 					"n_ensembles x cluster size <= %d SMs, the table in shared memory and no multi-GPU sharding",
@@ -750,7 +777,11 @@ static int choose_path(apm_gpu * h, int * path, bool for_run = false) {
 	} else if (want == APM_PATH_TILED) {
 		*path = APM_PATH_TILED;
 	} else {
-		*path = cl > 0 ? APM_PATH_CLUSTER : ((fits && !h->comm) ? APM_PATH_FUSED : APM_PATH_TILED);
+		// tiled steps cost ~28 us of launch gaps and fixed latencies; the grid path pays one grid
+		// barrier instead, until the row evaluations themselves take several times that
+		const bool grid_pays = gslice > 0 && (double) h->n_rows * h->n_chains <= 6e7;
+		*path = cl > 0 ? APM_PATH_CLUSTER
+				: ((fits && !h->comm) ? APM_PATH_FUSED : (grid_pays ? APM_PATH_GRID : APM_PATH_TILED));
 	}
 	return APM_OK;
 }
@@ -866,6 +897,51 @@ static int run_cluster_t(apm_gpu * h, long long n_rounds, int n_swap) {
 	return APM_OK;
 }
 
+template<class M>
+static int run_grid_t(apm_gpu * h, long long n_rounds, int n_swap) {
+	if (!M::HAS_DATA)
+		return fail(h, APM_EINVAL, "the grid path is for models with data");
+	const int slice = grid_slice_rows(h, true);
+	if (slice == 0)
+		return fail(h, APM_ESTATE, "no grid geometry");
+	const int G = h->sm_count;
+	CU(ensure_cap(&h->d_grid_partials, &h->grid_partials_cap, (size_t) 2 * h->n_chains * G));
+	CU(ensure_cap(&h->d_grid_draws, &h->grid_draws_cap, (size_t) CLUSTER_DRAW_RING * h->n_chains * 32));
+	GridArgs ga;
+	ga.data = h->d_data;
+	ga.n_rows = h->n_rows;
+	ga.xabsmax = reinterpret_cast<const double *>(h->d_xabsmax);
+	ga.n_rounds = n_rounds;
+	ga.n_swap = n_swap;
+	ga.partials = h->d_grid_partials;
+	ga.draws = h->d_grid_draws;
+	ga.max_slice_rows = slice;
+	const size_t smem = (((size_t) slice * sizeof(Row<M>) + 127) & ~(size_t) 127) + 64
+			+ grid_state_bytes(h->n_chains, h->cfg.n_par);
+	int per_sm = 0;
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_run_kernel<M>, GRID_THREADS, smem));
+	if (per_sm < 1)
+		return fail(h, APM_ECUDA, "the grid kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+	DevState S = h->S;
+	void * args[] = { (void *) &S, (void *) &ga };
+	h->ev_used = 0;
+	cudaEvent_t t0 = next_event(h), t1 = next_event(h);
+	CU(cudaEventRecord(t0, h->stream));
+	CU(cudaLaunchCooperativeKernel((const void *) grid_run_kernel<M>, dim3((unsigned) G), dim3(GRID_THREADS), args,
+			smem, h->stream));
+	h->launches++;
+	CU(cudaEventRecord(t1, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	CU(cudaGetLastError());
+	float tot = 0;
+	cudaEventElapsedTime(&tot, t0, t1);
+	h->last_total_ms = tot;
+	h->last_ll_ms = 0;
+	h->last_ll_launches = 0;
+	h->last_path = APM_PATH_GRID;
+	return APM_OK;
+}
+
 // ------------------------------------------------------------------ run (tiled path)
 static int setup_trace(apm_gpu * h, long long n_steps, const apm_gpu_trace_cfg * tr) {
 	h->tr_prob_rows = h->tr_param_rows = 0;
@@ -971,6 +1047,9 @@ extern "C" int apm_gpu_run(apm_gpu * h, long long n_rounds, int n_swap, const ap
 		return rc;
 	if (path == APM_PATH_CLUSTER) {
 		DISPATCH(h->cfg.model_id, run_cluster_t, h, n_rounds, n_swap)
+	}
+	if (path == APM_PATH_GRID) {
+		DISPATCH(h->cfg.model_id, run_grid_t, h, n_rounds, n_swap)
 	}
 	if (path == APM_PATH_FUSED) {
 		DISPATCH(h->cfg.model_id, run_fused_t, h, n_rounds, n_swap)

@@ -16,6 +16,9 @@
 //   fused_run_kernel<M>      the small-table path: one CTA per ensemble, one warp per chain,
 //   fused_calibrate_kernel<M>  table and ensemble state resident in shared memory, a whole
 //                            run (n_rounds x (n_swap steps + swap)) or calibration per launch.
+//   cluster_run_kernel<M>    the fused path with an ensemble spread over a thread-block cluster.
+//   grid_run_kernel<M>       mid-size tables: one cooperative launch per run, the table partitioned
+//                            over the shared memories of all SMs, one grid barrier per step.
 //   eval_finish_kernel<M>    turns running sums into (prob, prior) for apm_gpu_eval.
 //   absmax_col0_kernel       max |x| of the table (range bound of the fast sine).
 //   fp64_peak_kernel         DFMA issue-rate microbenchmark (the roofline denominator).
@@ -1046,6 +1049,225 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) cluster_run_kernel(co
 			ca.timing[warp * 8 + k] = t_sum[k];
 #endif
 	fused_writeback_block(S, L, ens, k0, rank == 0);
+}
+
+// ------------------------------------------------------------------ grid path
+// Tables too large for one SM's shared memory but far too small to keep the GPU busy for long
+// (10^4 .. 10^6 rows, a few ensembles): the tiled path spends ~28 us per Metropolis step there,
+// almost all of it launch gaps and fixed kernel latencies.  The grid path is ONE cooperative
+// launch per apm_gpu_run with the table PARTITIONED over the shared memories of all SMs:
+//   * CTA b keeps rows [n_rows b / G, n_rows (b + 1) / G) resident for the whole run (one TMA
+//     bulk copy at the start; 148 x ~200 KB holds ~1.8 M two-column rows);
+//   * per step every CTA evaluates ALL chains' proposals on its slice (a warp per chain, 4
+//     independent row evaluations in flight per lane) and publishes one partial sum per chain;
+//     ONE grid barrier; then every CTA adds the G partials of every chain in a fixed order,
+//     takes the accept decision and forms the next proposal -- redundantly, with the chains'
+//     current points replicated in every CTA's shared memory (same instructions, same inputs,
+//     same bits everywhere), exactly like the warps of a group on the cluster path;
+//   * chain g is OWNED by CTA g mod G, whose last warp (it walks no rows) writes the outcome
+//     into the chain state in global memory one step behind (chain_apply_step_warp,
+//     chain_record_warp) and publishes the chain's random draws K steps ahead
+//     (chain_draw_batch); once per round the owners' writes are fenced by a grid barrier, CTA 0
+//     runs adapt + ensemble_swap on the global state, and everybody reloads.
+constexpr int GRID_THREADS = 256, GRID_WARPS = GRID_THREADS / 32;
+constexpr int GRID_MAX_CHAINS = 512;
+
+struct GridArgs {
+	const double * data;
+	long long n_rows;
+	const double * xabsmax;
+	long long n_rounds;
+	int n_swap;
+	double * partials;  // [2][n_chains][G]
+	double * draws;     // [CLUSTER_DRAW_RING][n_chains][32]
+	int max_slice_rows; // shared-memory room for the slice (host-computed)
+};
+
+// shared memory of one CTA: the slice, then per chain {cur, prop, pprop, stepw}[n_par] and
+// {prob, prior, beta, pend_prob, pend_prior} + ctr0 + pend_acc
+__host__ __device__ inline size_t grid_state_bytes(int n_chains, int n_par) {
+	return (size_t) n_chains * (4 * n_par + 5) * sizeof(double) + (size_t) n_chains * (sizeof(u64) + sizeof(int)) + 64;
+}
+
+template<class M>
+__global__ void __launch_bounds__(GRID_THREADS, 1) grid_run_kernel(const DevState S, const GridArgs a) {
+	extern __shared__ __align__(128) unsigned char grid_smem[];
+	namespace cg = cooperative_groups;
+	cg::grid_group grid = cg::this_grid();
+	const int G = gridDim.x, b = blockIdx.x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int n = S.n_par, NC = S.n_chains;
+	const int K = 32 / (n + 1);
+
+	// ---- this CTA's slice of the table, resident for the whole run
+	const long long r0 = a.n_rows * b / G, r1 = a.n_rows * (b + 1) / G;
+	const int n_slice = (int) (r1 - r0);
+	Row<M> * sdata = reinterpret_cast<Row<M> *>(grid_smem);
+	const size_t slice_bytes = (((size_t) a.max_slice_rows * sizeof(Row<M>) + 127) & ~(size_t) 127);
+	uint64_t * bar = reinterpret_cast<uint64_t *>(grid_smem + slice_bytes);
+	if (n_slice > 0) {
+		if (tid == 0) {
+			mbar_init(bar, 1);
+			mbar_fence_init();
+			const uint32_t total = (uint32_t) n_slice * sizeof(Row<M>);
+			mbar_arrive_expect_tx(bar, total);
+			const unsigned char * src = reinterpret_cast<const unsigned char *>(a.data) + (size_t) r0 * sizeof(Row<M>);
+			for (uint32_t off = 0; off < total; off += 32768u)
+				tma_bulk_g2s(reinterpret_cast<unsigned char *>(sdata) + off, src + off, min(32768u, total - off), bar);
+		}
+		__syncthreads();
+		mbar_wait(bar, 0);
+	}
+	// ---- the chains' current points, replicated in every CTA
+	double * f = reinterpret_cast<double *>(grid_smem + slice_bytes + 64);
+	double * cur = f;                    // [NC][n]
+	double * prop = cur + (size_t) NC * n;
+	double * pprop = prop + (size_t) NC * n;   // the proposal of the step being written down
+	double * stepw = pprop + (size_t) NC * n;
+	double * prob_cur = stepw + (size_t) NC * n; // [NC]
+	double * prior_cur = prob_cur + NC;
+	double * beta = prior_cur + NC;
+	double * pend_prob = beta + NC;
+	double * pend_prior = pend_prob + NC;
+	u64 * ctr0 = reinterpret_cast<u64 *>(pend_prior + NC);
+	int * pend_acc = reinterpret_cast<int *>(ctr0 + NC);
+
+	const bool service = warp == GRID_WARPS - 1; // walks no rows
+	const double xub = *a.xabsmax;
+	const double mc[4] = { S.model_const[0], S.model_const[1], S.model_const[2], S.model_const[3] };
+	const double lo = lane < n ? S.pmin[lane] : 0.0, hi = lane < n ? S.pmax[lane] : 0.0;
+	long long step = 0;
+
+	for (long long round = 0; round < a.n_rounds; round++) {
+		// ---- round start: reload the replicated state; the owners publish the first batch of draws
+		for (int i = tid; i < NC * n; i += GRID_THREADS) {
+			cur[i] = __ldcg(S.params + i);
+			stepw[i] = __ldcg(S.steps + i);
+		}
+		for (int c = tid; c < NC; c += GRID_THREADS) {
+			prob_cur[c] = __ldcg(S.prob + c);
+			prior_cur[c] = __ldcg(S.prior + c);
+			beta[c] = __ldcg(S.beta + c);
+			ctr0[c] = __ldcg(S.rng_ctr + c);
+		}
+		for (int c = b + warp * G; c < NC; c += G * GRID_WARPS) // owned chains, spread over the warps
+			chain_draw_batch(S, c, S.rng_ctr[c], K, lane, a.draws + (size_t) c * 32);
+		__syncthreads();
+		grid.sync();
+		// the round's first proposal: the jumps of batch 0 (first attempt), the rare rest as usual
+		for (int c = warp; c < NC; c += GRID_WARPS) {
+			if (lane < n) {
+				const double x = cur[(size_t) c * n + lane];
+				double v = x + __ldcg(a.draws + (size_t) c * 32 + lane);
+				if (v > hi || v < lo)
+					v = propose_coordinate(S, c, ctr0[c], lane, x, stepw[(size_t) c * n + lane]);
+				prop[(size_t) c * n + lane] = v;
+			}
+		}
+		__syncthreads();
+
+		for (int sub = 0; sub < a.n_swap; sub++, step++) {
+			const int par = sub & 1;
+			double * part = a.partials + (size_t) par * NC * G;
+			if (service) {
+				// owned chains: write down step sub - 1, publish the draws of the batch after next
+				for (int c = b; c < NC; c += G) {
+					if (sub > 0) {
+						chain_apply_step_warp(S, c, pend_acc[c], pend_prob[c], pend_prior[c],
+								lane < n ? pprop[(size_t) c * n + lane] : 0.0, lane);
+						chain_record_warp(S, c, step - 1, lane);
+					}
+					if ((sub + 1) % K == 0 && sub + 1 < a.n_swap) {
+						const int bt = (sub + 1) / K;
+						chain_draw_batch(S, c, ctr0[c] + (u64) bt * K, K, lane,
+								a.draws + ((size_t) (bt % CLUSTER_DRAW_RING) * NC + c) * 32);
+					}
+				}
+			} else {
+				// every chain's proposal on this CTA's slice: a warp per chain
+				for (int c = warp; c < NC; c += GRID_WARPS - 1) {
+					const double v = n_slice > 0
+							? group_loglik<M>(S, prop + (size_t) c * n, sdata, n_slice, xub, lane, 32) : 0.0;
+					if (lane == 0)
+						part[(size_t) c * G + b] = v;
+				}
+			}
+			__syncthreads();
+			grid.sync();
+			// ---- every CTA: markov_chain_step's second half for every chain, redundantly
+			const int bsub = (sub / K) % CLUSTER_DRAW_RING, jsub = sub % K;
+			const int bnext = ((sub + 1) / K) % CLUSTER_DRAW_RING, jnext = (sub + 1) % K;
+			for (int c = warp; c < NC; c += GRID_WARPS) {
+				// the G partial sums in a fixed order: lane l adds l, l + 32, ..., then a butterfly
+				double sum = 0.0;
+				for (int k = lane; k < G; k += 32)
+					sum += __ldcg(part + (size_t) c * G + k);
+				sum = warp_sum(sum);
+				const double * wp = prop + (size_t) c * n;
+				double prior_new = prior_cur[c];
+				if (M::HAS_PRIOR)
+					prior_new = M::prior(wp, n, mc);
+				const double prob_new = M::finish(beta[c], M::sum0(wp) + sum, prior_new, wp, mc);
+				const double prob_old = prob_cur[c];
+				int accepted;
+				if (prob_new == prob_old)
+					accepted = 1;
+				else if (prob_new > prob_old)
+					accepted = 1;
+				else
+					accepted = __ldcg(a.draws + ((size_t) bsub * NC + c) * 32 + jsub * (n + 1) + n) < (prob_new - prob_old) ? 1 : 0;
+				const double p_old = lane < n ? prop[(size_t) c * n + lane] : 0.0;
+				double x = lane < n ? cur[(size_t) c * n + lane] : 0.0;
+				if (accepted)
+					x = p_old;
+				__syncwarp(); // everybody has read prob_cur / prop / cur of chain c
+				if (lane < n) {
+					pprop[(size_t) c * n + lane] = p_old;
+					cur[(size_t) c * n + lane] = x;
+					if (sub + 1 < a.n_swap) {
+						double v = x + __ldcg(a.draws + ((size_t) bnext * NC + c) * 32 + jnext * (n + 1) + lane);
+						if (v > hi || v < lo)
+							v = propose_coordinate(S, c, ctr0[c] + (u64) (sub + 1), lane, x, stepw[(size_t) c * n + lane]);
+						prop[(size_t) c * n + lane] = v;
+					}
+				}
+				if (lane == 0) {
+					pend_acc[c] = accepted;
+					pend_prob[c] = prob_new;
+					pend_prior[c] = prior_new;
+					if (accepted) {
+						prob_cur[c] = prob_new;
+						prior_cur[c] = prior_new;
+					} else if (S.quirks & 2u) {
+						prior_cur[c] = prior_new;
+					}
+				}
+			}
+			__syncthreads();
+		}
+		// ---- round end: the owners write down the last step, then adapt + swap on the global state
+		if (service) {
+			for (int c = b; c < NC; c += G) {
+				chain_apply_step_warp(S, c, pend_acc[c], pend_prob[c], pend_prior[c],
+						lane < n ? pprop[(size_t) c * n + lane] : 0.0, lane);
+				chain_record_warp(S, c, step - 1, lane);
+				if (lane == 0)
+					S.pend[c] = PEND_NONE;
+			}
+		}
+		__syncthreads();
+		grid.sync();
+		if (b == 0) {
+			if (S.adapt)
+				for (int c = tid; c < NC; c += GRID_THREADS)
+					chain_adapt(S, c);
+			__syncthreads();
+			for (int e = tid; e < S.n_ens; e += GRID_THREADS)
+				ensemble_swap(S, e);
+		}
+		__syncthreads();
+		grid.sync();
+	}
 }
 
 // markov_chain_calibrate of every selected chain, start to finish in one launch: the per-chain

@@ -70,13 +70,17 @@ extern "C" {
 #define APM_QUIRKS_REFERENCE (APM_QUIRK_STALE_PROB_ON_SWAP | APM_QUIRK_STALE_PRIOR_ON_REJECT)
 
 /* ---- kernel path selection ---------------------------------------------- */
-#define APM_PATH_AUTO    0  /* cluster or fused if the data table fits in shared memory, else tiled */
+#define APM_PATH_AUTO    0  /* cluster or fused if the data table fits in shared memory, else grid or tiled */
 #define APM_PATH_TILED   1  /* (chain tile x row split) likelihood kernel + control kernel per step */
 #define APM_PATH_FUSED   2  /* one persistent launch per run: CTA per ensemble, warp per chain */
 #define APM_PATH_CLUSTER 3  /* fused, with every ensemble spread over a thread-block cluster (2..8 CTAs,
                                warp groups per chain, table by TMA multicast, swaps through distributed
                                shared memory): for fewer ensembles than SMs.  apm_gpu_run only;
                                calibration takes the fused path */
+
+#define APM_PATH_GRID    4  /* mid-size tables (too large for one SM's shared memory, at most 512 chains):
+                               one cooperative launch per run, the table partitioned over the shared
+                               memories of all SMs, one grid barrier per step.  apm_gpu_run only */
 
 /* ---- calibration status per chain --------------------------------------- */
 #define APM_CALIB_OK             0
@@ -259,7 +263,7 @@ long long apm_gpu_launch_count(const apm_gpu * h);
  * on the engine's stream), and how many launches that covers */
 int apm_gpu_last_kernel_ms(const apm_gpu * h, double * loglik_ms,
 		long long * loglik_launches, double * total_ms);
-/* which path the last run used: APM_PATH_TILED, APM_PATH_FUSED or APM_PATH_CLUSTER */
+/* which path the last run used: APM_PATH_TILED, _FUSED, _CLUSTER or _GRID */
 int apm_gpu_last_path(const apm_gpu * h);
 /* microbenchmark: sustained FP64 FMA issue rate of this device, in
  * FP64 instructions (lane-operations) per second; used as the roofline peak */

@@ -139,8 +139,10 @@ def test_linearity_in_rows(capi):
 
 
 # ---------------------------------------------------------------- sampler trajectories
-# APM_PATH_TILED / APM_PATH_FUSED / APM_PATH_CLUSTER
-PATHS = [pytest.param(1, id="tiled"), pytest.param(2, id="fused"), pytest.param(3, id="cluster")]
+# APM_PATH_TILED / APM_PATH_FUSED / APM_PATH_CLUSTER / APM_PATH_GRID
+PATHS = [pytest.param(1, id="tiled"), pytest.param(2, id="fused"), pytest.param(3, id="cluster"),
+         pytest.param(4, id="grid")]
+CALIBRATION_PATH = {1: 1, 2: 2, 3: 2, 4: 1}  # cluster and grid are for runs: calibration falls back
 
 
 def _pair(capi, model, n_ens, n_beta, n_par=None, seed=1, path=0, **kw):
@@ -166,8 +168,8 @@ def test_run_trajectory_equals_oracle(capi, name, kw, quirks, path):
     """3 ensembles x the fixture's ladder, started from the reference's own calibration_results:
     the whole run (steps, swaps, best tracking, traces, accumulators) against the oracle"""
     fx = load(name)
-    if path == 3 and fx["model"] == "normal":
-        pytest.skip("the cluster path is for models with data")
+    if path in (3, 4) and fx["model"] == "normal":
+        pytest.skip("the cluster and grid paths are for models with data")
     rows = [tuple(r) for r in fx["rows"]]
     n_par, n_beta, n_ens = len(rows), fx["config"]["N_BETA"], 3
     data = (np.loadtxt(os.path.join(GOLDEN, fx["data_file"])) if fx["data_file"]
@@ -209,8 +211,8 @@ def test_bernoulli_rows_of_four_doubles(capi, path, n_cols, n_rows):
     rows of 4 doubles on the device; calc_model to 1e-12 and whole runs against the oracle on
     every kernel path (5000 rows x 32 B does not fit the fused paths' shared memory twice over,
     so that case is tiled only)"""
-    if n_rows * 32 > 150_000 and path != 1:
-        pytest.skip("table too large for the shared-memory paths")
+    if n_rows * 32 > 150_000 and path in (2, 3):
+        pytest.skip("table too large for the one-SM shared-memory paths")
     data = _logistic_table(n_rows, n_cols, 7 * n_cols)
     n_ens, n_beta, n_par = 2, 6, n_cols
     n = n_ens * n_beta
@@ -344,6 +346,36 @@ def test_auto_path_prefers_cluster_for_few_ensembles(capi):
         assert e.last_path() == want, (n_ens, e.last_path())
 
 
+@pytest.mark.parametrize("n_rows,n_ens,n_beta", [(40_000, 1, 20), (300_001, 3, 7), (100, 2, 5), (1_200_000, 1, 4)])
+def test_grid_path_mid_size_tables(capi, n_rows, n_ens, n_beta):
+    """the grid path (table partitioned over the shared memories of all SMs, one grid barrier per
+    step, decisions replicated in every CTA) against the oracle: tables from fewer rows than SMs to
+    1.2 M rows, with traces, accumulators and accepted swaps"""
+    data = lightcurve(n_rows, seed=n_beta)
+    n = n_ens * n_beta
+    rng = np.random.default_rng(n)
+    scale = (1e6 / n_rows) ** 0.5
+    params = np.tile([1.3, 7.25, 0.31 * 2 * np.pi, 0.2], (n, 1)) + rng.normal(0, 1e-5, (n, 4)) * scale
+    beta = np.tile(np.linspace(1.0, 0.8, n_beta), n_ens)
+    steps = np.tile([7e-4, 3e-7, 1.1e-3, 5e-4], (n, 1)) * scale * beta[:, None] ** -0.5
+    res = []
+    for eng in _pair(capi, "simplesin5", n_ens, n_beta, seed=61, path=4):
+        eng.set_data(data)
+        eng.set_bounds(SS5_LO, SS5_HI)
+        eng.set_chains(0, n, beta=beta, params=params, steps=steps, params_best=params)
+        eng.reset_stats()
+        rounds, n_swap = (2, 4) if n_rows > 1_000_000 else (6, 9)
+        eng.run(rounds, n_swap, prob_every=1, params_chains=1)
+        eng.run(2, 3, prob_every=2, params_chains=2)
+        res.append((eng.read_trace(), eng.get_chains(), eng.get_stats()))
+    (tr_g, st_g, ac_g), (tr_c, st_c, ac_c) = res
+    _compare_state(st_g, st_c)
+    for k in ("prob", "prob_minus_prior", "params"):
+        np.testing.assert_allclose(tr_g[k], tr_c[k], rtol=RTOL_TRAJ, atol=1e-300, err_msg=k)
+    np.testing.assert_array_equal(ac_g["n"], ac_c["n"])
+    np.testing.assert_allclose(ac_g["sum_dl"], ac_c["sum_dl"], rtol=RTOL_TRAJ)
+
+
 def test_fused_path_refuses_a_table_that_does_not_fit(capi):
     e = capi.Engine("simplesin5", 1, 2, path=2)
     e.set_data(lightcurve(20_000))
@@ -420,7 +452,7 @@ def test_calibration_trajectory_equals_oracle(capi, name, path):
         status, prog = eng.calibrate(burn_in_iterations=600, progress_capacity=100000)
         res.append((status, prog, eng.get_chains()))
     (s_g, p_g, st_g), (s_c, p_c, st_c) = res
-    assert engines[0].last_path() == (2 if path == 3 else path)  # calibration: cluster -> fused
+    assert engines[0].last_path() == CALIBRATION_PATH[path]
     np.testing.assert_array_equal(s_g, s_c)
     assert (s_g == 0).all()
     _compare_state(st_g, st_c)
