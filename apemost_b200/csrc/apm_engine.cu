@@ -724,10 +724,9 @@ static int cluster_size_for(const apm_gpu * h, bool has_data) {
 	return 0;
 }
 
-// grid path: rows per CTA (0 = the path does not apply).  Worth it where a step of the tiled path is
-// dominated by launch gaps and fixed latencies (~28 us): up to ~3e7 row evaluations per step.
+// grid path: rows per CTA (0 = the path does not apply)
 static int grid_slice_rows(const apm_gpu * h, bool has_data) {
-	if (!has_data || h->comm || h->n_chains > GRID_MAX_CHAINS || h->n_rows < 1)
+	if (!has_data || h->comm || h->n_chains > GRID_MAX_CHAINS_PER_SM * h->sm_count || h->n_rows < 1)
 		return 0;
 	if (getenv("APM_NO_GRID"))
 		return 0;
@@ -757,8 +756,8 @@ static int choose_path(apm_gpu * h, int * path, bool for_run = false) {
 	if (want == APM_PATH_GRID) {
 		if (gslice == 0)
 			return fail(h, APM_EINVAL, "the grid path needs a data model, at most %d chains, a slice of the table "
-					"(rows / %d SMs) plus the chains' state in shared memory and no multi-GPU sharding",
-					GRID_MAX_CHAINS, h->sm_count);
+					"(rows / %d SMs) plus the chains' proposals in shared memory and no multi-GPU sharding",
+					GRID_MAX_CHAINS_PER_SM * h->sm_count, h->sm_count);
 		*path = APM_PATH_GRID;
 	} else if (want == APM_PATH_CLUSTER) {
 		if (cl == 0)
@@ -777,9 +776,10 @@ static int choose_path(apm_gpu * h, int * path, bool for_run = false) {
 	} else if (want == APM_PATH_TILED) {
 		*path = APM_PATH_TILED;
 	} else {
-		// tiled steps cost ~28 us of launch gaps and fixed latencies; the grid path pays one grid
-		// barrier instead, until the row evaluations themselves take several times that
-		const bool grid_pays = gslice > 0 && (double) h->n_rows * h->n_chains <= 6e7;
+		// a tiled step costs ~27 us of launch gaps and fixed latencies, a grid step two grid barriers
+		// (~7 us); measured (tools/mid_bench.py) the grid path is ahead up to ~5e8 row evaluations
+		// per step, where both are bound by the row evaluations themselves
+		const bool grid_pays = gslice > 0 && (double) h->n_rows * h->n_chains <= 5e8;
 		*path = cl > 0 ? APM_PATH_CLUSTER
 				: ((fits && !h->comm) ? APM_PATH_FUSED : (grid_pays ? APM_PATH_GRID : APM_PATH_TILED));
 	}
@@ -905,8 +905,8 @@ static int run_grid_t(apm_gpu * h, long long n_rounds, int n_swap) {
 	if (slice == 0)
 		return fail(h, APM_ESTATE, "no grid geometry");
 	const int G = h->sm_count;
-	CU(ensure_cap(&h->d_grid_partials, &h->grid_partials_cap, (size_t) 2 * h->n_chains * G));
-	CU(ensure_cap(&h->d_grid_draws, &h->grid_draws_cap, (size_t) CLUSTER_DRAW_RING * h->n_chains * 32));
+	CU(ensure_cap(&h->d_grid_partials, &h->grid_partials_cap, (size_t) h->n_chains * G));
+	CU(ensure_cap(&h->d_grid_draws, &h->grid_draws_cap, (size_t) h->n_chains * h->cfg.n_par));
 	GridArgs ga;
 	ga.data = h->d_data;
 	ga.n_rows = h->n_rows;
@@ -914,7 +914,7 @@ static int run_grid_t(apm_gpu * h, long long n_rounds, int n_swap) {
 	ga.n_rounds = n_rounds;
 	ga.n_swap = n_swap;
 	ga.partials = h->d_grid_partials;
-	ga.draws = h->d_grid_draws;
+	ga.props = h->d_grid_draws;
 	ga.max_slice_rows = slice;
 	const size_t smem = (((size_t) slice * sizeof(Row<M>) + 127) & ~(size_t) 127) + 64
 			+ grid_state_bytes(h->n_chains, h->cfg.n_par);

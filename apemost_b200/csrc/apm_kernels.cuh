@@ -1058,19 +1058,21 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) cluster_run_kernel(co
 // launch per apm_gpu_run with the table PARTITIONED over the shared memories of all SMs:
 //   * CTA b keeps rows [n_rows b / G, n_rows (b + 1) / G) resident for the whole run (one TMA
 //     bulk copy at the start; 148 x ~200 KB holds ~1.8 M two-column rows);
-//   * per step every CTA evaluates ALL chains' proposals on its slice (a warp per chain, 4
+//   * chain c is OWNED by CTA c mod G: its whole state lives in that CTA's shared memory for the
+//     run (fused_localize_block, as on the fused path), and one of its warps plays the chain's
+//     markov_chain_step;
+//   * per step: every CTA evaluates ALL chains' proposals on its slice (a warp per chain, 4
 //     independent row evaluations in flight per lane) and publishes one partial sum per chain;
-//     ONE grid barrier; then every CTA adds the G partials of every chain in a fixed order,
-//     takes the accept decision and forms the next proposal -- redundantly, with the chains'
-//     current points replicated in every CTA's shared memory (same instructions, same inputs,
-//     same bits everywhere), exactly like the warps of a group on the cluster path;
-//   * chain g is OWNED by CTA g mod G, whose last warp (it walks no rows) writes the outcome
-//     into the chain state in global memory one step behind (chain_apply_step_warp,
-//     chain_record_warp) and publishes the chain's random draws K steps ahead
-//     (chain_draw_batch); once per round the owners' writes are fenced by a grid barrier, CTA 0
-//     runs adapt + ensemble_swap on the global state, and everybody reloads.
+//     grid barrier; the owner adds the G partials in a fixed order (lane-strided, then an fp64
+//     butterfly), finalises the step, draws the next proposal (random draws in lane-parallel
+//     batches of K steps) and publishes it; grid barrier; everybody fetches the new proposals
+//     (one coalesced read) while the owner does the step's bookkeeping (best, trace rows,
+//     accumulators) in its shared memory;
+//   * once per round the owners write their chains back, CTA 0 runs adapt + ensemble_swap on the
+//     global state, and the owners reload.
 constexpr int GRID_THREADS = 256, GRID_WARPS = GRID_THREADS / 32;
-constexpr int GRID_MAX_CHAINS = 512;
+constexpr int GRID_MAX_OWNED = 8;                // chains per CTA: one per warp
+constexpr int GRID_MAX_CHAINS_PER_SM = GRID_MAX_OWNED;
 
 struct GridArgs {
 	const double * data;
@@ -1078,15 +1080,16 @@ struct GridArgs {
 	const double * xabsmax;
 	long long n_rounds;
 	int n_swap;
-	double * partials;  // [2][n_chains][G]
-	double * draws;     // [CLUSTER_DRAW_RING][n_chains][32]
+	double * partials;  // [n_chains][G]
+	double * props;     // [n_chains][n_par]: the pending proposals, published by the owners
 	int max_slice_rows; // shared-memory room for the slice (host-computed)
 };
 
-// shared memory of one CTA: the slice, then per chain {cur, prop, pprop, stepw}[n_par] and
-// {prob, prior, beta, pend_prob, pend_prior} + ctr0 + pend_acc
+// shared memory of one CTA after the slice: all chains' proposals, and per owned chain its
+// localized state and a batch of draws
 __host__ __device__ inline size_t grid_state_bytes(int n_chains, int n_par) {
-	return (size_t) n_chains * (4 * n_par + 5) * sizeof(double) + (size_t) n_chains * (sizeof(u64) + sizeof(int)) + 64;
+	return (size_t) n_chains * n_par * sizeof(double)
+			+ (size_t) GRID_MAX_OWNED * (fused_state_bytes(1, n_par) + 32 * sizeof(double)) + 64;
 }
 
 template<class M>
@@ -1118,142 +1121,109 @@ __global__ void __launch_bounds__(GRID_THREADS, 1) grid_run_kernel(const DevStat
 		__syncthreads();
 		mbar_wait(bar, 0);
 	}
-	// ---- the chains' current points, replicated in every CTA
-	double * f = reinterpret_cast<double *>(grid_smem + slice_bytes + 64);
-	double * cur = f;                    // [NC][n]
-	double * prop = cur + (size_t) NC * n;
-	double * pprop = prop + (size_t) NC * n;   // the proposal of the step being written down
-	double * stepw = pprop + (size_t) NC * n;
-	double * prob_cur = stepw + (size_t) NC * n; // [NC]
-	double * prior_cur = prob_cur + NC;
-	double * beta = prior_cur + NC;
-	double * pend_prob = beta + NC;
-	double * pend_prior = pend_prob + NC;
-	u64 * ctr0 = reinterpret_cast<u64 *>(pend_prior + NC);
-	int * pend_acc = reinterpret_cast<int *>(ctr0 + NC);
+	double * props = reinterpret_cast<double *>(grid_smem + slice_bytes + 64); // [NC][n]
+	unsigned char * own_mem = reinterpret_cast<unsigned char *>(props + (size_t) NC * n);
+	const size_t own_stride = fused_state_bytes(1, n) + 32 * sizeof(double);
+	__shared__ DevState L_own[GRID_MAX_OWNED];
 
-	const bool service = warp == GRID_WARPS - 1; // walks no rows
+	// the chain this warp plays (warp w of CTA b owns chain b + w G), if any
+	const int my_chain = b + warp * G;
+	const bool owner = my_chain < NC;
+	const int my_ens = owner ? my_chain / S.n_beta : 0, my_k = owner ? my_chain % S.n_beta : 0;
+	unsigned char * my_mem = own_mem + (size_t) warp * own_stride;
+	double * my_draws = reinterpret_cast<double *>(my_mem + fused_state_bytes(1, n)); // [K][n + 1]
 	const double xub = *a.xabsmax;
-	const double mc[4] = { S.model_const[0], S.model_const[1], S.model_const[2], S.model_const[3] };
-	const double lo = lane < n ? S.pmin[lane] : 0.0, hi = lane < n ? S.pmax[lane] : 0.0;
 	long long step = 0;
 
 	for (long long round = 0; round < a.n_rounds; round++) {
-		// ---- round start: reload the replicated state; the owners publish the first batch of draws
-		for (int i = tid; i < NC * n; i += GRID_THREADS) {
-			cur[i] = __ldcg(S.params + i);
-			stepw[i] = __ldcg(S.steps + i);
-		}
-		for (int c = tid; c < NC; c += GRID_THREADS) {
-			prob_cur[c] = __ldcg(S.prob + c);
-			prior_cur[c] = __ldcg(S.prior + c);
-			beta[c] = __ldcg(S.beta + c);
-			ctr0[c] = __ldcg(S.rng_ctr + c);
-		}
-		for (int c = b + warp * G; c < NC; c += G * GRID_WARPS) // owned chains, spread over the warps
-			chain_draw_batch(S, c, S.rng_ctr[c], K, lane, a.draws + (size_t) c * 32);
-		__syncthreads();
-		grid.sync();
-		// the round's first proposal: the jumps of batch 0 (first attempt), the rare rest as usual
-		for (int c = warp; c < NC; c += GRID_WARPS) {
-			if (lane < n) {
-				const double x = cur[(size_t) c * n + lane];
-				double v = x + __ldcg(a.draws + (size_t) c * 32 + lane);
-				if (v > hi || v < lo)
-					v = propose_coordinate(S, c, ctr0[c], lane, x, stepw[(size_t) c * n + lane]);
-				prop[(size_t) c * n + lane] = v;
+		// ---- round start: the owners take their chains into shared memory and publish the round's
+		// first proposals.  (fused_localize_block is written for a whole CTA; one chain is tiny,
+		// so the warps go through it one after the other.)
+		for (int w = 0; w < GRID_WARPS; w++) {
+			const int c = b + w * G;
+			if (c < NC) { // uniform over the CTA
+				const DevState L_tmp = fused_localize_block(S, c / S.n_beta, c % S.n_beta, 1, own_mem + (size_t) w * own_stride);
+				if (tid == 0)
+					L_own[w] = L_tmp;
+				__syncthreads();
 			}
 		}
+		u64 draw_base = 0;
+		if (owner) {
+			const DevState & L = L_own[warp];
+			draw_base = L.rng_ctr[0];
+			chain_draw_batch(L, 0, draw_base, K, lane, my_draws);
+			__syncwarp();
+			if (lane < n) {
+				const double x = L.params[lane];
+				double v = x + my_draws[lane];
+				if (v > L.pmax[lane] || v < L.pmin[lane])
+					v = propose_coordinate(L, 0, draw_base, lane, x, L.steps[lane]);
+				L.prop[lane] = v;
+				a.props[(size_t) my_chain * n + lane] = v;
+			}
+			if (lane == 0)
+				L.pend[0] = n;
+		}
+		__syncthreads();
+		grid.sync();
+		for (int i = tid; i < NC * n; i += GRID_THREADS)
+			props[i] = __ldcg(a.props + i);
 		__syncthreads();
 
 		for (int sub = 0; sub < a.n_swap; sub++, step++) {
-			const int par = sub & 1;
-			double * part = a.partials + (size_t) par * NC * G;
-			if (service) {
-				// owned chains: write down step sub - 1, publish the draws of the batch after next
-				for (int c = b; c < NC; c += G) {
-					if (sub > 0) {
-						chain_apply_step_warp(S, c, pend_acc[c], pend_prob[c], pend_prior[c],
-								lane < n ? pprop[(size_t) c * n + lane] : 0.0, lane);
-						chain_record_warp(S, c, step - 1, lane);
+			// ---- every chain's proposal on this CTA's slice: a warp per chain
+			for (int c = warp; c < NC; c += GRID_WARPS) {
+				const double v = n_slice > 0 ? group_loglik<M>(S, props + (size_t) c * n, sdata, n_slice, xub, lane, 32) : 0.0;
+				if (lane == 0)
+					a.partials[(size_t) c * G + b] = v;
+			}
+			__syncthreads();
+			grid.sync();
+			// ---- the owners: markov_chain_step's second half and the next proposal
+			if (owner) {
+				const DevState & L = L_own[warp];
+				// the G partial sums in a fixed order: lane l adds l, l + 32, ..., then a butterfly
+				double sum = 0.0;
+				for (int k = lane; k < G; k += 32)
+					sum += __ldcg(a.partials + (size_t) my_chain * G + k);
+				sum = warp_sum(sum);
+				const u64 ctr = L.rng_ctr[0];
+				const double * logu = my_draws + (size_t) (ctr - draw_base) * (n + 1) + n;
+				chain_finalize_warp<M>(L, 0, M::sum0(L.prop) + sum, logu, lane);
+				if (sub + 1 < a.n_swap) {
+					if (ctr + 1 >= draw_base + (u64) K) { // the batch is used up: draw the next K steps
+						draw_base = ctr + 1;
+						chain_draw_batch(L, 0, draw_base, K, lane, my_draws);
+						__syncwarp();
 					}
-					if ((sub + 1) % K == 0 && sub + 1 < a.n_swap) {
-						const int bt = (sub + 1) / K;
-						chain_draw_batch(S, c, ctr0[c] + (u64) bt * K, K, lane,
-								a.draws + ((size_t) (bt % CLUSTER_DRAW_RING) * NC + c) * 32);
+					if (lane < n) {
+						const double x = L.params[lane];
+						double v = x + my_draws[(size_t) (ctr + 1 - draw_base) * (n + 1) + lane];
+						if (v > L.pmax[lane] || v < L.pmin[lane])
+							v = propose_coordinate(L, 0, ctr + 1, lane, x, L.steps[lane]);
+						L.prop[lane] = v;
+						a.props[(size_t) my_chain * n + lane] = v;
 					}
-				}
-			} else {
-				// every chain's proposal on this CTA's slice: a warp per chain
-				for (int c = warp; c < NC; c += GRID_WARPS - 1) {
-					const double v = n_slice > 0
-							? group_loglik<M>(S, prop + (size_t) c * n, sdata, n_slice, xub, lane, 32) : 0.0;
 					if (lane == 0)
-						part[(size_t) c * G + b] = v;
+						L.pend[0] = n;
 				}
 			}
 			__syncthreads();
 			grid.sync();
-			// ---- every CTA: markov_chain_step's second half for every chain, redundantly
-			const int bsub = (sub / K) % CLUSTER_DRAW_RING, jsub = sub % K;
-			const int bnext = ((sub + 1) / K) % CLUSTER_DRAW_RING, jnext = (sub + 1) % K;
-			for (int c = warp; c < NC; c += GRID_WARPS) {
-				// the G partial sums in a fixed order: lane l adds l, l + 32, ..., then a butterfly
-				double sum = 0.0;
-				for (int k = lane; k < G; k += 32)
-					sum += __ldcg(part + (size_t) c * G + k);
-				sum = warp_sum(sum);
-				const double * wp = prop + (size_t) c * n;
-				double prior_new = prior_cur[c];
-				if (M::HAS_PRIOR)
-					prior_new = M::prior(wp, n, mc);
-				const double prob_new = M::finish(beta[c], M::sum0(wp) + sum, prior_new, wp, mc);
-				const double prob_old = prob_cur[c];
-				int accepted;
-				if (prob_new == prob_old)
-					accepted = 1;
-				else if (prob_new > prob_old)
-					accepted = 1;
-				else
-					accepted = __ldcg(a.draws + ((size_t) bsub * NC + c) * 32 + jsub * (n + 1) + n) < (prob_new - prob_old) ? 1 : 0;
-				const double p_old = lane < n ? prop[(size_t) c * n + lane] : 0.0;
-				double x = lane < n ? cur[(size_t) c * n + lane] : 0.0;
-				if (accepted)
-					x = p_old;
-				__syncwarp(); // everybody has read prob_cur / prop / cur of chain c
-				if (lane < n) {
-					pprop[(size_t) c * n + lane] = p_old;
-					cur[(size_t) c * n + lane] = x;
-					if (sub + 1 < a.n_swap) {
-						double v = x + __ldcg(a.draws + ((size_t) bnext * NC + c) * 32 + jnext * (n + 1) + lane);
-						if (v > hi || v < lo)
-							v = propose_coordinate(S, c, ctr0[c] + (u64) (sub + 1), lane, x, stepw[(size_t) c * n + lane]);
-						prop[(size_t) c * n + lane] = v;
-					}
-				}
-				if (lane == 0) {
-					pend_acc[c] = accepted;
-					pend_prob[c] = prob_new;
-					pend_prior[c] = prior_new;
-					if (accepted) {
-						prob_cur[c] = prob_new;
-						prior_cur[c] = prior_new;
-					} else if (S.quirks & 2u) {
-						prior_cur[c] = prior_new;
-					}
-				}
-			}
+			// ---- everybody fetches the proposals; the owners do the step's bookkeeping meanwhile
+			if (sub + 1 < a.n_swap)
+				for (int i = tid; i < NC * n; i += GRID_THREADS)
+					props[i] = __ldcg(a.props + i);
+			if (owner)
+				chain_record_warp(L_own[warp], 0, step, lane);
 			__syncthreads();
 		}
-		// ---- round end: the owners write down the last step, then adapt + swap on the global state
-		if (service) {
-			for (int c = b; c < NC; c += G) {
-				chain_apply_step_warp(S, c, pend_acc[c], pend_prob[c], pend_prior[c],
-						lane < n ? pprop[(size_t) c * n + lane] : 0.0, lane);
-				chain_record_warp(S, c, step - 1, lane);
-				if (lane == 0)
-					S.pend[c] = PEND_NONE;
-			}
+		// ---- round end: write the chains back, adapt + swap on the global state
+		for (int w = 0; w < GRID_WARPS; w++) {
+			const int c = b + w * G;
+			if (c < NC)
+				fused_writeback_block(S, L_own[w], c / S.n_beta, c % S.n_beta, false);
 		}
 		__syncthreads();
 		grid.sync();
