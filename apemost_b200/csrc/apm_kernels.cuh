@@ -1129,7 +1129,6 @@ __global__ void __launch_bounds__(GRID_THREADS, 1) grid_run_kernel(const DevStat
 	// the chain this warp plays (warp w of CTA b owns chain b + w G), if any
 	const int my_chain = b + warp * G;
 	const bool owner = my_chain < NC;
-	const int my_ens = owner ? my_chain / S.n_beta : 0, my_k = owner ? my_chain % S.n_beta : 0;
 	unsigned char * my_mem = own_mem + (size_t) warp * own_stride;
 	double * my_draws = reinterpret_cast<double *>(my_mem + fused_state_bytes(1, n)); // [K][n + 1]
 	const double xub = *a.xabsmax;
