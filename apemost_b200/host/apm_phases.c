@@ -575,6 +575,78 @@ static void * write_trace(void * arg) {
 	return NULL;
 }
 
+/* the helper thread: lives for the whole run (so does its OpenMP team), takes one job at a time */
+typedef struct {
+	pthread_t thread;
+	pthread_mutex_t lock;
+	pthread_cond_t wake, idle;
+	write_job job;
+	int has_job, busy, quit, started;
+} writer_t;
+
+static void * writer_main(void * arg) {
+	writer_t * w = (writer_t *) arg;
+	pthread_mutex_lock(&w->lock);
+	while (1) {
+		while (!w->has_job && !w->quit)
+			pthread_cond_wait(&w->wake, &w->lock);
+		if (!w->has_job && w->quit)
+			break;
+		w->has_job = 0;
+		w->busy = 1;
+		pthread_mutex_unlock(&w->lock);
+		write_trace(&w->job);
+		pthread_mutex_lock(&w->lock);
+		w->busy = 0;
+		pthread_cond_broadcast(&w->idle);
+	}
+	pthread_mutex_unlock(&w->lock);
+	return NULL;
+}
+
+static void writer_start(writer_t * w) {
+	memset(w, 0, sizeof(*w));
+	pthread_mutex_init(&w->lock, NULL);
+	pthread_cond_init(&w->wake, NULL);
+	pthread_cond_init(&w->idle, NULL);
+	w->started = pthread_create(&w->thread, NULL, writer_main, w) == 0;
+}
+
+/* block until the job handed over last (if any) has been written */
+static void writer_wait(writer_t * w) {
+	if (!w->started)
+		return;
+	pthread_mutex_lock(&w->lock);
+	while (w->has_job || w->busy)
+		pthread_cond_wait(&w->idle, &w->lock);
+	pthread_mutex_unlock(&w->lock);
+}
+
+/* hand over a job (the previous one must have been waited for) */
+static void writer_submit(writer_t * w, const write_job * job) {
+	if (!w->started) {
+		write_trace((void *) job);
+		return;
+	}
+	pthread_mutex_lock(&w->lock);
+	w->job = *job;
+	w->has_job = 1;
+	pthread_cond_signal(&w->wake);
+	pthread_mutex_unlock(&w->lock);
+}
+
+static void writer_stop(writer_t * w) {
+	if (!w->started)
+		return;
+	writer_wait(w);
+	pthread_mutex_lock(&w->lock);
+	w->quit = 1;
+	pthread_cond_signal(&w->wake);
+	pthread_mutex_unlock(&w->lock);
+	pthread_join(w->thread, NULL);
+	w->started = 0;
+}
+
 static void report(apm_session * s) {
 	int e, i;
 	printf("printing chain parameters: \n");
@@ -635,7 +707,19 @@ static void write_run_statistics(apm_session * s) {
 	free(cnt); free(sdl); free(sp); free(sp2);
 }
 
+/* APM_HOST_TIMING=1: where the wall time of `run` goes, on stderr */
+static double wall_s(void) {
+	struct timespec t;
+	clock_gettime(CLOCK_MONOTONIC, &t);
+	return t.tv_sec + 1e-9 * t.tv_nsec;
+}
+#define TIMING_MARK(what) do { if (timing) { const double t_now = wall_s(); \
+		fprintf(stderr, "[timing] %-28s %8.3f s\n", what, t_now - t_mark); t_mark = t_now; } } while (0)
+
 void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
+	const int timing = getenv("APM_HOST_TIMING") != NULL;
+	double t_mark = wall_s(), t_a = 0, t_b = 0, t_engine = 0, t_read = 0, t_join = 0;
+	long n_calls = 0;
 	apm_session * s = apm_session_open();
 	const int n_beta = s->n_beta, n_ens = s->n_ens, n_par = s->n_par, n_chains = s->n_chains;
 	char * mode = append == 1 ? "a" : "w";
@@ -648,8 +732,8 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 	double * t_prob[2] = { NULL, NULL }, *t_dl[2] = { NULL, NULL }, *t_par[2] = { NULL, NULL };
 	size_t t_cap[2] = { 0, 0 };
 	write_job job;
-	pthread_t writer;
-	int writer_active = 0, cur = 0;
+	writer_t writer;
+	int cur = 0;
 	char name[64];
 	int e, i, n_dumped;
 
@@ -714,9 +798,11 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 	signal(SIGUSR2, on_sigusr);
 	keep_running = 1;
 	dump_requested = 0;
+	writer_start(&writer);
 	iter = s->chains[0]->n_iter;
 	printf("starting the analysis\n");
 	fflush(stdout);
+	TIMING_MARK("start-up (files, CUDA, upload)");
 
 	while (keep_running && (max_iterations == 0 || iter < max_iterations)) {
 		/* one engine call: up to the next status row, the end of the run, the trace bound and
@@ -737,9 +823,13 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 		if (rounds * n_swap > max_rows)
 			rounds = max_rows / n_swap;
 		clock_gettime(CLOCK_MONOTONIC, &t0);
+		t_a = wall_s();
 		apm_gpu_check(s, apm_gpu_run(s->gpu, rounds, n_swap, &trace), "sampling");
+		t_b = wall_s();
+		t_engine += t_b - t_a;
+		n_calls++;
 		need = (size_t) rounds * n_swap;
-		if (need > t_cap[cur]) { /* (buffer `cur` is idle: its writer was joined one call ago) */
+		if (need > t_cap[cur]) { /* (buffer `cur` is idle: its job was waited for one call ago) */
 			free(t_prob[cur]); free(t_dl[cur]); free(t_par[cur]);
 			t_cap[cur] = need;
 			t_prob[cur] = (double *) malloc(need * n_chains * sizeof(double));
@@ -749,6 +839,7 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 		}
 		apm_gpu_check(s, apm_gpu_read_trace(s->gpu, t_prob[cur], t_dl[cur], t_par[cur], &n_prob_rows, &n_par_rows),
 				"reading the trace");
+		t_read += wall_s() - t_b;
 		clock_gettime(CLOCK_MONOTONIC, &t1);
 		secs = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 		if (secs < 0.25 && call_cap < (1ll << 40))
@@ -757,8 +848,9 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 			call_cap /= 2;
 
 		/* hand the trace to the writer; the previous job (other buffer, same files) must be done */
-		if (writer_active)
-			pthread_join(writer, NULL);
+		t_a = wall_s();
+		writer_wait(&writer);
+		t_join += wall_s() - t_a;
 		job.s = s;
 		job.prob_files = prob_files;
 		job.t_prob = t_prob[cur];
@@ -768,12 +860,7 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 		job.n_par_rows = n_par_rows;
 		job.n_dumped = n_dumped;
 		job.params_chains = trace.params_chains;
-		if (pthread_create(&writer, NULL, write_trace, &job) == 0) {
-			writer_active = 1;
-		} else {
-			writer_active = 0;
-			write_trace(&job);
-		}
+		writer_submit(&writer, &job);
 		cur ^= 1;
 		iter += (unsigned long) rounds * n_swap;
 
@@ -783,10 +870,7 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 			if (dump_requested) {
 				report(s);
 				dump_requested = 0;
-				if (writer_active) {
-					pthread_join(writer, NULL);
-					writer_active = 0;
-				}
+				writer_wait(&writer);
 				for (i = 0; i < n_chains; i++)
 					fflush(prob_files[i]);
 			}
@@ -804,8 +888,12 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 			fflush(stdout);
 		}
 	}
-	if (writer_active)
-		pthread_join(writer, NULL);
+	TIMING_MARK("sampling loop");
+	if (timing)
+		fprintf(stderr, "[timing]   of which: engine %.3f s, reading the trace %.3f s, waiting for the writer %.3f s "
+				"(%ld engine calls)\n", t_engine, t_read, t_join, n_calls);
+	writer_stop(&writer);
+	TIMING_MARK("waiting for the dump writer");
 	apm_session_pull(s, 0, n_chains);
 	for (e = 0; e < n_ens; e++)
 		fclose(accept_files[e]);
@@ -821,5 +909,7 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 	}
 	free(prob_files);
 	free(accept_files);
+	TIMING_MARK("closing files, statistics");
 	apm_session_close(s);
+	TIMING_MARK("engine shutdown");
 }
