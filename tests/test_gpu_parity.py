@@ -138,6 +138,53 @@ def test_linearity_in_rows(capi):
     np.testing.assert_allclose(full.eval(params)[0], a.eval(params)[0] + b.eval(params)[0], rtol=1e-13)
 
 
+def test_full_size_properties_c3(capi):
+    """BASELINE config C3 at full size (1M rows x 4096 parameter vectors, one launch of the hot
+    kernel), through properties that need no CPU evaluation: a vector's value does not depend on
+    its slot (which chain tile, which position in the tile), is reproducible bit for bit from
+    launch to launch, and a sample of slots agrees with the oracle to 1e-12"""
+    data = lightcurve(1_000_000)
+    rng = np.random.default_rng(11)
+    distinct = rng.uniform(SS5_LO, SS5_HI, size=(64, 4))
+    distinct[0] = [1.3, 7.25, 0.31 * 2 * np.pi, 0.2]
+    slot_of = rng.integers(0, 64, size=4096)
+    params = distinct[slot_of]
+    e = capi.Engine("simplesin5", 1, 1)
+    e.set_data(data)
+    p1, _ = e.eval(params)
+    p2, _ = e.eval(params)
+    np.testing.assert_array_equal(p1, p2)
+    for k in range(64):
+        vals = p1[slot_of == k]
+        assert (vals == vals[0]).all(), k
+    o = Oracle("simplesin5", 1, 1)
+    o.set_data(data)
+    want, _ = o.eval(distinct[:6])
+    got = np.array([p1[slot_of == k][0] for k in range(6)])
+    np.testing.assert_allclose(got, want, rtol=RTOL_LOGLIK)
+
+
+def test_full_size_properties_c5_shard(capi):
+    """one GPU's shard of BASELINE config C5 (12.5M rows = 200 MB, more than L2): the running sum
+    over the shard equals the sum over two unequal parts (1e-13), and does not depend on the tile
+    a vector sits in"""
+    n = 12_500_000
+    data = lightcurve(n, seed=5)
+    params = np.tile(np.array([[1.3, 7.25, 0.31 * 2 * np.pi, 0.2], [0.7, 5.5, 1.0, -0.1]]), (9, 1))  # 18 slots
+    full = capi.Engine("simplesin5", 1, 1)
+    full.set_data(data)
+    p_full, _ = full.eval(params)
+    assert (p_full[0::2] == p_full[0]).all() and (p_full[1::2] == p_full[1]).all()
+    cut = 4_999_999
+    parts = []
+    for lo, hi in ((0, cut), (cut, n)):
+        e = capi.Engine("simplesin5", 1, 1)
+        e.set_data(data[lo:hi])
+        parts.append(e.eval(params[:2])[0])
+        e.close()
+    np.testing.assert_allclose(p_full[:2], parts[0] + parts[1], rtol=1e-13)
+
+
 # ---------------------------------------------------------------- sampler trajectories
 # APM_PATH_TILED / APM_PATH_FUSED / APM_PATH_CLUSTER / APM_PATH_GRID
 PATHS = [pytest.param(1, id="tiled"), pytest.param(2, id="fused"), pytest.param(3, id="cluster"),
