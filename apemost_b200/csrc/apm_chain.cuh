@@ -444,6 +444,55 @@ APM_D void chain_draw_batch(const DevState & S, int g, u64 ctr0, int K, int lane
 	}
 }
 
+// ---- a warp that plays a whole chain (fused and grid paths): steps with batched draws ---------
+// `draws` is the chain's 32-double buffer holding the draws of step counters draw_base ..
+// draw_base + K - 1 (chain_draw_batch), K = 32 / (n_par + 1).
+// the first proposal after the chain's state has been (re)loaded: draws a fresh batch
+APM_D void chain_first_proposal_warp(const DevState & L, int g, double * draws, u64 & draw_base, int K, int lane) {
+	const int n = L.n_par;
+	draw_base = L.rng_ctr[g];
+	chain_draw_batch(L, g, draw_base, K, lane, draws);
+	__syncwarp();
+	if (lane < n) {
+		const double x = L.params[(size_t) g * n + lane];
+		double v = x + draws[lane];
+		if (v > L.pmax[lane] || v < L.pmin[lane])
+			v = propose_coordinate(L, g, draw_base, lane, x, L.steps[(size_t) g * n + lane]);
+		L.prop[(size_t) g * n + lane] = v;
+	}
+	if (lane == 0)
+		L.pend[g] = n;
+	__syncwarp();
+}
+
+// markov_chain_step's second half for the pending full step (sum valid on lane 0) and, if
+// propose_next, the next step's proposal; the accept draw and the first-attempt jumps come
+// from the batch, which is refilled when used up
+template<class M>
+APM_D void chain_step_tail_warp(const DevState & L, int g, double sum, double * draws, u64 & draw_base, int K,
+		bool propose_next, int lane) {
+	const int n = L.n_par;
+	const u64 ctr = L.rng_ctr[g];
+	chain_finalize_warp<M>(L, g, sum, draws + (size_t) (ctr - draw_base) * (n + 1) + n, lane);
+	if (!propose_next)
+		return;
+	if (ctr + 1 >= draw_base + (u64) K) {
+		draw_base = ctr + 1;
+		chain_draw_batch(L, g, draw_base, K, lane, draws);
+		__syncwarp();
+	}
+	if (lane < n) {
+		const double x = L.params[(size_t) g * n + lane];
+		double v = x + draws[(size_t) (ctr + 1 - draw_base) * (n + 1) + lane];
+		if (v > L.pmax[lane] || v < L.pmin[lane])
+			v = propose_coordinate(L, g, ctr + 1, lane, x, L.steps[(size_t) g * n + lane]);
+		L.prop[(size_t) g * n + lane] = v;
+	}
+	if (lane == 0)
+		L.pend[g] = n;
+	__syncwarp();
+}
+
 // adapt() as compiled with -DADAPT (reference src/parallel_tempering.c:282-302): once per
 // round, before the swap, every chain nudges all its step widths by 1 % from the sums of its
 // per-parameter accept / reject counters (accepts / REJECTS, as coded: SURVEY App. D 7)

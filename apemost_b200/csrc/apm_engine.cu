@@ -743,7 +743,8 @@ static int choose_path(apm_gpu * h, int * path, bool for_run = false) {
 	if (has_data < 0)
 		return has_data;
 	const long long n_slots = has_data ? h->n_rows * (model_row_w(h, h->cfg.model_id) / 2) : 0; // 16-byte units
-	const size_t need = fused_table_bytes(n_slots) + fused_state_bytes(h->cfg.n_beta, h->cfg.n_par);
+	const size_t need = fused_table_bytes(n_slots) + fused_state_bytes(h->cfg.n_beta, h->cfg.n_par)
+			+ fused_draws_bytes(h->cfg.n_beta);
 	const bool fits = need <= FUSED_SMEM_LIMIT && (!has_data || h->n_rows < (1ll << 24));
 	const bool rows_ok = !has_data || h->n_rows < (1ll << 24);
 	const int cl = for_run && rows_ok ? cluster_size_for(h, has_data != 0) : 0;
@@ -794,7 +795,7 @@ static void fused_geometry(const apm_gpu * h, bool has_data, int * threads, size
 		*threads = std::min(FUSED_MAX_WARPS * 32, 32 * ((h->cfg.n_beta + 31) / 32));
 	}
 	*smem = fused_table_bytes(has_data ? h->n_rows * (model_row_w(const_cast<apm_gpu *>(h), h->cfg.model_id) / 2) : 0)
-			+ fused_state_bytes(h->cfg.n_beta, h->cfg.n_par);
+			+ fused_state_bytes(h->cfg.n_beta, h->cfg.n_par) + fused_draws_bytes(h->cfg.n_beta);
 	memset(a, 0, sizeof(*a));
 	a->data = has_data ? h->d_data : nullptr;
 	a->n_rows = has_data ? (int) h->n_rows : 0;

@@ -474,6 +474,10 @@ __host__ __device__ inline size_t fused_state_bytes(int n_beta, int n_par) {
 	return (per_chain * n_beta + 8 /* swap_round */ + 15) & ~(size_t) 15;
 }
 // (n_slots = table rows x ROW_W / 2: 16-byte units)
+// fused_run_kernel: per chain a batch of random draws (32 doubles) and its base counter
+__host__ __device__ inline size_t fused_draws_bytes(int n_beta) {
+	return (size_t) n_beta * (32 * sizeof(double) + sizeof(unsigned long long));
+}
 __host__ __device__ inline size_t fused_table_bytes(long long n_slots) {
 	return (((size_t) n_slots * 16 + 127) & ~(size_t) 127) + 16 /* mbarrier */;
 }
@@ -657,21 +661,32 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_run_kernel(cons
 	const double xub = M::HAS_DATA ? *a.xabsmax : 0.0;
 	long long step = 0;
 	if (M::HAS_DATA) {
-		for (int k = warp; k < nb; k += n_warps)
-			chain_propose_warp(L, k, n, lane);
+		// per chain: a batch of K steps' random draws (lane-parallel, chain_draw_batch) and its base counter
+		const int K = 32 / (n + 1);
+		double * draws = reinterpret_cast<double *>(fused_smem + fused_table_bytes((long long) a.n_rows * (M::ROW_W / 2))
+				+ fused_state_bytes(nb, n));
+		u64 * draw_base = reinterpret_cast<u64 *>(draws + (size_t) nb * 32);
 		for (long long round = 0; round < a.n_rounds; round++) {
+			for (int k = warp; k < nb; k += n_warps) {
+				u64 base;
+				chain_first_proposal_warp(L, k, draws + (size_t) k * 32, base, K, lane);
+				if (lane == 0)
+					draw_base[k] = base;
+			}
+			__syncwarp();
 			for (int sub = 0; sub < a.n_swap; sub++, step++) {
 				const bool last_of_round = sub + 1 == a.n_swap;
 				for (int k = warp; k < nb; k += n_warps) {
 					const double sum = fused_loglik<M>(L, k, sdata, a.n_rows, xub, lane);
-					chain_finalize_warp<M>(L, k, M::sum0(L.prop + (size_t) k * n) + sum, nullptr, lane);
+					u64 base = draw_base[k];
+					chain_step_tail_warp<M>(L, k, M::sum0(L.prop + (size_t) k * n) + sum, draws + (size_t) k * 32, base, K,
+							!last_of_round, lane);
+					if (lane == 0)
+						draw_base[k] = base;
 					chain_record_warp(L, k, step, lane);
-					if (!last_of_round)
-						chain_propose_warp(L, k, n, lane);
 				}
 			}
-			// adapt (if compiled in), tempering_interaction for this ensemble, then the
-			// proposals of the next round
+			// adapt (if compiled in), tempering_interaction for this ensemble
 			__syncthreads();
 			if (L.adapt)
 				for (int k = threadIdx.x; k < nb; k += blockDim.x)
@@ -680,9 +695,6 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_run_kernel(cons
 			if (threadIdx.x == 0)
 				ensemble_swap(L, 0);
 			__syncthreads();
-			if (round + 1 < a.n_rounds)
-				for (int k = warp; k < nb; k += n_warps)
-					chain_propose_warp(L, k, n, lane);
 		}
 	} else {
 		for (int k = threadIdx.x; k < nb; k += blockDim.x)
@@ -1150,19 +1162,9 @@ __global__ void __launch_bounds__(GRID_THREADS, 1) grid_run_kernel(const DevStat
 		u64 draw_base = 0;
 		if (owner) {
 			const DevState & L = L_own[warp];
-			draw_base = L.rng_ctr[0];
-			chain_draw_batch(L, 0, draw_base, K, lane, my_draws);
-			__syncwarp();
-			if (lane < n) {
-				const double x = L.params[lane];
-				double v = x + my_draws[lane];
-				if (v > L.pmax[lane] || v < L.pmin[lane])
-					v = propose_coordinate(L, 0, draw_base, lane, x, L.steps[lane]);
-				L.prop[lane] = v;
-				a.props[(size_t) my_chain * n + lane] = v;
-			}
-			if (lane == 0)
-				L.pend[0] = n;
+			chain_first_proposal_warp(L, 0, my_draws, draw_base, K, lane);
+			if (lane < n)
+				a.props[(size_t) my_chain * n + lane] = L.prop[lane];
 		}
 		__syncthreads();
 		grid.sync();
@@ -1187,26 +1189,9 @@ __global__ void __launch_bounds__(GRID_THREADS, 1) grid_run_kernel(const DevStat
 				for (int k = lane; k < G; k += 32)
 					sum += __ldcg(a.partials + (size_t) my_chain * G + k);
 				sum = warp_sum(sum);
-				const u64 ctr = L.rng_ctr[0];
-				const double * logu = my_draws + (size_t) (ctr - draw_base) * (n + 1) + n;
-				chain_finalize_warp<M>(L, 0, M::sum0(L.prop) + sum, logu, lane);
-				if (sub + 1 < a.n_swap) {
-					if (ctr + 1 >= draw_base + (u64) K) { // the batch is used up: draw the next K steps
-						draw_base = ctr + 1;
-						chain_draw_batch(L, 0, draw_base, K, lane, my_draws);
-						__syncwarp();
-					}
-					if (lane < n) {
-						const double x = L.params[lane];
-						double v = x + my_draws[(size_t) (ctr + 1 - draw_base) * (n + 1) + lane];
-						if (v > L.pmax[lane] || v < L.pmin[lane])
-							v = propose_coordinate(L, 0, ctr + 1, lane, x, L.steps[lane]);
-						L.prop[lane] = v;
-						a.props[(size_t) my_chain * n + lane] = v;
-					}
-					if (lane == 0)
-						L.pend[0] = n;
-				}
+				chain_step_tail_warp<M>(L, 0, M::sum0(L.prop) + sum, my_draws, draw_base, K, sub + 1 < a.n_swap, lane);
+				if (sub + 1 < a.n_swap && lane < n)
+					a.props[(size_t) my_chain * n + lane] = L.prop[lane];
 			}
 			__syncthreads();
 			grid.sync();
