@@ -311,6 +311,15 @@ void apm_session_calc_model(apm_session * s, const int * which, int n) {
 	free(p); free(b); free(prob); free(prior);
 }
 
+/* APM_HOST_TIMING=1: where the wall time of a phase goes, on stderr */
+static double wall_s(void) {
+	struct timespec t;
+	clock_gettime(CLOCK_MONOTONIC, &t);
+	return t.tv_sec + 1e-9 * t.tv_nsec;
+}
+#define TIMING_MARK(what) do { if (timing) { const double t_now = wall_s(); \
+		fprintf(stderr, "[timing] %-28s %8.3f s\n", what, t_now - t_mark); t_mark = t_now; } } while (0)
+
 /* markov_chain_calibrate for the selected chains, all at once on the device.  On failure:
  * the reference's message and exit code (src/markov_chain_calibrate.c:1104-1110,1169-1174) */
 static void calibrate_selected(apm_session * s, const unsigned char * select, int skip,
@@ -421,6 +430,8 @@ static void place_chain(mcmc * c, const mcmc * c0, double beta, const gsl_vector
 }
 
 void calibrate_rest(void) {
+	const int timing = getenv("APM_HOST_TIMING") != NULL;
+	double t_mark = wall_s();
 	apm_session * s = apm_session_open();
 	const int n_beta = s->n_beta, n_ens = s->n_ens;
 	gsl_vector ** factors = (gsl_vector **) calloc(n_ens, sizeof(gsl_vector *));
@@ -445,6 +456,7 @@ void calibrate_rest(void) {
 	}
 	printf("Calibrating chains\n");
 	fflush(stdout);
+	TIMING_MARK("start-up (files, CUDA, upload)");
 
 	if (n_beta > 1) {
 		/* the second chain tells how step widths really scale with beta */
@@ -462,6 +474,7 @@ void calibrate_rest(void) {
 		dump_vectorln(get_steps(s->chains[1]));
 		fflush(stdout);
 		calibrate_selected(s, select, 0, NULL, NULL);
+		TIMING_MARK("calibrating the second chain");
 		apm_session_pull(s, 0, s->n_chains);
 		for (e = 0; e < n_ens; e++) {
 			mcmc ** c = apm_ensemble(s, e);
@@ -498,6 +511,7 @@ void calibrate_rest(void) {
 		apm_session_push(s, 0, s->n_chains);
 		apm_session_calc_model(s, which, n);
 		calibrate_selected(s, select, skip, &rows, &n_rows);
+		TIMING_MARK("calibrating chains 1 .. n-1");
 		apm_session_pull(s, 0, s->n_chains);
 	}
 	printf("all chains calibrated.\n");
@@ -515,7 +529,9 @@ void calibrate_rest(void) {
 	}
 	apm_set_output_dir(-1);
 	free(rows); free(select); free(which); free(factors); free(beta_0);
+	TIMING_MARK("writing the files");
 	apm_session_close(s);
+	TIMING_MARK("engine shutdown");
 }
 
 /* ------------------------------------------------------------------ run
@@ -706,15 +722,6 @@ static void write_run_statistics(apm_session * s) {
 	apm_set_output_dir(-1);
 	free(cnt); free(sdl); free(sp); free(sp2);
 }
-
-/* APM_HOST_TIMING=1: where the wall time of `run` goes, on stderr */
-static double wall_s(void) {
-	struct timespec t;
-	clock_gettime(CLOCK_MONOTONIC, &t);
-	return t.tv_sec + 1e-9 * t.tv_nsec;
-}
-#define TIMING_MARK(what) do { if (timing) { const double t_now = wall_s(); \
-		fprintf(stderr, "[timing] %-28s %8.3f s\n", what, t_now - t_mark); t_mark = t_now; } } while (0)
 
 void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 	const int timing = getenv("APM_HOST_TIMING") != NULL;

@@ -18,6 +18,7 @@ for phase in calibrate_first calibrate_rest run analyse; do
 done
 s=$(date +%s%N); GSL_RNG_SEED=1 OMP_NUM_THREADS=1 ./simplesin.exe run > run1.log 2>&1; e=$(date +%s%N)
 echo "run (OMP_NUM_THREADS=1: dump files formatted by one thread): $(( (e - s) / 1000000 )) ms"
+GSL_RNG_SEED=1 APM_HOST_TIMING=1 ./simplesin.exe calibrate_rest 2>&1 >/dev/null | grep timing || true
 GSL_RNG_SEED=1 APM_HOST_TIMING=1 ./simplesin.exe run 2>&1 >/dev/null | grep timing || true
 echo "chain-steps: $((ITER * 20)); dump bytes: $(cat *.dump | wc -c)"
 grep -a -o "Model probability.*" analyse.log || true
