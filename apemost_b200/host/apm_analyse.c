@@ -64,25 +64,29 @@ static double integrate_over_beta(mcmc ** chains, const double * sums, unsigned 
 }
 
 static int evidence_from_dumps(mcmc ** chains, unsigned int n_beta, double * result) {
+	/* the files are parsed side by side, one thread per file (fscanf is what `analyse` spends
+	 * its time in); every file's sum is accumulated in file order, like the reference's */
 	double * sums = (double *) calloc(n_beta, sizeof(double));
-	unsigned int i;
-	char name[64];
-	for (i = 0; i < n_beta; i++) {
+	int * status = (int *) calloc(n_beta, sizeof(int)); /* 1 = not found, 2 = empty */
+	int i, failed = 0;
+	for (i = 0; i < (int) n_beta; i++)
+		printf("reading probabilities of chain %d\r", i);
+	fflush(stdout);
+#pragma omp parallel for schedule(dynamic, 1)
+	for (i = 0; i < (int) n_beta; i++) {
 		unsigned long n = 0;
-		double w, v;
+		double w, v, sum = 0;
+		char name[64];
 		FILE * f;
 		snprintf(name, sizeof(name), "prob-chain%d.dump", i);
-		printf("reading probabilities of chain %d\r", i);
-		fflush(stdout);
 		f = fopen(apm_out_path(name), "r");
 		if (f == NULL) {
-			fprintf(stderr, "calculating data probability failed: file %s not found\n", name);
-			free(sums);
-			return 1;
+			status[i] = 1;
+			continue;
 		}
 		while (!feof(f)) {
 			if (fscanf(f, "%le\t%le", &w, &v) == 2) {
-				sums[i] += v;
+				sum += v;
 				n++;
 			} else if (!feof(f)) {
 				int c = fgetc(f); /* skip what cannot be parsed */
@@ -91,15 +95,23 @@ static int evidence_from_dumps(mcmc ** chains, unsigned int n_beta, double * res
 		}
 		fclose(f);
 		if (n == 0) {
-			fprintf(stderr, "calculating data probability failed: no data points found in %s\n", name);
-			free(sums);
-			return 1;
+			status[i] = 2;
+			continue;
 		}
-		sums[i] = sums[i] / get_beta(chains[i]) / n;
+		sums[i] = sum / get_beta(chains[i]) / n;
 	}
-	*result = integrate_over_beta(chains, sums, n_beta);
+	for (i = 0; i < (int) n_beta && !failed; i++) {
+		if (status[i] == 1)
+			fprintf(stderr, "calculating data probability failed: file prob-chain%d.dump not found\n", i);
+		else if (status[i] == 2)
+			fprintf(stderr, "calculating data probability failed: no data points found in prob-chain%d.dump\n", i);
+		failed = status[i] != 0;
+	}
+	if (!failed)
+		*result = integrate_over_beta(chains, sums, n_beta);
 	free(sums);
-	return 0;
+	free(status);
+	return failed;
 }
 
 static int evidence_from_accumulators(mcmc ** chains, unsigned int n_beta, double * result) {
@@ -214,7 +226,11 @@ static double batch_means_error(const double mean, const char * filename, unsign
 	return sqrt(errorsum / nbatches);
 }
 
-static void marginal_distribution(mcmc ** chains, unsigned int n_beta, unsigned int param) {
+/* (called for all parameters side by side: what it has to say goes to `report`, printed in
+ * parameter order by the caller) */
+static void marginal_distribution(mcmc ** chains, unsigned int n_beta, unsigned int param, char * report,
+		size_t report_size) {
+	size_t used = 0;
 	const char * paramname = get_params_descr(chains[0])[param];
 	double lo = get_params_min_for(chains[0], param), hi = get_params_max_for(chains[0], param);
 	char in_name[APM_PATH_MAX], out_name[APM_PATH_MAX];
@@ -241,8 +257,6 @@ static void marginal_distribution(mcmc ** chains, unsigned int n_beta, unsigned 
 	h = uniform_histogram(NBINS, lo, hi);
 	for (i = 0; i < filecount; i++) {
 		snprintf(in_name, sizeof(in_name), "%s-chain-%d.prob.dump", paramname, i);
-		printf("reading values: chain %3d parameter %s   \r", i, paramname);
-		fflush(stdout);
 		fill_from_file(h, apm_out_path(in_name), NULL, NULL);
 	}
 	iter = gsl_histogram_sum(h);
@@ -258,9 +272,12 @@ static void marginal_distribution(mcmc ** chains, unsigned int n_beta, unsigned 
 		double err;
 		snprintf(in_name, sizeof(in_name), "%s-chain-%d.prob.dump", paramname, i);
 		err = batch_means_error(mean, apm_out_path(in_name), (unsigned long) sqrt(iter));
-		printf("mcmc error estimate of %s: %f %s\n", paramname, err, err > sigma * 0.01 ? "** high!" : " (ok)");
+		if (used < report_size)
+			used += snprintf(report + used, report_size - used, "mcmc error estimate of %s: %f %s\n", paramname, err,
+					err > sigma * 0.01 ? "** high!" : " (ok)");
 	}
-	printf("Note: Include a error estimate in your publication!\n");
+	if (used < report_size)
+		snprintf(report + used, report_size - used, "Note: Include a error estimate in your publication!\n");
 	gsl_histogram_free(h);
 }
 
@@ -273,8 +290,20 @@ void analyse_marginal_distributions(void) {
 		apm_set_output_dir(e);
 		chains = chains_from_files();
 		n_par = get_n_par(chains[0]);
-		for (i = 0; i < n_par; i++)
-			marginal_distribution(chains, N_BETA, i);
+		{
+			enum { REPORT = 256 * (N_BETA + 2) };
+			char * reports = (char *) calloc(n_par, REPORT);
+			int p;
+			for (i = 0; i < n_par; i++)
+				printf("reading values: chain %3d parameter %s   \r", 0, get_params_descr(chains[0])[i]);
+			fflush(stdout);
+#pragma omp parallel for schedule(dynamic, 1)
+			for (p = 0; p < (int) n_par; p++)
+				marginal_distribution(chains, N_BETA, (unsigned int) p, reports + (size_t) p * REPORT, REPORT);
+			for (i = 0; i < n_par; i++)
+				fputs(reports + (size_t) i * REPORT, stdout);
+			free(reports);
+		}
 		plot = fopen(apm_out_path("marginal_distributions.gnuplot"), "w");
 		assert(plot != NULL);
 		fprintf(plot, "# set terminal png size %d,%d; set output \"marginal_distributions.png\"\n", 600,

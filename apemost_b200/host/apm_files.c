@@ -29,8 +29,8 @@ void apm_set_output_dir(int ensemble) {
 }
 
 const char * apm_out_path(const char * name) {
-	static char buf[4][APM_PATH_MAX + 64];
-	static int slot = 0;
+	static __thread char buf[4][APM_PATH_MAX + 64]; /* per thread: analyse reads its files in parallel */
+	static __thread int slot = 0;
 	char * b = buf[slot++ & 3];
 	snprintf(b, sizeof(buf[0]), "%s%s", out_dir, name);
 	return b;
