@@ -575,8 +575,18 @@ static void * write_trace(void * arg) {
 		if (k < n_chains) {
 			/* prob-chain<k>.dump: "prob, prob - prior" of every chain */
 			FILE * f = w->prob_files[k];
-			for (r = 0; r < w->n_prob_rows; r++)
-				fprintf(f, "%6e\t%6e\n", w->t_prob[r * n_chains + k], w->t_dl[r * n_chains + k]);
+			char text[64 * 256];
+			size_t used = 0;
+			for (r = 0; r < w->n_prob_rows; r++) {
+				/* "%6e\t%6e\n" (apm_fastfmt.c: the bytes printf would write, several times faster) */
+				used += (size_t) apm_format_prob_line(w->t_prob[r * n_chains + k], w->t_dl[r * n_chains + k], text + used);
+				if (used > sizeof(text) - 64) {
+					fwrite(text, 1, used, f);
+					used = 0;
+				}
+			}
+			if (used > 0)
+				fwrite(text, 1, used, f);
 		} else {
 			/* <name>-chain-<i>.prob.dump: one parameter of one dumped chain */
 			const int i = (k - n_chains) / n_par, j = (k - n_chains) % n_par;

@@ -48,6 +48,10 @@ unsigned int apm_assess_acceptance_rate(apm_session * s, int g, unsigned int par
 void apm_calibrate_alt(apm_session * s, int g, double desired_acceptance_rate, const double max_ar_deviation,
 		const unsigned int iter_limit);
 
+/* apm_fastfmt.c: "%6e" without printf (declines with 0 where it cannot guarantee printf's bytes) */
+int apm_format_e6(double v, char * out);
+int apm_format_prob_line(double prob, double dl, char * buf);
+
 /* apm_files.c */
 void apm_set_output_dir(int ensemble);
 const char * apm_out_path(const char * name);

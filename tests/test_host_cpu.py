@@ -33,7 +33,7 @@ def build_host_over_oracle(name, model, ccflags):
     build_oracle()
     exe = os.path.join(BUILD, f"host_{name}.exe")
     src = [os.path.join(HOST, f) for f in ("apm_main.c", "apm_chainobj.c", "apm_files.c", "apm_phases.c",
-                                           "apm_analyse.c", "apm_calibrate_alt.c")]
+                                           "apm_analyse.c", "apm_calibrate_alt.c", "apm_fastfmt.c")]
     src += [os.path.join(ROOT, "apemost_b200", "compat", "gsl", "gsl_compat.c"),
             os.path.join(ROOT, "tests", "host_shim", "apm_gpu_over_oracle.c")]
     cmd = ["gcc", "-O2", "-std=gnu99", "-fopenmp", "-pthread", "-I", os.path.join(HOST, "include"), "-I", os.path.join(ROOT, "include"),
@@ -90,6 +90,51 @@ def test_host_layer_files_byte_identical_to_reference(name, tmp_path):
     # new: the evidence from the accumulators of `run` agrees with the one from the 7-digit dumps
     m2 = re.search(r"on-device accumulators \(full precision\): (-?[\d.]+)", r.stdout)
     assert m2 and abs(float(m2.group(1)) - float(fx["evidence"])) < 2e-4 * max(1.0, abs(float(fx["evidence"])))
+
+
+def test_fast_e6_formatter_writes_printf_bytes(tmp_path):
+    """apm_fastfmt.c ("%6e" for prob-chain<k>.dump without printf) against snprintf on millions of
+    values: random bit patterns, typical log-likelihoods, scaled integers, values sitting on
+    rounding ties (which it must decline), powers of ten +- a few ulps"""
+    src = tmp_path / "t.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <stdint.h>
+int apm_format_e6(double v, char * out);
+static uint64_t s = 88172645463325252ULL;
+static uint64_t rnd(void) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
+int main(void) {
+	long n = 6000000, i, declined = 0, bad = 0, ties_taken = 0;
+	char a[64], b[64];
+	for (i = 0; i < n; i++) {
+		double v;
+		uint64_t r = rnd();
+		switch (i % 6) {
+		case 0: { union { uint64_t u; double d; } x; x.u = r; v = x.d; break; }
+		case 1: v = -(double) (r % 2000000000) / 1e3 - 700000.0; break;
+		case 2: v = ldexp((double) (r >> 11), (int) (rnd() % 200) - 150); break;
+		case 3: { long k = (long) (r % 9000000) + 1000000; int e = (int) (rnd() % 60) - 30; v = (k + 0.5) * pow(10, e - 6); break; }
+		case 4: v = pow(10, (int) (r % 40) - 20) * (1 + ((double) (int) (rnd() % 7) - 3) * 1.1102230246251565e-16); break;
+		default: v = ((double) (r % 10000000) - 5e6) * 1e-7; break;
+		}
+		int la = apm_format_e6(v, a);
+		if (la == 0) { declined++; continue; }
+		if (i % 6 == 3) ties_taken++;
+		a[la] = 0;
+		snprintf(b, sizeof(b), "%6e", v);
+		if (strcmp(a, b) != 0 && bad++ < 10) printf("MISMATCH %.17g: fast '%s' printf '%s'\n", v, a, b);
+	}
+	printf("%ld values, %ld declined, %ld mismatches\n", n, declined, bad);
+	return bad != 0 || declined > n / 2;
+}
+''')
+    exe = str(tmp_path / "t.exe")
+    subprocess.run(["gcc", "-O2", str(src), os.path.join(HOST, "apm_fastfmt.c"), "-lm", "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
 
 
 def test_host_layer_rejects_bad_params_file(tmp_path):
