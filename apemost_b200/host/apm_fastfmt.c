@@ -91,6 +91,76 @@ int apm_format_e6(double v, char * out) {
 	return len;
 }
 
+/* "%.15e" (DUMP_FORMAT: the parameter dumps, sixteen significant digits): the same idea with much
+ * less room.  The scaled value a * 10^(15 - e10) has up to 54 bits before the point; with an exact
+ * power of ten (10^k is exact in the 64-bit mantissa for 0 <= k <= 27, and 10^-k is then one
+ * correctly rounded division) it carries an absolute error below 0.002, so everything whose
+ * fractional part is not within 0.01 of .5 can be decided; the rest, and decimal exponents
+ * outside [-12, 42], goes to snprintf.  Returns the length written, or 0 to decline. */
+int apm_format_e15(double v, char * out) {
+	static long double pos[28], neg[28];
+	static int ready = 0;
+	double a = fabs(v);
+	int e10, tries, len = 0, k, i;
+	long double m, fl, frac;
+	unsigned long long digits;
+	char d[17];
+	if (!ready) {
+		pos[0] = 1.0L;
+		for (k = 1; k < 28; k++)
+			pos[k] = pos[k - 1] * 10.0L; /* exact */
+		for (k = 0; k < 28; k++)
+			neg[k] = 1.0L / pos[k];      /* correctly rounded */
+		ready = 1;
+	}
+	if (!(a >= 1e-12 && a < 1e42))
+		return 0;
+	e10 = (int) floor(ilogb(a) * 0.30102999566398120);
+	for (tries = 0; tries < 3; tries++) {
+		k = 15 - e10;
+		if (k < -27 || k > 27)
+			return 0;
+		m = k >= 0 ? (long double) a * pos[k] : (long double) a * neg[-k];
+		if (m < 1e15L) {
+			e10--;
+			continue;
+		}
+		if (m >= 1e16L) {
+			e10++;
+			continue;
+		}
+		break;
+	}
+	if (tries == 3)
+		return 0;
+	fl = floorl(m);
+	frac = m - fl;
+	if (frac > 0.49L && frac < 0.51L)
+		return 0;
+	digits = (unsigned long long) fl + (frac > 0.5L ? 1 : 0);
+	if (digits >= 10000000000000000ULL) {
+		digits = 1000000000000000ULL;
+		e10++;
+	}
+	if (v < 0)
+		out[len++] = '-';
+	for (i = 15; i >= 0; i--) {
+		d[i] = (char) ('0' + digits % 10);
+		digits /= 10;
+	}
+	out[len++] = d[0];
+	out[len++] = '.';
+	memcpy(out + len, d + 1, 15);
+	len += 15;
+	out[len++] = 'e';
+	out[len++] = e10 < 0 ? '-' : '+';
+	if (e10 < 0)
+		e10 = -e10;
+	out[len++] = (char) ('0' + e10 / 10);
+	out[len++] = (char) ('0' + e10 % 10);
+	return len;
+}
+
 /* "%6e\t%6e\n" into buf (at least 64 bytes); returns the length */
 int apm_format_prob_line(double prob, double dl, char * buf) {
 	int n = apm_format_e6(prob, buf), m;

@@ -564,38 +564,78 @@ typedef struct {
 	int n_dumped, params_chains;
 } write_job;
 
+enum { WR_BLOCK = 256, WR_LINE = 32, WR_SUPER = 16 }; /* rows per formatting item, bytes reserved per line, items per file and pass */
+
 static void * write_trace(void * arg) {
 	const write_job * w = (const write_job *) arg;
 	const apm_session * s = w->s;
 	const int n_chains = s->n_chains, n_par = s->n_par, n_beta = s->n_beta;
-	int k;
-#pragma omp parallel for schedule(dynamic, 1)
-	for (k = 0; k < n_chains + w->n_dumped * n_par; k++) {
-		long long r;
-		if (k < n_chains) {
-			/* prob-chain<k>.dump: "prob, prob - prior" of every chain */
-			FILE * f = w->prob_files[k];
-			char text[64 * 256];
-			size_t used = 0;
-			for (r = 0; r < w->n_prob_rows; r++) {
-				/* "%6e\t%6e\n" (apm_fastfmt.c: the bytes printf would write, several times faster) */
-				used += (size_t) apm_format_prob_line(w->t_prob[r * n_chains + k], w->t_dl[r * n_chains + k], text + used);
-				if (used > sizeof(text) - 64) {
-					fwrite(text, 1, used, f);
-					used = 0;
+	const int n_files = n_chains + w->n_dumped * n_par;
+	const long long rows_max = w->n_prob_rows > w->n_par_rows ? w->n_prob_rows : w->n_par_rows;
+	static char * text = NULL;   /* [n_files][WR_SUPER][WR_BLOCK * WR_LINE] (only the writer thread uses it) */
+	static int * length = NULL;  /* [n_files][WR_SUPER] */
+	static size_t text_cap = 0;
+	const size_t item_bytes = (size_t) WR_BLOCK * WR_LINE;
+	long long base;
+	if ((size_t) n_files * WR_SUPER * item_bytes > text_cap) {
+		text_cap = (size_t) n_files * WR_SUPER * item_bytes;
+		text = (char *) realloc(text, text_cap);
+		length = (int *) realloc(length, (size_t) n_files * WR_SUPER * sizeof(int));
+		assert(text != NULL && length != NULL);
+	}
+	/* A file's lines must be written in order, but they can be FORMATTED in any order: the rows are
+	 * cut into blocks, (file, block) items are formatted into memory by the whole team -- so the
+	 * few "%.15e" parameter files do not become the critical path -- and then every file's blocks
+	 * are written out in order. */
+	for (base = 0; base < rows_max; base += (long long) WR_SUPER * WR_BLOCK) {
+		int item, k;
+#pragma omp parallel
+		{
+#pragma omp for schedule(dynamic, 1)
+			for (item = 0; item < n_files * WR_SUPER; item++) {
+				const int file = item / WR_SUPER, blk = item % WR_SUPER;
+				const long long r0 = base + (long long) blk * WR_BLOCK;
+				char * out = text + (size_t) item * item_bytes;
+				size_t used = 0;
+				long long r, r1;
+				if (file < n_chains) {
+					/* prob-chain<k>.dump: "%6e\t%6e\n" = prob, prob - prior (apm_fastfmt.c) */
+					r1 = r0 + WR_BLOCK < w->n_prob_rows ? r0 + WR_BLOCK : w->n_prob_rows;
+					for (r = r0; r < r1; r++)
+						used += (size_t) apm_format_prob_line(w->t_prob[r * n_chains + file], w->t_dl[r * n_chains + file],
+								out + used);
+				} else {
+					/* <name>-chain-<i>.prob.dump: one parameter of one dumped chain, "%.15e\n" */
+					const int i = (file - n_chains) / n_par, j = (file - n_chains) % n_par;
+					r1 = r0 + WR_BLOCK < w->n_par_rows ? r0 + WR_BLOCK : w->n_par_rows;
+					for (r = r0; r < r1; r++) {
+						const double v = w->t_par[((size_t) r * w->n_dumped + i) * n_par + j];
+						int len = apm_format_e15(v, out + used); /* DUMP_FORMAT is "%.15e" */
+						if (len == 0)
+							len = snprintf(out + used, WR_LINE - 1, DUMP_FORMAT, v);
+						used += (size_t) len;
+						out[used++] = '\n';
+					}
 				}
+				length[item] = (int) used;
 			}
-			if (used > 0)
-				fwrite(text, 1, used, f);
-		} else {
-			/* <name>-chain-<i>.prob.dump: one parameter of one dumped chain */
-			const int i = (k - n_chains) / n_par, j = (k - n_chains) % n_par;
-			const mcmc * m = w->params_chains == 2 ? s->chains[i] : s->chains[i * n_beta];
-			FILE * f = m->files != NULL ? m->files[j] : NULL;
-			if (f == NULL)
-				continue;
-			for (r = 0; r < w->n_par_rows; r++)
-				fprintf(f, DUMP_FORMAT "\n", w->t_par[((size_t) r * w->n_dumped + i) * n_par + j]);
+#pragma omp for schedule(dynamic, 1)
+			for (k = 0; k < n_files; k++) {
+				FILE * f;
+				int blk;
+				if (k < n_chains) {
+					f = w->prob_files[k];
+				} else {
+					const int i = (k - n_chains) / n_par, j = (k - n_chains) % n_par;
+					const mcmc * m = w->params_chains == 2 ? s->chains[i] : s->chains[i * n_beta];
+					f = m->files != NULL ? m->files[j] : NULL;
+				}
+				if (f == NULL)
+					continue;
+				for (blk = 0; blk < WR_SUPER; blk++)
+					if (length[k * WR_SUPER + blk] > 0)
+						fwrite(text + (size_t) (k * WR_SUPER + blk) * item_bytes, 1, (size_t) length[k * WR_SUPER + blk], f);
+			}
 		}
 	}
 	return NULL;

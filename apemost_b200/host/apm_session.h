@@ -50,6 +50,7 @@ void apm_calibrate_alt(apm_session * s, int g, double desired_acceptance_rate, c
 
 /* apm_fastfmt.c: "%6e" without printf (declines with 0 where it cannot guarantee printf's bytes) */
 int apm_format_e6(double v, char * out);
+int apm_format_e15(double v, char * out); /* "%.15e" */
 int apm_format_prob_line(double prob, double dl, char * buf);
 
 /* apm_files.c */

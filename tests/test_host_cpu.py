@@ -93,7 +93,7 @@ def test_host_layer_files_byte_identical_to_reference(name, tmp_path):
 
 
 def test_fast_e6_formatter_writes_printf_bytes(tmp_path):
-    """apm_fastfmt.c ("%6e" for prob-chain<k>.dump without printf) against snprintf on millions of
+    """apm_fastfmt.c ("%6e" for prob-chain<k>.dump and "%.15e" for the parameter dumps without printf) against snprintf on millions of
     values: random bit patterns, typical log-likelihoods, scaled integers, values sitting on
     rounding ties (which it must decline), powers of ten +- a few ulps"""
     src = tmp_path / "t.c"
@@ -104,6 +104,7 @@ def test_fast_e6_formatter_writes_printf_bytes(tmp_path):
 #include <math.h>
 #include <stdint.h>
 int apm_format_e6(double v, char * out);
+int apm_format_e15(double v, char * out);
 static uint64_t s = 88172645463325252ULL;
 static uint64_t rnd(void) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
 int main(void) {
@@ -125,6 +126,22 @@ int main(void) {
 		if (i % 6 == 3) ties_taken++;
 		a[la] = 0;
 		snprintf(b, sizeof(b), "%6e", v);
+		if (strcmp(a, b) != 0 && bad++ < 10) printf("MISMATCH %.17g: fast '%s' printf '%s'\n", v, a, b);
+	}
+	for (i = 0; i < n; i++) { /* "%.15e": the parameter dumps */
+		double v;
+		uint64_t r = rnd();
+		switch (i % 5) {
+		case 0: { union { uint64_t u; double d; } x; x.u = r; v = x.d; break; }
+		case 1: v = 15.2 + ((double) (r >> 11) / 9007199254740992.0 - 0.5) * 1e-3; break;
+		case 2: v = ldexp((double) (r >> 11), (int) (rnd() % 120) - 90); break;
+		case 3: v = pow(10, (int) (r % 40) - 12) * (1 + ((double) (int) (rnd() % 7) - 3) * 1.1102230246251565e-16); break;
+		default: v = ((double) (r % 1000000007) - 5e8) * 1e-9; break;
+		}
+		int la = apm_format_e15(v, a);
+		if (la == 0) continue;
+		a[la] = 0;
+		snprintf(b, sizeof(b), "%.15e", v);
 		if (strcmp(a, b) != 0 && bad++ < 10) printf("MISMATCH %.17g: fast '%s' printf '%s'\n", v, a, b);
 	}
 	printf("%ld values, %ld declined, %ld mismatches\n", n, declined, bad);
