@@ -337,6 +337,37 @@ def test_run_continues_across_calls(capi, path):
         np.testing.assert_array_equal(outs[0][k], outs[1][k], err_msg=k)
 
 
+@pytest.mark.parametrize("path", PATHS)
+def test_paths_are_bit_reproducible(capi, path):
+    """the same run six times over: every array must come back bit for bit the same (the paths with
+    warp groups, clusters and grid barriers have plenty of places where a missing synchronisation
+    would show up as run-to-run differences; compute-sanitizer is not available on this pool)"""
+    n_rows = 1522 if path in (2, 3) else 40_000
+    data = lightcurve(n_rows, seed=3)
+    n_ens, n_beta = 3, 20
+    n = n_ens * n_beta
+    rng = np.random.default_rng(8)
+    scale = (1e6 / n_rows) ** 0.5
+    params = np.tile([1.3, 7.25, 0.31 * 2 * np.pi, 0.2], (n, 1)) + rng.normal(0, 1e-5, (n, 4)) * scale
+    beta = np.tile(np.linspace(1.0, 0.7, n_beta), n_ens)
+    steps = np.tile([7e-4, 3e-7, 1.1e-3, 5e-4], (n, 1)) * scale * beta[:, None] ** -0.5
+    outs = []
+    for rep in range(6):
+        e = capi.Engine("simplesin5", n_ens, n_beta, seed=71, path=path)
+        e.set_data(data)
+        e.set_bounds(SS5_LO, SS5_HI)
+        e.set_chains(0, n, beta=beta, params=params, steps=steps, params_best=params)
+        e.set_adapt(True, 0.5)
+        e.reset_stats()
+        e.run(7, 13, prob_every=1, params_chains=2)
+        outs.append((e.get_chains(), e.read_trace(), e.get_stats()))
+        e.close()
+    for st, tr, ac in outs[1:]:
+        for ref, got in ((outs[0][0], st), (outs[0][1], tr), (outs[0][2], ac)):
+            for k in ref:
+                np.testing.assert_array_equal(ref[k], got[k], err_msg=k)
+
+
 def test_single_chain_ladder_never_swaps(capi):
     data = lightcurve(3000)
     for eng in _pair(capi, "simplesin5", 5, 1, seed=2):
