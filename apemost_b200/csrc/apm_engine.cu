@@ -76,6 +76,8 @@ struct apm_gpu {
 	// row-split plan for n_chains slots
 	int plan_splits = 0, plan_cps = 0;
 	double * d_grid_partials = nullptr, *d_grid_draws = nullptr; // grid path workspaces
+	int * d_grid_active = nullptr;
+	size_t grid_active_cap = 0;
 	size_t grid_partials_cap = 0, grid_draws_cap = 0;
 	size_t partial_cap = 0;
 	unsigned long long * d_xabsmax = nullptr; // bits of max |x| over the table
@@ -187,6 +189,7 @@ static int configure_kernels(apm_gpu * h) {
 	CU(cudaFuncSetAttribute(fused_calibrate_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
 	CU(cudaFuncSetAttribute(cluster_run_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
 	CU(cudaFuncSetAttribute(grid_run_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
+	CU(cudaFuncSetAttribute(grid_calibrate_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
 	return APM_OK;
 }
 
@@ -301,7 +304,7 @@ extern "C" int apm_gpu_destroy(apm_gpu * h) {
 			S.accept, S.reject, S.pacc, S.prej, S.n_iter, S.swapcount, S.rng_ctr, S.swap_round, S.pmin,
 			S.pmax, S.pend, S.partial, S.stat_n, S.stat_sum_dl, S.stat_sum_p, S.stat_sum_p2, S.cal,
 			S.progress, S.progress_n, S.n_active, S.act_idx, S.act_n, h->d_select, h->d_shard_sum,
-			h->d_pack_first, h->d_pack_last, h->d_pack_prev, h->d_pack_next, h->d_grid_partials, h->d_grid_draws,
+			h->d_pack_first, h->d_pack_last, h->d_pack_prev, h->d_pack_next, h->d_grid_partials, h->d_grid_draws, h->d_grid_active,
 			h->d_xabsmax, h->d_data, h->d_tr_prob, h->d_tr_dl, h->d_tr_params };
 	for (void * p : ptrs)
 		if (p)
@@ -726,7 +729,8 @@ static int cluster_size_for(const apm_gpu * h, bool has_data) {
 
 // grid path: rows per CTA (0 = the path does not apply)
 static int grid_slice_rows(const apm_gpu * h, bool has_data) {
-	if (!has_data || h->comm || h->n_chains > GRID_MAX_CHAINS_PER_SM * h->sm_count || h->n_rows < 1)
+	if (!has_data || h->comm || h->n_chains > GRID_MAX_CHAINS_PER_SM * h->sm_count || h->n_chains > GRID_MAX_CHAINS
+			|| h->n_rows < 1)
 		return 0;
 	if (getenv("APM_NO_GRID"))
 		return 0;
@@ -748,12 +752,12 @@ static int choose_path(apm_gpu * h, int * path, bool for_run = false) {
 	const bool fits = need <= FUSED_SMEM_LIMIT && (!has_data || h->n_rows < (1ll << 24));
 	const bool rows_ok = !has_data || h->n_rows < (1ll << 24);
 	const int cl = for_run && rows_ok ? cluster_size_for(h, has_data != 0) : 0;
-	const int gslice = for_run ? grid_slice_rows(h, has_data != 0) : 0;
+	const int gslice = grid_slice_rows(h, has_data != 0);
 	int want = h->cfg.path;
-	if (want == APM_PATH_CLUSTER && !for_run)
-		want = fits ? APM_PATH_FUSED : APM_PATH_TILED; // calibration: chains do not interact, no cluster needed
-	if (want == APM_PATH_GRID && !for_run)
-		want = APM_PATH_TILED;
+	if (want == APM_PATH_CLUSTER && !for_run) // calibration: chains do not interact, no cluster needed
+		want = fits ? APM_PATH_FUSED : APM_PATH_AUTO;
+	if (want == APM_PATH_GRID && !for_run && gslice == 0) // e.g. a data-free model
+		want = APM_PATH_AUTO;
 	if (want == APM_PATH_GRID) {
 		if (gslice == 0)
 			return fail(h, APM_EINVAL, "the grid path needs a data model, at most %d chains, a slice of the table "
@@ -1116,8 +1120,36 @@ static int calibrate_t(apm_gpu * h, const apm_gpu_calib_cfg * cfg, int * status,
 		h->launches++;
 		n_selected = 0; // skips the tiled loop below
 	}
-	// the likelihood kernel walks a compacted list of the chains still calibrating; the
-	// control kernel of step s fills list (s + 1) & 1 and clears list s & 1
+	if (path == APM_PATH_GRID) {
+		if constexpr (M::HAS_DATA) {
+			const int slice = grid_slice_rows(h, true);
+			const int G = h->sm_count;
+			CU(ensure_cap(&h->d_grid_partials, &h->grid_partials_cap, (size_t) h->n_chains * G));
+			CU(ensure_cap(&h->d_grid_draws, &h->grid_draws_cap, (size_t) h->n_chains * h->cfg.n_par));
+			CU(ensure_cap(&h->d_grid_active, &h->grid_active_cap, (size_t) h->n_chains));
+			GridArgs ga;
+			memset(&ga, 0, sizeof(ga));
+			ga.data = h->d_data;
+			ga.n_rows = h->n_rows;
+			ga.xabsmax = reinterpret_cast<const double *>(h->d_xabsmax);
+			ga.partials = h->d_grid_partials;
+			ga.props = h->d_grid_draws;
+			ga.max_slice_rows = slice;
+			const size_t smem = (((size_t) slice * sizeof(Row<M>) + 127) & ~(size_t) 127) + 64
+					+ grid_state_bytes(h->n_chains, h->cfg.n_par);
+			DevState S = h->S;
+			CalibCfgDev cd = a.cal;
+			const unsigned char * sel = h->d_select;
+			int * act = h->d_grid_active;
+			void * args[] = { (void *) &S, (void *) &ga, (void *) &cd, (void *) &sel, (void *) &act };
+			CU(cudaLaunchCooperativeKernel((const void *) grid_calibrate_kernel<M>, dim3((unsigned) G), dim3(GRID_THREADS),
+					args, smem, h->stream));
+			h->launches++;
+		}
+		n_selected = 0;
+	}
+	// (tiled path) the likelihood kernel walks a compacted list of the chains still calibrating;
+	// the control kernel of step s fills list (s + 1) & 1 and clears list s & 1
 	CU(cudaMemsetAsync(h->S.act_n, 0, 2 * sizeof(int), h->stream));
 	if (path == APM_PATH_TILED) {
 		a.flags = ADV_CALIB_BEGIN;

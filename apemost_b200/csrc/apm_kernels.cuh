@@ -1085,6 +1085,7 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) cluster_run_kernel(co
 constexpr int GRID_THREADS = 256, GRID_WARPS = GRID_THREADS / 32;
 constexpr int GRID_MAX_OWNED = 8;                // chains per CTA: one per warp
 constexpr int GRID_MAX_CHAINS_PER_SM = GRID_MAX_OWNED;
+constexpr int GRID_MAX_CHAINS = 2048;
 
 struct GridArgs {
 	const double * data;
@@ -1221,6 +1222,129 @@ __global__ void __launch_bounds__(GRID_THREADS, 1) grid_run_kernel(const DevStat
 		}
 		__syncthreads();
 		grid.sync();
+	}
+}
+
+// markov_chain_calibrate (or apm_gpu_steps) of the selected chains on the grid path: the owners run
+// the calibration state machine of apm_chain.cuh for their chains, chain by chain at its own pace;
+// a chain that is done (or not selected) simply stops publishing proposals.  `active` is a global
+// flag per chain, written by the owner together with the proposal.
+template<class M>
+__global__ void __launch_bounds__(GRID_THREADS, 1) grid_calibrate_kernel(const DevState S, const GridArgs a,
+		const CalibCfgDev cal, const unsigned char * select, int * active) {
+	extern __shared__ __align__(128) unsigned char grid_smem[];
+	namespace cg = cooperative_groups;
+	cg::grid_group grid = cg::this_grid();
+	const int G = gridDim.x, b = blockIdx.x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int n = S.n_par, NC = S.n_chains;
+
+	const long long r0 = a.n_rows * b / G, r1 = a.n_rows * (b + 1) / G;
+	const int n_slice = (int) (r1 - r0);
+	Row<M> * sdata = reinterpret_cast<Row<M> *>(grid_smem);
+	const size_t slice_bytes = (((size_t) a.max_slice_rows * sizeof(Row<M>) + 127) & ~(size_t) 127);
+	uint64_t * bar = reinterpret_cast<uint64_t *>(grid_smem + slice_bytes);
+	if (n_slice > 0) {
+		if (tid == 0) {
+			mbar_init(bar, 1);
+			mbar_fence_init();
+			const uint32_t total = (uint32_t) n_slice * sizeof(Row<M>);
+			mbar_arrive_expect_tx(bar, total);
+			const unsigned char * src = reinterpret_cast<const unsigned char *>(a.data) + (size_t) r0 * sizeof(Row<M>);
+			for (uint32_t off = 0; off < total; off += 32768u)
+				tma_bulk_g2s(reinterpret_cast<unsigned char *>(sdata) + off, src + off, min(32768u, total - off), bar);
+		}
+		__syncthreads();
+		mbar_wait(bar, 0);
+	}
+	double * props = reinterpret_cast<double *>(grid_smem + slice_bytes + 64); // [NC][n]
+	unsigned char * own_mem = reinterpret_cast<unsigned char *>(props + (size_t) NC * n);
+	const size_t own_stride = fused_state_bytes(1, n) + 32 * sizeof(double);
+	__shared__ DevState L_own[GRID_MAX_OWNED];
+	__shared__ unsigned char s_active[GRID_MAX_CHAINS]; // flags of all chains
+	__shared__ int s_any;
+
+	const int my_chain = b + warp * G;
+	const bool owner = my_chain < NC;
+	const double xub = *a.xabsmax;
+	for (int w = 0; w < GRID_WARPS; w++) {
+		const int c = b + w * G;
+		if (c < NC) {
+			const DevState L_tmp = fused_localize_block(S, c / S.n_beta, c % S.n_beta, 1, own_mem + (size_t) w * own_stride);
+			if (tid == 0)
+				L_own[w] = L_tmp;
+			__syncthreads();
+		}
+	}
+	if (owner && lane == 0) {
+		const DevState & L = L_own[warp];
+		L.pend[0] = PEND_NONE;
+		L.cal[0].phase = CAL_IDLE;
+		if (select == nullptr || select[my_chain]) {
+			atomicAdd(L.n_active, 1);
+			cal_begin(L, 0, cal);
+		} else {
+			L.cal[0].status = -1;
+		}
+	}
+	__syncthreads();
+	while (true) {
+		// ---- the owners publish what their chains need evaluated next (if anything)
+		if (owner) {
+			const DevState & L = L_own[warp];
+			const int kind = cal_next_kind(L, 0); // same value in every lane (shared memory)
+			if (kind != PEND_NONE) {
+				chain_propose_warp(L, 0, kind, lane);
+				if (lane < n)
+					a.props[(size_t) my_chain * n + lane] = L.prop[lane];
+			}
+			if (lane == 0)
+				active[my_chain] = kind != PEND_NONE;
+		}
+		__syncthreads();
+		grid.sync();
+		if (tid == 0)
+			s_any = 0;
+		__syncthreads();
+		for (int c = tid; c < NC; c += GRID_THREADS) {
+			const int f = __ldcg(active + c);
+			s_active[c] = (unsigned char) (f != 0);
+			if (f)
+				s_any = 1; // benign race: everybody writes 1
+		}
+		for (int i = tid; i < NC * n; i += GRID_THREADS)
+			props[i] = __ldcg(a.props + i);
+		__syncthreads();
+		if (!s_any)
+			break; // the same decision in every CTA: all read the same flags
+		// ---- the pending proposals on this CTA's slice
+		for (int c = warp; c < NC; c += GRID_WARPS) {
+			if (!s_active[c])
+				continue;
+			const double v = n_slice > 0 ? group_loglik<M>(S, props + (size_t) c * n, sdata, n_slice, xub, lane, 32) : 0.0;
+			if (lane == 0)
+				a.partials[(size_t) c * G + b] = v;
+		}
+		__syncthreads();
+		grid.sync();
+		// ---- the owners: finish the step, advance the chain's calibration
+		if (owner && s_active[my_chain]) {
+			const DevState & L = L_own[warp];
+			double sum = 0.0;
+			for (int k = lane; k < G; k += 32)
+				sum += __ldcg(a.partials + (size_t) my_chain * G + k);
+			sum = warp_sum(sum);
+			chain_finalize_warp<M>(L, 0, M::sum0(L.prop) + sum, nullptr, lane);
+			if (lane == 0)
+				cal_after_step(L, 0, cal);
+			__syncwarp();
+		}
+		__syncthreads();
+	}
+	for (int w = 0; w < GRID_WARPS; w++) {
+		const int c = b + w * G;
+		if (c < NC)
+			fused_writeback_block(S, L_own[w], c / S.n_beta, c % S.n_beta, false);
 	}
 }
 

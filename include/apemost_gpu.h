@@ -80,7 +80,8 @@ extern "C" {
 
 #define APM_PATH_GRID    4  /* mid-size tables (too large for one SM's shared memory, at most 512 chains):
                                one cooperative launch per run, the table partitioned over the shared
-                               memories of all SMs, one grid barrier per step.  apm_gpu_run only */
+                               memories of all SMs, two grid barriers per step; runs, calibration and
+                               apm_gpu_steps */
 
 /* ---- calibration status per chain --------------------------------------- */
 #define APM_CALIB_OK             0
