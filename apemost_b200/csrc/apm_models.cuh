@@ -223,10 +223,26 @@ struct ModelPulseVrot {
 		y += lorentz(q.f2 - freq + 1 * q.vrot, q.lifetime, q.h2);
 		return acc + (log(y) + d / y); // (:61)
 	}
+	// The same row term with ONE division instead of five: y = P / Q over the common denominator
+	// Q = d1 d2 d3 d4, d_k = 1 + t_k^2 (all terms positive: no cancellation), log y + d / y =
+	// -log(Q / P) + d (Q / P).  A few ulps from the reference's sum of quotients, far inside
+	// the 1e-12 parity bound; ~30 % fewer FP64 instructions.  fast_ok keeps Q far from overflow.
 	APM_D static double accum_fast(double acc, const Prep & q, double freq, double d) {
-		return accum(acc, q, freq, d);
+		const double tw = APM_TWO_PI * q.lifetime;
+		const double t1 = (q.f1 - freq) * tw, t2 = (q.f2 - freq + -1 * q.vrot) * tw;
+		const double t3 = (q.f2 - freq) * tw, t4 = (q.f2 - freq + 1 * q.vrot) * tw;
+		const double d1 = fma(t1, t1, 1.0), d2 = fma(t2, t2, 1.0), d3 = fma(t3, t3, 1.0), d4 = fma(t4, t4, 1.0);
+		const double d34 = d3 * d4;
+		const double Q = (d1 * d2) * d34;
+		// P = h1 d2 d3 d4 + h2 d1 (d3 d4 + d2 d4 + d2 d3)
+		const double P = fma(q.h1 * d2, d34, (q.h2 * d1) * fma(d2, d3 + d4, d34));
+		const double r = Q / P; // = 1 / y
+		return acc + fma(d, r, -log(r));
 	}
-	APM_D static bool fast_ok(const Prep &, double) { return true; }
+	APM_D static bool fast_ok(const Prep & q, double xub) {
+		const double t = APM_TWO_PI * fabs(q.lifetime) * (fabs(q.f1) + fabs(q.f2) + fabs(q.vrot) + xub);
+		return t < 1e30 && q.h1 > 0 && q.h2 > 0; // d_k < 1e60, Q < 1e240; positive heights: P > 0
+	}
 	APM_D static double sum0(const double * p) { return p[1]; } // accumulator starts at params[1] (:34)
 	APM_D static double prior(const double * p, int n_par, const double * mc) {
 		const double hmin = mc[0] != 0 ? mc[0] : 1e-6; // HMIN (:8-10)

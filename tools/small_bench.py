@@ -19,11 +19,25 @@ from oracle_binding import Oracle, RNG_PHILOX  # noqa: E402
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def pulse_spectrum(n, seed=4242):
+    """SURVEY 8d's C4 input: n bins on [90, 110], two modes (the second a rotationally split triplet)"""
+    rng = np.random.default_rng(seed)
+    nu = np.linspace(90, 110, n)
+
+    def lor(d, h):
+        return h / (1 + (2 * np.pi * d * 0.5) ** 2)
+    y = lor(98 - nu, 5.0) + lor(103 - nu, 3.0) + lor(103 - nu - 0.4, 3.0) + lor(103 - nu + 0.4, 3.0) + 0.05
+    return np.stack([nu, y * rng.exponential(1.0, n)], axis=1)
+
+
 def case(name, n_ens, n_beta=None):
+    name, _, rows_override = name.partition(":")
     fx = json.load(open(os.path.join(GOLDEN, name + ".json")))
     rows = [tuple(r) for r in fx["rows"]]
     data = (np.loadtxt(os.path.join(GOLDEN, fx["data_file"])) if fx["data_file"]
             else np.array(fx["data"], dtype=float).reshape(-1, 2))
+    if rows_override:
+        data = pulse_spectrum(int(rows_override))
     nb0 = fx["config"]["N_BETA"]
     cal = np.array(fx["phases"]["calibrate_rest"].split(), dtype=float).reshape(nb0, 1 + 2 * len(rows))
     n_beta = n_beta or nb0
@@ -45,14 +59,21 @@ def time_engine(eng, rows, data, beta, steps, params, n_ens, rounds, n_swap):
 
 
 def main():
+    if os.environ.get("APM_LIB"):  # a variant build
+        capi._lib = capi.load_library(os.environ["APM_LIB"])
     out = {}
+    only = os.environ.get("SMALL_BENCH_ONLY", "")
     for label, name, n_ens, n_beta in [("C1 simplesin testlc.dat 1x20", "c1_phases", 1, 20),
                                        ("C1 simplesin testlc.dat 8x20", "c1_phases", 8, 20),
                                        ("C1 simplesin testlc.dat 64x20", "c1_phases", 64, 20),
                                        ("C2 normal 1x64", "c2_phases", 1, 64),
                                        ("C2 normal 64x64", "c2_phases", 64, 64),
                                        ("C4 pulse_vrot 200 rows 1x20", "c4_phases", 1, 20),
-                                       ("C4 pulse_vrot 200 rows 64x20", "c4_phases", 64, 20)]:
+                                       ("C4 pulse_vrot 200 rows 64x20", "c4_phases", 64, 20),
+                                       ("C4 pulse_vrot 2000 rows 1x20", "c4_phases:2000", 1, 20),
+                                       ("C4 pulse_vrot 2000 rows 8x20", "c4_phases:2000", 8, 20)]:
+        if only and only not in label:
+            continue
         model, rows, data, beta, steps, params = case(name, n_ens, n_beta)
         n_swap = max(1, 2000 // n_beta)
         res = {}
