@@ -287,10 +287,36 @@ struct ModelPulse {
 		}
 		return acc + (log(y) + d / y);
 	}
+	// one division for any number of modes: P_j / Q_j = sum_{i <= j} h_i / d_i by the recurrence
+	// P <- P d_j + h_j Q, Q <- Q d_j (all terms positive), then -log(Q / P) + d (Q / P) as in pulse_vrot
 	APM_D static double accum_fast(double acc, const Prep & q, double freq, double d) {
-		return accum(acc, q, freq, d);
+		const double tw = APM_TWO_PI * q.lifetime;
+		double P = 0.0, Q = 1.0;
+#pragma unroll
+		for (int j = 0; j < (APM_MAX_PAR - 2) / 2; j++) {
+			if (j < q.n_modes) {
+				const double t = (q.f[j] - freq) * tw;
+				const double dj = fma(t, t, 1.0);
+				P = fma(P, dj, q.h[j] * Q);
+				Q = Q * dj;
+			}
+		}
+		const double r = Q / P;
+		return acc + fma(d, r, -log(r));
 	}
-	APM_D static bool fast_ok(const Prep &, double) { return true; }
+	APM_D static bool fast_ok(const Prep & q, double xub) {
+		double fmax = 0.0;
+		bool positive = true;
+#pragma unroll
+		for (int j = 0; j < (APM_MAX_PAR - 2) / 2; j++) {
+			if (j < q.n_modes) {
+				fmax = fmax > fabs(q.f[j]) ? fmax : fabs(q.f[j]);
+				positive = positive && q.h[j] > 0 && q.h[j] < 1e30;
+			}
+		}
+		// d_j < 1e38: Q < 1e266, P < 7e296
+		return APM_TWO_PI * fabs(q.lifetime) * (fmax + xub) < 1e19 && positive;
+	}
 	APM_D static double sum0(const double * p) { return p[1]; }
 	APM_D static double prior(const double * p, int n_par, const double * mc) {
 		const double hmin = mc[0] != 0 ? mc[0] : 1e-6;

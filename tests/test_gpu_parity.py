@@ -284,6 +284,57 @@ def test_bernoulli_rows_of_four_doubles(capi, path, n_cols, n_rows):
     assert st_g["swapcount"].sum() > 0 and 0.05 < st_g["accept"].sum() / (n * 100) < 0.95
 
 
+def _pulse_spectrum(n_bins, modes, lifetime, seed):
+    rng = np.random.default_rng(seed)
+    nu = np.linspace(90.0, 110.0, n_bins)
+    y = sum(h / (1 + (2 * np.pi * (f - nu) * lifetime) ** 2) for f, h in modes)
+    return np.stack([nu, y * rng.exponential(1.0, n_bins)], axis=1)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("n_modes", [1, 2, 3, 5, 7])
+def test_pulse_any_number_of_modes(capi, path, n_modes):
+    """apps/pulse.c:12-56 takes n_par = 2 + 2k for k modes.  The device row term puts the k Lorentzians
+    over one denominator (ModelPulse::accum_fast, one division per bin instead of k + 1): calc_model
+    to 1e-12 and whole runs against the oracle's sum of quotients for k = 1 .. 7 on every kernel path;
+    a non-positive height (the common-denominator form is not used then) takes the reference-order
+    fallback and must agree as well"""
+    modes = [(92.0 + 2.4 * j, 5.0 - 0.5 * j) for j in range(n_modes)]
+    data = _pulse_spectrum(600, modes, 0.5, 11 * n_modes)
+    n_ens, n_beta, n_par = 2, 6, 2 + 2 * n_modes
+    n = n_ens * n_beta
+    truth = np.array([0.5, 0.0] + [v for m in modes for v in m])
+    lo = np.array([0.05, -1.0] + [v for f, h in modes for v in (f - 1.0, 0.0)])
+    hi = np.array([2.0, 1.0] + [v for f, h in modes for v in (f + 1.0, 20.0)])
+    rng = np.random.default_rng(n_modes)
+    params = np.clip(truth * (1 + rng.normal(0, 0.02, (n, n_par))), lo, hi)
+    params[:, 1] = rng.normal(0, 0.1, n)
+    beta = np.tile(np.linspace(1.0, 0.4, n_beta), n_ens)
+    steps = np.tile(0.01 * (hi - lo), (n, 1)) * beta[:, None] ** -0.5
+    edge = params[:4].copy()
+    edge[0, 3] = 0.0       # h_1 = 0: y loses a term
+    edge[1, 3] = -1e-3     # a negative height
+    edge[2, 0] = 1e12      # very long lifetime: d_j ~ 1e27
+    edge[3, 3] = 1e35      # beyond fast_ok's height bound
+    res = []
+    for eng in _pair(capi, "pulse", n_ens, n_beta, n_par=n_par, seed=71, path=path):
+        eng.set_data(data)
+        eng.set_bounds(lo, hi)
+        e_prob, e_prior = eng.eval(edge, beta[:4])
+        prob, prior = eng.eval(params, beta)
+        eng.set_chains(0, n, beta=beta, params=params, steps=steps, params_best=params, prob=prob, prior=prior)
+        eng.run(5, 20, prob_every=1, params_chains=1)
+        res.append((prob, prior, e_prob, e_prior, eng.read_trace(), eng.get_chains()))
+    (p_g, pr_g, ep_g, epr_g, tr_g, st_g), (p_c, pr_c, ep_c, epr_c, tr_c, st_c) = res
+    np.testing.assert_allclose(p_g, p_c, rtol=RTOL_LOGLIK)
+    np.testing.assert_allclose(pr_g, pr_c, rtol=RTOL_LOGLIK, atol=1e-300)
+    np.testing.assert_allclose(ep_g, ep_c, rtol=RTOL_LOGLIK, equal_nan=True)
+    np.testing.assert_allclose(epr_g, epr_c, rtol=RTOL_LOGLIK, equal_nan=True)
+    _compare_state(st_g, st_c)
+    np.testing.assert_allclose(tr_g["prob"], tr_c["prob"], rtol=RTOL_TRAJ)
+    assert 0.02 < st_g["accept"].sum() / (n * 100) < 0.98
+
+
 @pytest.mark.parametrize("path", PATHS)
 def test_adapt_trajectory_equals_oracle(capi, path):
     """-DADAPT (reference src/parallel_tempering.c:282-302): once the counter sums reach 20000 the

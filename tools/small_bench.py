@@ -30,8 +30,27 @@ def pulse_spectrum(n, seed=4242):
     return np.stack([nu, y * rng.exponential(1.0, n)], axis=1)
 
 
+def pulse_modes_case(n_modes, n_bins, n_beta):
+    """apps/pulse.c with n_modes Lorentzians (n_par = 2 + 2 n_modes) on n_bins bins; no fixture:
+    a fixed ladder and step widths that give a mid-range acceptance rate"""
+    modes = [(92.0 + 2.4 * j, 5.0 - 0.5 * j) for j in range(n_modes)]
+    rng = np.random.default_rng(99)
+    nu = np.linspace(90, 110, n_bins)
+    y = sum(h / (1 + (2 * np.pi * (f - nu) * 0.5) ** 2) for f, h in modes)
+    data = np.stack([nu, y * rng.exponential(1.0, n_bins)], axis=1)
+    rows = [(0.5, 0.05, 2.0, "lifetime", 0.01), (0.0, -1.0, 1.0, "offset", 0.01)]
+    for j, (f, h) in enumerate(modes):
+        rows += [(f, f - 1.0, f + 1.0, "f%d" % j, 0.005), (h, 0.0, 20.0, "h%d" % j, 0.05)]
+    beta = pt_flow.chebyshev_ladder(n_beta, 0.05)
+    steps = np.array([r[4] for r in rows])[None, :] * beta[:, None] ** -0.5
+    params = np.tile(np.array([r[0] for r in rows]), (n_beta, 1))
+    return "pulse", rows, data, beta, steps, params
+
+
 def case(name, n_ens, n_beta=None):
     name, _, rows_override = name.partition(":")
+    if name.startswith("pulse_modes"):
+        return pulse_modes_case(int(name[len("pulse_modes"):]), int(rows_override), n_beta)
     fx = json.load(open(os.path.join(GOLDEN, name + ".json")))
     rows = [tuple(r) for r in fx["rows"]]
     data = (np.loadtxt(os.path.join(GOLDEN, fx["data_file"])) if fx["data_file"]
@@ -71,7 +90,10 @@ def main():
                                        ("C4 pulse_vrot 200 rows 1x20", "c4_phases", 1, 20),
                                        ("C4 pulse_vrot 200 rows 64x20", "c4_phases", 64, 20),
                                        ("C4 pulse_vrot 2000 rows 1x20", "c4_phases:2000", 1, 20),
-                                       ("C4 pulse_vrot 2000 rows 8x20", "c4_phases:2000", 8, 20)]:
+                                       ("C4 pulse_vrot 2000 rows 8x20", "c4_phases:2000", 8, 20),
+                                       ("pulse 3 modes 2000 rows 1x20", "pulse_modes3:2000", 1, 20),
+                                       ("pulse 3 modes 2000 rows 8x20", "pulse_modes3:2000", 8, 20),
+                                       ("pulse 7 modes 200 rows 64x20", "pulse_modes7:200", 64, 20)]:
         if only and only not in label:
             continue
         model, rows, data, beta, steps, params = case(name, n_ens, n_beta)
