@@ -145,14 +145,16 @@ REF_EXE = os.path.join(ROOT, "oracle", "_ref", "simplesin5fix_b64_it%d.exe")
 REF_ITERS = (31, 124)   # 1 and 4 rounds of n_swap = 31 iterations (oracle/Makefile refbench)
 
 
-def reference_exe_rate(data, n_threads=None):
+def reference_exe_rate(data, n_threads=None, repeats=1, warm=0, budget_s=150.0):
     """chain-steps/s of the REFERENCE ITSELF on this box's cores: its own engine (src/*.c, OpenMP
     over the chains of one 64-rung ladder) with apps/simplesin5.c (two stale lines fixed by sed,
     SURVEY.md D1), built in the container as oracle/_ref/simplesin5fix_b64_it<N>.exe.  `run` is
     executed from the same calibration_results our arm starts from, for 31 and for 124 iterations;
     the difference removes process start-up and the parsing of the 1M-row data file.  Steps are
     counted from the lines of prob-chain<k>.dump, because the OpenMP build's shared loop counter
-    makes it execute fewer steps than it reports.  None if the binaries are absent."""
+    makes it execute fewer steps than it reports.  The pair of runs is one "step" of
+    the reference arm: `warm` untimed pairs, then up to `repeats` timed ones (fewer if `budget_s`
+    runs out), the rate being total steps over total time.  None if the binaries are absent."""
     import shutil
     import tempfile
     exes = [REF_EXE % it for it in REF_ITERS]
@@ -173,28 +175,41 @@ def reference_exe_rate(data, n_threads=None):
                 vals = [st["beta"][k], *st["steps"][k], *st["params"][k]]
                 f.write("\t".join("%.15e" % v for v in vals) + "\n")
         env = dict(os.environ, OMP_NUM_THREADS=str(cores), GSL_RNG_SEED="1")
-        meas = []
-        for exe in exes:
-            for fn in os.listdir(wd):
-                if fn.endswith(".dump"):
-                    os.remove(os.path.join(wd, fn))
-            t0 = time.perf_counter()
-            r = subprocess.run([exe, "run"], cwd=wd, env=env, capture_output=True, text=True)
-            dt = time.perf_counter() - t0
-            if r.returncode != 0:
+        def pair():
+            meas = []
+            for exe in exes:
+                for fn in os.listdir(wd):
+                    if fn.endswith(".dump"):
+                        os.remove(os.path.join(wd, fn))
+                t0 = time.perf_counter()
+                r = subprocess.run([exe, "run"], cwd=wd, env=env, capture_output=True, text=True)
+                dt = time.perf_counter() - t0
+                if r.returncode != 0:
+                    return None
+                lines = 0
+                for k in range(N_BETA):
+                    with open(os.path.join(wd, "prob-chain%d.dump" % k), "rb") as f:
+                        lines += sum(1 for _ in f)
+                meas.append((dt, lines))
+            (t_a, n_a), (t_b, n_b) = meas
+            return n_b - n_a, t_b - t_a
+
+        t_start = time.perf_counter()
+        n_sum, t_sum, done = 0, 0.0, 0
+        for i in range(warm + repeats):
+            if i > warm and time.perf_counter() - t_start > budget_s:
+                break
+            m = pair()
+            if m is None:
                 return None
-            lines = 0
-            for k in range(N_BETA):
-                with open(os.path.join(wd, "prob-chain%d.dump" % k), "rb") as f:
-                    lines += sum(1 for _ in f)
-            meas.append((dt, lines))
-        (t_a, n_a), (t_b, n_b) = meas
-        rate = (n_b - n_a) / (t_b - t_a)
+            if i >= warm:
+                n_sum, t_sum, done = n_sum + m[0], t_sum + m[1], done + 1
+        rate = n_sum / t_sum
         sample = (f"reference build (src/*.c + apps/simplesin5.c, -DN_BETA={N_BETA}), `run` on the full {N_ROWS}-row "
-                  f"table with {cores} OpenMP threads: {n_b - n_a} chain-steps counted from the dump files in "
-                  f"{t_b - t_a:.1f} s ({REF_ITERS[1]}-iteration run minus {REF_ITERS[0]}-iteration run; "
-                  f"{N_BETA * (REF_ITERS[1] - REF_ITERS[0])} were requested)")
-        return rate, cores, sample, (t_b - t_a) / max(n_b - n_a, 1) * 1e3 * N_BETA
+                  f"table with {cores} OpenMP threads: {n_sum} chain-steps counted from the dump files in "
+                  f"{t_sum:.1f} s over {done} timed repeat(s) after {warm} untimed ({REF_ITERS[1]}-iteration run "
+                  f"minus {REF_ITERS[0]}-iteration run; {N_BETA * (REF_ITERS[1] - REF_ITERS[0])} per repeat were requested)")
+        return rate, cores, sample, t_sum / max(n_sum, 1) * 1e3 * N_BETA
     finally:
         shutil.rmtree(wd, ignore_errors=True)
 
@@ -240,13 +255,15 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        real = reference_exe_rate(data)
+        real = reference_exe_rate(data, repeats=K, warm=min(W, 1))
         if real is not None:
-            # the reference itself (one measurement covers the K "steps": each is the same bounded
-            # sample of the workload, and the run is minutes of CPU time already)
+            # the reference itself: each of the K "steps" is the same bounded sample of the workload
+            # (a 124- and a 31-iteration run of one 64-rung ladder on the full table); ms_per_step is
+            # what one full step of the workload (64 ensembles x 31 iterations) would take at that rate
             v, cores, sample, ms = real
             line = {"impl": "reference", "metric": "chain-steps/sec", "value": v, "unit": "chain-steps/s",
                     "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms * N_SWAP * N_ENS,
+                    "ms_per_step_note": "extrapolated from the bounded sample to one full step of the workload",
                     "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                     "data": "synthetic", "config": config,
                     "cpu_baseline": {"value": v, "unit": "chain-steps/s", "cores": cores, "kind": "reference",
