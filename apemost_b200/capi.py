@@ -247,6 +247,14 @@ class EngineBase:
         self._check(f(self._h, None if sel is None else sel.ctypes.data, int(kind), int(n_steps), log.ctypes.data))
         return log
 
+    # -- host-side uniforms (the regression calibrator's noise) ----------------------
+    def host_uniform(self, g):
+        u = C.c_double()
+        f = self._fn("host_uniform")
+        f.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        self._check(f(self._h, int(g), C.byref(u)))
+        return u.value
+
     # -- -DADAPT -------------------------------------------------------------------
     def set_adapt(self, enabled=True, target_acceptance_rate=0.5):
         f = self._fn("set_adapt")

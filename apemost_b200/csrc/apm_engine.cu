@@ -101,6 +101,7 @@ struct apm_gpu {
 	// ladder split: packs of the boundary chains, [n_ens][LADDER_PACK(n_par)] each
 	bool ladder = false;
 	double * d_pack_first = nullptr, *d_pack_last = nullptr, *d_pack_prev = nullptr, *d_pack_next = nullptr;
+	std::vector<unsigned long long> host_draws; // per chain: uniforms handed out by apm_gpu_host_uniform
 	std::string err;
 };
 
@@ -1294,6 +1295,19 @@ extern "C" int apm_gpu_steps(apm_gpu * h, const unsigned char * select, int kind
 	if (e != cudaSuccess)
 		return fail(h, APM_ECUDA, "reading the accept log failed: %s", cudaGetErrorString(e));
 	return rc;
+}
+
+// ------------------------------------------------------------------ host-side uniforms
+extern "C" int apm_gpu_host_uniform(apm_gpu * h, int g, double * u) {
+	if (!h || !u || g < 0 || g >= h->n_chains)
+		return APM_EINVAL;
+	if (h->host_draws.size() != (size_t) h->n_chains)
+		h->host_draws.assign(h->n_chains, 0ull);
+	const DevState & S = h->S;
+	const uint32_t id = (uint32_t) (S.chain_id_offset + (g / S.n_beta) * S.id_stride + S.k_offset + g % S.n_beta);
+	double u1;
+	philox_uniforms(S.seed, id, h->host_draws[g]++, PURPOSE_HOST, 0, 0, *u, u1);
+	return APM_OK;
 }
 
 // ------------------------------------------------------------------ -DADAPT

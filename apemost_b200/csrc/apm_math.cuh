@@ -133,6 +133,64 @@ APM_HD double sin_full(double x) {
 	return sin(x); /* Payne-Hanek path of the math library; NaN/Inf land here too */
 }
 
+// ---- branch-free quotient and logarithm for positive normal arguments -------------------
+// The math library's a / b and log(x) each carry a slow-path branch (denormals, infinities,
+// huge quotients); inside a row loop those branches keep the compiler from interleaving the
+// independent chains of a thread, and the FP64 pipe idles on every dependent chain (ncu on
+// pulse_vrot's row term: 49 % pipe, `wait` the top stall; profiles/r01n_full_pulse_vrot.json).
+// These versions have no branch and no call.  Domain -- the caller's fast_ok() vouches for it --:
+// every argument positive, finite, in [1e-300, 1e300], and so is the quotient.
+//   rcp_seed   : MUFU.RCP64H, at least 20 good bits
+//   div_pos    : two Newton steps on the seed (error squared twice: below 2^-53 for any seed
+//                better than 2^-14) and one correction of the quotient by its exact residual;
+//                within 1 ulp of a / b.  1 MUFU + 7 FP64 instructions.
+//   log_pos    : x = 2^e m, m in [sqrt(1/2), sqrt(2)); s = (m - 1) / (m + 1) by div_pos;
+//                log m = 2 atanh s = 2 s + s^3 (2/3 + 2/5 s^2 + ... + 2/19 s^16), truncation
+//                below 3e-17 relative for |s| <= 0.1716; + e ln2 in two parts.
+//                Absolute error below 2.5e-16 max(1, |log x|) (tests/test_math_cpu.py).
+//                1 MUFU + 24 FP64 instructions, exponent handling on the integer pipe.
+APM_HD double rcp_seed(double b) {
+#if defined(__CUDA_ARCH__)
+	double y;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+	return y;
+#else
+	return make_double(hi32(1.0 / b), 0); /* the host twin: same algorithm, its own 20-bit seed */
+#endif
+}
+APM_HD double div_pos(double a, double b) {
+	double y = rcp_seed(b);
+	double e = fma(-b, y, 1.0);
+	y = fma(y, e, y);
+	e = fma(-b, y, 1.0);
+	y = fma(y, e, y);
+	double q = a * y;
+	return fma(fma(-b, q, a), y, q);
+}
+APM_HD double log_pos(double x) {
+	const double LN2_HI = 0x1.62e42fefa39efp-1, LN2_LO = 0x1.abc9e3b39803fp-56;
+	int hi = hi32(x);
+	// mantissa above sqrt(2) (0x6a09e667f3bcd...): halve it, one more power of two
+	int up = (hi & 0x000fffff) >= 0x0006a09f ? 1 : 0;
+	double m = make_double((hi & 0x000fffff) | ((1023 - up) << 20), lo32(x));
+	// the exponent as a double without a conversion instruction: the biased exponent in the low
+	// word of 2^52, minus (2^52 + 1023)
+	double ed = make_double(0x43300000, (hi >> 20) + up) - 4503599627371519.0;
+	double s = div_pos(m - 1.0, m + 1.0);
+	double z = s * s;
+	double p = 2.0 / 19.0;
+	p = fma(p, z, 2.0 / 17.0);
+	p = fma(p, z, 2.0 / 15.0);
+	p = fma(p, z, 2.0 / 13.0);
+	p = fma(p, z, 2.0 / 11.0);
+	p = fma(p, z, 2.0 / 9.0);
+	p = fma(p, z, 2.0 / 7.0);
+	p = fma(p, z, 2.0 / 5.0);
+	p = fma(p, z, 2.0 / 3.0);
+	double lm = fma(s * z, p, s + s);
+	return fma(ed, LN2_HI, fma(ed, LN2_LO, lm));
+}
+
 // ---- Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011) -----------------------------
 struct Philox4 {
 	uint32_t w[4];
@@ -175,7 +233,8 @@ APM_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
 //   id      = global chain id for per-chain draws, global ensemble id for swap draws
 //   u0, u1  = two 53-bit uniforms strictly inside (0, 1)
 enum {
-	PURPOSE_JUMP = 0, PURPOSE_ACCEPT = 1, PURPOSE_SWAP_PICK = 2, PURPOSE_SWAP_TEST = 3
+	PURPOSE_JUMP = 0, PURPOSE_ACCEPT = 1, PURPOSE_SWAP_PICK = 2, PURPOSE_SWAP_TEST = 3,
+	PURPOSE_HOST = 4 // apm_gpu_host_uniform: step = the chain's count of host draws
 };
 
 APM_HD void philox_uniforms(uint64_t seed, uint32_t id, uint64_t step, uint32_t purpose,

@@ -236,12 +236,15 @@ struct ModelPulseVrot {
 		const double Q = (d1 * d2) * d34;
 		// P = h1 d2 d3 d4 + h2 d1 (d3 d4 + d2 d4 + d2 d3)
 		const double P = fma(q.h1 * d2, d34, (q.h2 * d1) * fma(d2, d3 + d4, d34));
-		const double r = Q / P; // = 1 / y
-		return acc + fma(d, r, -log(r));
+		// = 1 / y; quotient and logarithm without the library's slow-path branches, so that the
+		// chains (or rows) a thread works on interleave (apm_math.cuh)
+		const double r = div_pos(Q, P);
+		return acc + fma(d, r, -log_pos(r));
 	}
 	APM_D static bool fast_ok(const Prep & q, double xub) {
 		const double t = APM_TWO_PI * fabs(q.lifetime) * (fabs(q.f1) + fabs(q.f2) + fabs(q.vrot) + xub);
-		return t < 1e30 && q.h1 > 0 && q.h2 > 0; // d_k < 1e60, Q < 1e240; positive heights: P > 0
+		// d_k < 1e60: 1 <= Q < 1e240; heights in (1e-30, 1e30): 1e-30 < P < 1e211
+		return t < 1e30 && q.h1 > 1e-30 && q.h2 > 1e-30 && q.h1 < 1e30 && q.h2 < 1e30;
 	}
 	APM_D static double sum0(const double * p) { return p[1]; } // accumulator starts at params[1] (:34)
 	APM_D static double prior(const double * p, int n_par, const double * mc) {
@@ -301,8 +304,8 @@ struct ModelPulse {
 				Q = Q * dj;
 			}
 		}
-		const double r = Q / P;
-		return acc + fma(d, r, -log(r));
+		const double r = div_pos(Q, P);
+		return acc + fma(d, r, -log_pos(r));
 	}
 	APM_D static bool fast_ok(const Prep & q, double xub) {
 		double fmax = 0.0;
@@ -311,11 +314,11 @@ struct ModelPulse {
 		for (int j = 0; j < (APM_MAX_PAR - 2) / 2; j++) {
 			if (j < q.n_modes) {
 				fmax = fmax > fabs(q.f[j]) ? fmax : fabs(q.f[j]);
-				positive = positive && q.h[j] > 0 && q.h[j] < 1e30;
+				positive = positive && q.h[j] > 1e-30 && q.h[j] < 1e30;
 			}
 		}
-		// d_j < 1e38: Q < 1e266, P < 7e296
-		return APM_TWO_PI * fabs(q.lifetime) * (fmax + xub) < 1e19 && positive;
+		// d_j < 1e38: 1 <= Q < 1e266, 1e-30 < P < 7e258
+		return APM_TWO_PI * fabs(q.lifetime) * (fmax + xub) < 1e19 && positive && q.n_modes > 0;
 	}
 	APM_D static double sum0(const double * p) { return p[1]; }
 	APM_D static double prior(const double * p, int n_par, const double * mc) {

@@ -12,8 +12,8 @@
  * (:146,161 assign `accepts` at the top of the loop body), and the deviation statistics go
  * through the integer abs() (:182-183).
  *
- * The other alternates (CALIBRATE_QUADRATIC, CALIBRATE_MULTILIN) sit on the same two building
- * blocks plus a linear regression; they are not built yet.
+ * CALIBRATE_MULTILIN (apm_calibrate_multilin.c) sits on the same assessment plus a linear
+ * regression; CALIBRATE_QUADRATIC is not built.
  */
 #include "apm_session.h"
 

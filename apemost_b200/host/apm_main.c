@@ -147,7 +147,9 @@ void check(void) {
 #else
 	printf("off\n");
 #endif
-#ifdef CALIBRATE_ALTERNATE
+#if defined(CALIBRATE_MULTILIN)
+	printf("\tCALIBRATE_MULTILIN: on (assess_acceptance_rate + markov_chain_calibrate_multilinear_regression)\n");
+#elif defined(CALIBRATE_ALTERNATE)
 	printf("\tCALIBRATE_ALTERNATE: on (assess_acceptance_rate + markov_chain_calibrate_alt)\n");
 #else
 	printf("\tCALIBRATE_ALTERNATE: off (markov_chain_calibrate_orig)\n");

@@ -311,6 +311,13 @@ void apm_session_calc_model(apm_session * s, const int * which, int n) {
 	free(p); free(b); free(prob); free(prior);
 }
 
+/* gsl_rng_uniform(get_random(chains[g])) for host-side algorithms */
+double apm_session_uniform(apm_session * s, int g) {
+	double u = 0;
+	apm_gpu_check(s, apm_gpu_host_uniform(s->gpu, g, &u), "drawing a random number");
+	return u;
+}
+
 /* APM_HOST_TIMING=1: where the wall time of a phase goes, on stderr */
 static double wall_s(void) {
 	struct timespec t;
@@ -329,13 +336,14 @@ static void calibrate_selected(apm_session * s, const unsigned char * select, in
 	long long cap = 0, n_rows = 0;
 	apm_gpu_calib_progress * rows = NULL;
 	int g, rc, n_sel = 0;
-#if defined(CALIBRATE_QUADRATIC) || defined(CALIBRATE_MULTILIN)
-#error "of the alternate calibrators only CALIBRATE_ALTERNATE is built (apm_calibrate_alt.c)"
+#if defined(CALIBRATE_QUADRATIC)
+#error "of the alternate calibrators CALIBRATE_ALTERNATE and CALIBRATE_MULTILIN are built, CALIBRATE_QUADRATIC is not"
 #endif
-#ifdef CALIBRATE_ALTERNATE
+#if defined(CALIBRATE_ALTERNATE) || defined(CALIBRATE_MULTILIN)
 	if (!skip) {
-		/* markov_chain_calibrate = burn_in + markov_chain_calibrate_alt, one chain after the other
-		 * like the reference's loop (src/parallel_tempering.c:173-197 with one thread) */
+		/* markov_chain_calibrate = burn_in + the alternate calibrator (the reference's precedence:
+		 * MULTILIN before ALTERNATE, src/markov_chain_calibrate.c:1190-1202), one chain after the
+		 * other like the reference's loop (src/parallel_tempering.c:173-197 with one thread) */
 		unsigned char * one = (unsigned char *) calloc(s->n_chains, 1);
 		for (g = 0; g < s->n_chains; g++) {
 			if (!select[g])
@@ -346,7 +354,11 @@ static void calibrate_selected(apm_session * s, const unsigned char * select, in
 			one[g] = 0;
 			apm_session_pull(s, g, 1);
 			apm_set_output_dir(s->ens_first + g / s->n_beta);
+#ifdef CALIBRATE_MULTILIN
+			apm_calibrate_multilin(s, g, TARGET_ACCEPTANCE_RATE, MAX_AR_DEVIATION, ITER_LIMIT);
+#else
 			apm_calibrate_alt(s, g, TARGET_ACCEPTANCE_RATE, MAX_AR_DEVIATION, ITER_LIMIT);
+#endif
 		}
 		apm_set_output_dir(-1);
 		free(one);

@@ -48,6 +48,12 @@ unsigned int apm_assess_acceptance_rate(apm_session * s, int g, unsigned int par
 void apm_calibrate_alt(apm_session * s, int g, double desired_acceptance_rate, const double max_ar_deviation,
 		const unsigned int iter_limit);
 
+/* apm_calibrate_multilin.c: -DCALIBRATE_MULTILIN (reference src/markov_chain_calibrate.c:33-237,
+ * src/gsl_helper.c:189-298) for chain g, after its burn-in */
+void apm_calibrate_multilin(apm_session * s, int g, double desired_acceptance_rate, const double max_ar_deviation,
+		const unsigned int iter_limit);
+double apm_session_uniform(apm_session * s, int g);
+
 /* apm_fastfmt.c: "%6e" without printf (declines with 0 where it cannot guarantee printf's bytes) */
 int apm_format_e6(double v, char * out);
 int apm_format_e15(double v, char * out); /* "%.15e" */

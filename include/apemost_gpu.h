@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define APM_GPU_ABI_VERSION 4
+#define APM_GPU_ABI_VERSION 5
 
 /* ---- error codes -------------------------------------------------------- */
 #define APM_OK          0
@@ -219,6 +219,12 @@ int apm_gpu_calibrate(apm_gpu * h, const unsigned char * select,
  * field), 0 otherwise and for chains not selected. --------------------------------------- */
 int apm_gpu_steps(apm_gpu * h, const unsigned char * select, int kind,
 		long long n_steps, unsigned char * accepted /*[n_steps][n_chains]*/);
+
+/* ---- one uniform in (0, 1) from chain g's random stream, for host-side algorithms: what the
+ * regression calibrator draws with gsl_rng_uniform(get_random(m)) between its assessments
+ * (reference src/markov_chain_calibrate.c:93-94,155).  A stream of its own per chain (counter
+ * RNG, purpose 4), so the draws do not shift the chain's step streams; host work only. ------- */
+int apm_gpu_host_uniform(apm_gpu * h, int g, double * u);
 
 /* ---- adapt() as compiled with -DADAPT (reference src/parallel_tempering.c:282-302, called
  * once per round before the swap, :404): a chain whose per-parameter accept + reject counter

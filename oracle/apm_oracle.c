@@ -352,6 +352,7 @@ void orc_philox4x32_10(const unsigned ctr[4], const unsigned key[2], unsigned ou
 #define PURPOSE_ACCEPT 1u
 #define PURPOSE_SWAP_PICK 2u
 #define PURPOSE_SWAP_TEST 3u
+#define PURPOSE_HOST 4u
 
 /* Stream layout shared with the engine (apemost_b200/csrc/apm_rng.cuh):
  *   key     = (seed lo, seed hi)
@@ -407,6 +408,7 @@ struct orc_engine {
 	int n_cols;
 	mt_state mt;
 	u64 * swap_round; /* per ensemble: PHILOX swap-stream position */
+	u64 * host_draws; /* per chain: PHILOX host-stream position (orc_host_uniform) */
 	int adapt;            /* -DADAPT, ref src/parallel_tempering.c:282-302 */
 	double adapt_target;  /* TARGET_ACCEPTANCE_RATE */
 	int random_swap;      /* -DRANDOMSWAP, ref src/parallel_tempering_interaction.c:130-131 */
@@ -854,6 +856,7 @@ int orc_create(orc_engine ** out, const orc_config * cfg) {
 	n = cfg->n_par;
 	e->n_chains = cfg->n_ensembles * cfg->n_beta;
 	e->chains = (chain_t *) calloc(e->n_chains, sizeof(chain_t));
+	e->host_draws = (u64 *) calloc(e->n_chains, sizeof(u64));
 	e->pmin = (double *) calloc(n, sizeof(double));
 	e->pmax = (double *) calloc(n, sizeof(double));
 	e->swap_round = (u64 *) calloc(cfg->n_ensembles, sizeof(u64));
@@ -896,6 +899,7 @@ int orc_destroy(orc_engine * e) {
 	free(e->pmax);
 	free(e->data);
 	free(e->swap_round);
+	free(e->host_draws);
 	free(e->tr_prob);
 	free(e->tr_dl);
 	free(e->tr_params);
@@ -908,6 +912,21 @@ void orc_mt_seed(orc_engine * e, unsigned long seed) {
 }
 double orc_mt_uniform(orc_engine * e) {
 	return mt_uniform(&e->mt);
+}
+/* mirrors apm_gpu_host_uniform: gsl_rng_uniform(get_random(m)) outside the stepping loops
+ * (ref: src/markov_chain_calibrate.c:93-94,155).  MT19937 mode: the next number of the one global
+ * stream, like the reference; PHILOX mode: the chain's host stream (purpose 4) */
+int orc_host_uniform(orc_engine * e, int g, double * u) {
+	double u1;
+	if (e == NULL || u == NULL || g < 0 || g >= e->n_chains)
+		return -1;
+	if (e->cfg.rng_kind == ORC_RNG_MT19937) {
+		*u = mt_uniform(&e->mt);
+		return 0;
+	}
+	orc_philox_uniforms(e->cfg.seed, (unsigned) (e->cfg.chain_id_offset + g), e->host_draws[g]++, PURPOSE_HOST,
+			0, 0, u, &u1);
+	return 0;
 }
 
 int orc_set_data(orc_engine * e, const double * d, long long n_rows, int n_cols) {

@@ -154,6 +154,7 @@ double orc_evidence(int n_beta, const double * beta, const double * mean_dl);
 /* GSL-compatible MT19937 access (pins the shim and the oracle to the same stream) */
 void orc_mt_seed(orc_engine * e, unsigned long seed);
 double orc_mt_uniform(orc_engine * e);
+int orc_host_uniform(orc_engine * e, int g, double * u); /* mirrors apm_gpu_host_uniform */
 
 #ifdef __cplusplus
 }

@@ -234,6 +234,12 @@ def all_phase_fixtures():
         "simplesin", C1_ROWS, "testlc.dat", None, dict(small, GSL_RNG_SEED=23),
         ccflags_extra="-DCALIBRATE_ALTERNATE -DSKIP_CALIBRATE_ALLCHAINS", suffix="_pin_altskip",
         engine_opts=dict(host_only=1))
+    # -DCALIBRATE_MULTILIN: markov_chain_calibrate_multilinear_regression for every chain (pins
+    # apm_calibrate_multilin.c and the host-side uniform draws).  On the hottest chain the
+    # reference's regression walks one step width below zero -- kept: it is what the reference does.
+    fx["c1_multilin_phases"] = phases_fixture(
+        "simplesin", C1_ROWS, "testlc.dat", None, dict(small, GSL_RNG_SEED=29),
+        ccflags_extra="-DCALIBRATE_MULTILIN", suffix="_pin_multilin", engine_opts=dict(host_only=1))
     return fx
 
 

@@ -59,6 +59,9 @@ int apm_gpu_create(apm_gpu ** handle, const apm_gpu_config * cfg) {
 int apm_gpu_steps(apm_gpu * h, const unsigned char * select, int kind, long long n_steps, unsigned char * accepted) {
 	return orc_steps(h->e, select, kind, n_steps, accepted);
 }
+int apm_gpu_host_uniform(apm_gpu * h, int g, double * u) {
+	return orc_host_uniform(h->e, g, u);
+}
 int apm_gpu_set_adapt(apm_gpu * h, int enabled, double target_acceptance_rate) {
 	return orc_set_adapt(h->e, enabled, target_acceptance_rate);
 }

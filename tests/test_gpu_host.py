@@ -135,33 +135,38 @@ def test_benchmark_exe_reproduces_and_matches_fixture(tmp_path):
     assert r.returncode == 1 and "SYNOPSIS" in r.stderr
 
 
-def test_alternate_calibrator_on_gpu_equals_oracle_flow(tmp_path):
+@pytest.mark.parametrize("fixture", ["c1_altcal_phases", "c1_multilin_phases"])
+def test_alternate_calibrator_on_gpu_equals_oracle_flow(tmp_path, fixture):
     """-DCALIBRATE_ALTERNATE (assess_acceptance_rate + markov_chain_calibrate_alt, reference
-    src/markov_chain.c:117-224, src/markov_chain_calibrate.c:927-1037) in the host layer: the product
-    executable on the GPU against the very same host sources linked to the CPU oracle in PHILOX mode
-    (whose MT19937 twin is byte-pinned to a -DCALIBRATE_ALTERNATE reference build by test_host_cpu.py)"""
+    src/markov_chain.c:117-224, src/markov_chain_calibrate.c:927-1037) and -DCALIBRATE_MULTILIN
+    (markov_chain_calibrate_multilinear_regression, :33-237, with its host-side uniform draws through
+    apm_gpu_host_uniform) in the host layer: the product executable on the GPU against the very same
+    host sources linked to the CPU oracle in PHILOX mode (whose MT19937 twin is byte-pinned to a
+    reference build with the same flag by test_host_cpu.py)"""
     from test_host_cpu import build_host_over_oracle
-    fx = json.load(open(os.path.join(GOLDEN, "c1_altcal_phases.json")))
+    fx = json.load(open(os.path.join(GOLDEN, fixture + ".json")))
     cfg = fx["config"]
     flags = [f"-D{k}={v}" for k, v in cfg.items() if k != "GSL_RNG_SEED"] + fx["ccflags_extra"].split()
     exe_gpu = make("simplesin.exe", " ".join(flags), str(tmp_path / "bin"))
-    exe_cpu = build_host_over_oracle("altcal_philox", "simplesin", flags)
+    exe_cpu = build_host_over_oracle(fixture + "_philox", "simplesin", flags)
     out = {}
     for name, exe, extra in (("gpu", exe_gpu, {}), ("cpu", exe_cpu, {"APM_TEST_ORACLE_RNG": "philox"})):
         wd = str(tmp_path / name)
         setup_workdir(wd, fx)
         env = dict(os.environ, GSL_RNG_SEED="5", **extra)
-        codes = []
+        codes, said = [], []
         for phase in ("calibrate_first", "calibrate_rest"):
             r = subprocess.run([exe, phase], cwd=wd, env=env, capture_output=True, text=True)
             codes.append((phase, r.returncode, r.stderr.strip().splitlines()[-1:] if r.returncode else []))
+            said += re.findall(r"^ +\d+ iterations$", r.stdout, flags=re.M)  # the regression calibrator's log
             if r.returncode != 0:
                 # the reference's alternate calibrator gives up easily ("iteration limit reached",
                 # exit 1, src/markov_chain_calibrate.c:1017-1020); then both must give up alike
                 assert r.returncode == 1 and "iteration limit reached" in r.stderr, r.stderr[-500:]
                 break
+        progress = os.path.join(wd, "calibration_progress.data")  # written by calibrate_alt only
         out[name] = (codes, numbers(os.path.join(wd, "calibration_results")),
-                     open(os.path.join(wd, "calibration_progress.data")).read())
+                     open(progress).read() if os.path.exists(progress) else "\n".join(said))
     assert out["gpu"][0] == out["cpu"][0] and out["gpu"][0][0][1] == 0, out["gpu"][0]
     np.testing.assert_allclose(out["gpu"][1], out["cpu"][1], rtol=1e-9, atol=1e-300)
     assert out["gpu"][2] == out["cpu"][2] and len(out["gpu"][2]) > 0

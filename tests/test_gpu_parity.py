@@ -642,6 +642,16 @@ def test_steps_accept_log_equals_oracle(capi, path):
     _compare_state(st_g, st_c)
 
 
+def test_host_uniform_stream_equals_oracle(capi):
+    """apm_gpu_host_uniform: the chain's host-side stream (counter RNG, purpose 4) is the oracle's,
+    number for number, is a stream of its own per chain, and leaves the step streams alone"""
+    e, o = _pair(capi, "normal", 2, 3, seed=77)
+    got = [[eng.host_uniform(g) for g in (0, 4, 0, 0, 5, 4)] for eng in (e, o)]
+    assert got[0] == got[1]
+    assert len(set(got[0])) == 6 and all(0.0 < u < 1.0 for u in got[0])
+    assert e.get_chains(fields=("rng_counter",))["rng_counter"].sum() == 0
+
+
 # ---------------------------------------------------------------- statistical parity with the reference
 @pytest.mark.parametrize("name", ["c1_phases", "c4_phases"])
 def test_evidence_and_posterior_match_reference_statistics(capi, name):

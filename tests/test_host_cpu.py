@@ -24,7 +24,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 HOST = os.path.join(ROOT, "apemost_b200", "host")
 BUILD = os.path.join(ROOT, "oracle", "_build")
 FIXTURES = ["c1_phases", "c1_circular_phases", "c1_logistic_phases", "c1_uniform_phases", "c4_phases", "c2_phases",
-            "c1_adapt_phases", "c1_randomswap_phases", "c1_altcal_phases"]
+            "c1_adapt_phases", "c1_randomswap_phases", "c1_altcal_phases", "c1_multilin_phases"]
 MODEL_IDS = {"simplesin": 0, "simplesin5": 1, "normal": 2, "pulse_vrot": 3, "simplesin2": 4, "pulse": 5}
 
 
@@ -33,7 +33,7 @@ def build_host_over_oracle(name, model, ccflags):
     build_oracle()
     exe = os.path.join(BUILD, f"host_{name}.exe")
     src = [os.path.join(HOST, f) for f in ("apm_main.c", "apm_chainobj.c", "apm_files.c", "apm_phases.c",
-                                           "apm_analyse.c", "apm_calibrate_alt.c", "apm_fastfmt.c")]
+                                           "apm_analyse.c", "apm_calibrate_alt.c", "apm_calibrate_multilin.c", "apm_fastfmt.c")]
     src += [os.path.join(ROOT, "apemost_b200", "compat", "gsl", "gsl_compat.c"),
             os.path.join(ROOT, "tests", "host_shim", "apm_gpu_over_oracle.c")]
     cmd = ["gcc", "-O2", "-std=gnu99", "-fopenmp", "-pthread", "-I", os.path.join(HOST, "include"), "-I", os.path.join(ROOT, "include"),

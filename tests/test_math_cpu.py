@@ -17,6 +17,8 @@ SRC = r'''
 extern "C" {
 void t_sin_fast(const double * x, double * y, long n) { for (long i = 0; i < n; i++) y[i] = apm::sin_fast(x[i]); }
 void t_sin_full(const double * x, double * y, long n) { for (long i = 0; i < n; i++) y[i] = apm::sin_full(x[i]); }
+void t_log_pos(const double * x, double * y, long n) { for (long i = 0; i < n; i++) y[i] = apm::log_pos(x[i]); }
+void t_div_pos(const double * a, const double * b, double * y, long n) { for (long i = 0; i < n; i++) y[i] = apm::div_pos(a[i], b[i]); }
 double t_mod_double(double x, double d) { return apm::mod_double(x, d); }
 void t_philox(const unsigned * c, const unsigned * k, unsigned * o) {
 	apm::Philox4 r = apm::philox4x32_10(c[0], c[1], c[2], c[3], k[0], k[1]);
@@ -60,6 +62,26 @@ def test_sin_fast_absolute_error(lib, scale):
     err = np.abs(_apply(lib.t_sin_fast, x).astype(np.longdouble) - ref).astype(np.float64)
     assert err.max() < 3.5e-16, err.max()
     assert abs(np.mean((_apply(lib.t_sin_fast, x).astype(np.longdouble) - ref).astype(np.float64))) < 2e-18
+
+
+def test_log_pos_and_div_pos(lib):
+    """the branch-free logarithm and quotient of pulse / pulse_vrot's row term on their domain
+    (positive normal arguments, 1e-300 .. 1e300): log within 2.5e-16 max(1, |log x|) of an
+    extended-precision logarithm, the quotient within 1 ulp of a / b"""
+    rng = np.random.default_rng(31)
+    x = np.concatenate([10.0 ** rng.uniform(-300, 300, 300_000), rng.uniform(0.5, 2.0, 300_000),
+                        1 + rng.normal(0, 1e-9, 1000), [1.0, 2.0, 0.5, np.sqrt(2), 1 / np.sqrt(2), 1e-300, 1e300]])
+    ref = np.log(x.astype(np.longdouble))
+    err = np.abs(_apply(lib.t_log_pos, x).astype(np.longdouble) - ref).astype(np.float64)
+    assert (err <= 2.5e-16 * np.maximum(1.0, np.abs(ref.astype(np.float64)))).all(), err.max()
+    assert _apply(lib.t_log_pos, np.array([1.0]))[0] == 0.0
+    a, b = 10.0 ** rng.uniform(-140, 140, 300_000), 10.0 ** rng.uniform(-140, 140, 300_000)
+    a[:1000], b[:1000] = rng.uniform(1, 2, 1000), rng.uniform(1, 2, 1000)
+    q = np.empty_like(a)
+    lib.t_div_pos(a.ctypes.data_as(C.POINTER(C.c_double)), b.ctypes.data_as(C.POINTER(C.c_double)),
+                  q.ctypes.data_as(C.POINTER(C.c_double)), C.c_long(a.size))
+    assert (np.abs(q - a / b) <= np.spacing(a / b)).all()
+    assert (q == a / b).mean() > 0.99
 
 
 def test_sin_fast_special_points(lib):
