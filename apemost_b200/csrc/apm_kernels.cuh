@@ -26,6 +26,7 @@
 
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
+#include <type_traits>
 #include "apm_chain.cuh"
 
 namespace apm {
@@ -79,15 +80,36 @@ template<> struct RowT<2> { typedef double2 type; };
 template<> struct RowT<4> { typedef double4 type; };
 template<class M> using Row = typename RowT<M::ROW_W>::type;
 
+// A thread's running sum over rows is a plain double unless the model declares its own
+// accumulator (`typedef ... Acc; acc_zero(); acc_merge(a, b); acc_value(a)`): pulse and pulse_vrot
+// carry the product of their quotients next to the sum, so that the rows' logarithms become one
+// logarithm per thread (apm_models.cuh).  acc_merge folds two accumulators of a thread,
+// acc_value gives the double that enters the cross-thread reduction.
+template<class M, class = void>
+struct ModelAcc {
+	typedef double type;
+	__device__ __forceinline__ static double zero() { return 0.0; }
+	__device__ __forceinline__ static double merge(double a, double b) { return a + b; }
+	__device__ __forceinline__ static double value(double a) { return a; }
+};
 template<class M>
-__device__ __forceinline__ double row_accum(double acc, const typename M::Prep & q, const Row<M> & r) {
+struct ModelAcc<M, std::void_t<typename M::Acc>> {
+	typedef typename M::Acc type;
+	__device__ __forceinline__ static type zero() { return M::acc_zero(); }
+	__device__ __forceinline__ static type merge(const type & a, const type & b) { return M::acc_merge(a, b); }
+	__device__ __forceinline__ static double value(const type & a) { return M::acc_value(a); }
+};
+template<class M> using Acc = typename ModelAcc<M>::type;
+
+template<class M>
+__device__ __forceinline__ Acc<M> row_accum(const Acc<M> & acc, const typename M::Prep & q, const Row<M> & r) {
 	if constexpr (M::ROW_W == 2)
 		return M::accum(acc, q, r.x, r.y);
 	else
 		return M::accum(acc, q, r);
 }
 template<class M>
-__device__ __forceinline__ double row_accum_fast(double acc, const typename M::Prep & q, const Row<M> & r) {
+__device__ __forceinline__ Acc<M> row_accum_fast(const Acc<M> & acc, const typename M::Prep & q, const Row<M> & r) {
 	if constexpr (M::ROW_W == 2)
 		return M::accum_fast(acc, q, r.x, r.y);
 	else
@@ -214,7 +236,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) loglik_tiled_kernel(const LLArg
 
 		typename M::Prep q[C];
 		int gid[C];
-		double acc[C][U];
+		Acc<M> acc[C][U];
 		bool fast = true;
 #pragma unroll
 		for (int c = 0; c < C; c++) {
@@ -226,7 +248,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) loglik_tiled_kernel(const LLArg
 			fast = fast && M::fast_ok(q[c], xub);
 #pragma unroll
 			for (int u = 0; u < U; u++)
-				acc[c][u] = 0.0;
+				acc[c][u] = ModelAcc<M>::zero();
 		}
 
 		for (int k = 0; k < nk; k++, it++) {
@@ -283,11 +305,11 @@ __global__ void __launch_bounds__(LL_THREADS, 1) loglik_tiled_kernel(const LLArg
 		// chain the 8 strided thread slots of a lane in index order, then a butterfly
 #pragma unroll
 		for (int c = 0; c < C; c++) {
-			double v = acc[c][0];
+			Acc<M> v = acc[c][0];
 #pragma unroll
 			for (int u = 1; u < U; u++)
-				v += acc[c][u];
-			sacc[c * LL_THREADS + tid] = v;
+				v = ModelAcc<M>::merge(v, acc[c][u]);
+			sacc[c * LL_THREADS + tid] = ModelAcc<M>::value(v);
 		}
 		__syncthreads();
 		for (int c = warp; c < C; c += LL_WARPS) {
@@ -613,7 +635,7 @@ __device__ __forceinline__ double fused_loglik(const DevState & S, int g, const 
 		return 0.0;
 	typename M::Prep q;
 	M::prep(q, S.prop + (size_t) g * S.n_par, S.n_par, S.model_const);
-	double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+	Acc<M> a0 = ModelAcc<M>::zero(), a1 = a0, a2 = a0, a3 = a0;
 	int i = lane;
 	if (M::fast_ok(q, xub)) {
 		for (; i + 96 < n_rows; i += 128) {
@@ -633,7 +655,7 @@ __device__ __forceinline__ double fused_loglik(const DevState & S, int g, const 
 			a0 = row_accum<M>(a0, q, r);
 		}
 	}
-	return warp_sum((a0 + a1) + (a2 + a3));
+	return warp_sum(ModelAcc<M>::value(ModelAcc<M>::merge(ModelAcc<M>::merge(a0, a1), ModelAcc<M>::merge(a2, a3))));
 }
 
 // chain_propose with the coordinates drawn by the lanes of a warp in parallel (every draw has
@@ -799,7 +821,7 @@ __device__ __forceinline__ double group_loglik(const DevState & S, const double 
 		int n_rows, double xub, int gl, int GL) {
 	typename M::Prep q;
 	M::prep(q, prop, S.n_par, S.model_const);
-	double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+	Acc<M> a0 = ModelAcc<M>::zero(), a1 = a0, a2 = a0, a3 = a0;
 	int i = gl;
 	if (M::fast_ok(q, xub)) {
 		for (; i + 3 * GL < n_rows; i += 4 * GL) {
@@ -814,9 +836,9 @@ __device__ __forceinline__ double group_loglik(const DevState & S, const double 
 		if (i < n_rows) {
 			const bool v1 = i + GL < n_rows, v2 = i + 2 * GL < n_rows;
 			const Row<M> r0 = sdata[i], r1 = sdata[v1 ? i + GL : i], r2 = sdata[v2 ? i + 2 * GL : i];
-			const double b0 = row_accum_fast<M>(a0, q, r0);
-			const double b1 = row_accum_fast<M>(a1, q, r1);
-			const double b2 = row_accum_fast<M>(a2, q, r2);
+			const Acc<M> b0 = row_accum_fast<M>(a0, q, r0);
+			const Acc<M> b1 = row_accum_fast<M>(a1, q, r1);
+			const Acc<M> b2 = row_accum_fast<M>(a2, q, r2);
 			a0 = b0;
 			a1 = v1 ? b1 : a1;
 			a2 = v2 ? b2 : a2;
@@ -827,7 +849,7 @@ __device__ __forceinline__ double group_loglik(const DevState & S, const double 
 			a0 = row_accum<M>(a0, q, r);
 		}
 	}
-	return warp_sum((a0 + a1) + (a2 + a3));
+	return warp_sum(ModelAcc<M>::value(ModelAcc<M>::merge(ModelAcc<M>::merge(a0, a1), ModelAcc<M>::merge(a2, a3))));
 }
 
 #ifdef APM_CLUSTER_TIMING

@@ -22,6 +22,9 @@
 //   fast_ok()    says so: fast_ok(q, xub) is evaluated once per (chain, thread, chunk) from
 //                an upper bound xub >= |x| of the thread's rows, so the per-row code carries
 //                no range check at all; where it says no, the kernel uses accum()
+//   Acc, acc_zero(), acc_merge(), acc_value()   optional: the type of a thread's running sum when
+//               a double is not the best carrier (pulse*: sum and product, one logarithm per thread
+//               instead of one per row); accum / accum_fast then take and return an Acc
 //   prior()     value passed to set_prior()
 //   sum0()      initial value of the running sum (apps/pulse*.c start it at params[1])
 //   finish()    the value passed to set_prob()
@@ -215,19 +218,57 @@ struct ModelPulseVrot {
 		double t = (APM_TWO_PI * distance) * lifetime;
 		return height / (1 + t * t);
 	}
-	APM_D static double accum(double acc, const Prep & q, double freq, double d) {
+	// The running sum of a thread carries the product of the quotients r = 1 / y next to the sum of
+	// d r: sum_i log r_i = log prod_i r_i, so the fast path multiplies (one DMUL, the exponent moved
+	// to an integer counter every row so the product stays in [1, 2)) where it would take a
+	// logarithm (25 FP64 instructions), and acc_value takes ONE logarithm per thread.
+	struct Acc {
+		double sum, prod;
+		int e;
+	};
+	APM_D static Acc acc_zero() {
+		Acc a;
+		a.sum = 0.0;
+		a.prod = 1.0;
+		a.e = 0;
+		return a;
+	}
+	APM_D static Acc acc_merge(const Acc & a, const Acc & b) {
+		Acc c;
+		c.sum = a.sum + b.sum;
+		c.prod = a.prod * b.prod;
+		c.e = a.e + b.e;
+		return c;
+	}
+	APM_D static double acc_value(const Acc & a) {
+		const double LN2_HI = 0x1.62e42fefa39efp-1, LN2_LO = 0x1.abc9e3b39803fp-56;
+		const double e = (double) a.e;
+		return a.sum - fma(e, LN2_HI, fma(e, LN2_LO, log_pos(a.prod)));
+	}
+	APM_D static Acc acc_add_row(const Acc & acc, double d, double r) {
+		Acc o;
+		o.sum = fma(d, r, acc.sum);
+		const double pr = acc.prod * r;
+		const int hi = hi32(pr);
+		o.e = acc.e + ((hi >> 20) - 1023);
+		o.prod = make_double((hi & 0x000fffff) | 0x3ff00000, lo32(pr));
+		return o;
+	}
+	APM_D static Acc accum(const Acc & acc, const Prep & q, double freq, double d) {
 		double y = 0;
 		y += lorentz(q.f1 - freq, q.lifetime, q.h1);
 		y += lorentz(q.f2 - freq + -1 * q.vrot, q.lifetime, q.h2);
 		y += lorentz(q.f2 - freq, q.lifetime, q.h2);
 		y += lorentz(q.f2 - freq + 1 * q.vrot, q.lifetime, q.h2);
-		return acc + (log(y) + d / y); // (:61)
+		Acc o = acc;
+		o.sum = acc.sum + (log(y) + d / y); // (:61)
+		return o;
 	}
 	// The same row term with ONE division instead of five: y = P / Q over the common denominator
 	// Q = d1 d2 d3 d4, d_k = 1 + t_k^2 (all terms positive: no cancellation), log y + d / y =
 	// -log(Q / P) + d (Q / P).  A few ulps from the reference's sum of quotients, far inside
 	// the 1e-12 parity bound; ~30 % fewer FP64 instructions.  fast_ok keeps Q far from overflow.
-	APM_D static double accum_fast(double acc, const Prep & q, double freq, double d) {
+	APM_D static Acc accum_fast(const Acc & acc, const Prep & q, double freq, double d) {
 		const double tw = APM_TWO_PI * q.lifetime;
 		const double t1 = (q.f1 - freq) * tw, t2 = (q.f2 - freq + -1 * q.vrot) * tw;
 		const double t3 = (q.f2 - freq) * tw, t4 = (q.f2 - freq + 1 * q.vrot) * tw;
@@ -236,10 +277,9 @@ struct ModelPulseVrot {
 		const double Q = (d1 * d2) * d34;
 		// P = h1 d2 d3 d4 + h2 d1 (d3 d4 + d2 d4 + d2 d3)
 		const double P = fma(q.h1 * d2, d34, (q.h2 * d1) * fma(d2, d3 + d4, d34));
-		// = 1 / y; quotient and logarithm without the library's slow-path branches, so that the
-		// chains (or rows) a thread works on interleave (apm_math.cuh)
-		const double r = div_pos(Q, P);
-		return acc + fma(d, r, -log_pos(r));
+		// = 1 / y; the quotient without the library's slow-path branch, so that the chains (or rows)
+		// a thread works on interleave (apm_math.cuh); its logarithm goes into the product
+		return acc_add_row(acc, d, div_pos(Q, P));
 	}
 	APM_D static bool fast_ok(const Prep & q, double xub) {
 		const double t = APM_TWO_PI * fabs(q.lifetime) * (fabs(q.f1) + fabs(q.f2) + fabs(q.vrot) + xub);
@@ -281,18 +321,24 @@ struct ModelPulse {
 			}
 		}
 	}
-	APM_D static double accum(double acc, const Prep & q, double freq, double d) {
+	typedef ModelPulseVrot::Acc Acc; // sum of d r, product of r (see there)
+	APM_D static Acc acc_zero() { return ModelPulseVrot::acc_zero(); }
+	APM_D static Acc acc_merge(const Acc & a, const Acc & b) { return ModelPulseVrot::acc_merge(a, b); }
+	APM_D static double acc_value(const Acc & a) { return ModelPulseVrot::acc_value(a); }
+	APM_D static Acc accum(const Acc & acc, const Prep & q, double freq, double d) {
 		double y = 0;
 #pragma unroll
 		for (int j = 0; j < (APM_MAX_PAR - 2) / 2; j++) {
 			if (j < q.n_modes)
 				y += ModelPulseVrot::lorentz(q.f[j] - freq, q.lifetime, q.h[j]);
 		}
-		return acc + (log(y) + d / y);
+		Acc o = acc;
+		o.sum = acc.sum + (log(y) + d / y);
+		return o;
 	}
 	// one division for any number of modes: P_j / Q_j = sum_{i <= j} h_i / d_i by the recurrence
 	// P <- P d_j + h_j Q, Q <- Q d_j (all terms positive), then -log(Q / P) + d (Q / P) as in pulse_vrot
-	APM_D static double accum_fast(double acc, const Prep & q, double freq, double d) {
+	APM_D static Acc accum_fast(const Acc & acc, const Prep & q, double freq, double d) {
 		const double tw = APM_TWO_PI * q.lifetime;
 		double P = 0.0, Q = 1.0;
 #pragma unroll
@@ -304,8 +350,7 @@ struct ModelPulse {
 				Q = Q * dj;
 			}
 		}
-		const double r = div_pos(Q, P);
-		return acc + fma(d, r, -log_pos(r));
+		return ModelPulseVrot::acc_add_row(acc, d, div_pos(Q, P));
 	}
 	APM_D static bool fast_ok(const Prep & q, double xub) {
 		double fmax = 0.0;
