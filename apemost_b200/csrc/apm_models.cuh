@@ -197,8 +197,14 @@ struct ModelNormal {
 };
 
 // ---- apps/pulse_vrot.c:12-65 ----------------------------------------------------------------
+#ifndef APM_PV_C
+#define APM_PV_C 4 /* register tile of the likelihood kernel for pulse_vrot (overridable for sweeps) */
+#endif
+#ifndef APM_PV_U
+#define APM_PV_U 1
+#endif
 struct ModelPulseVrot {
-	static constexpr int LL_C = 4, LL_U = 1;
+	static constexpr int LL_C = APM_PV_C, LL_U = APM_PV_U;
 	static constexpr int NPAR = 7, NCOLS = 2;
 	static constexpr bool HAS_DATA = true, HAS_PRIOR = true;
 	static constexpr int ROW_W = 2;
