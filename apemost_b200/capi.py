@@ -326,6 +326,10 @@ class Engine(EngineBase):
     def last_path(self):
         return int(self._lib.apm_gpu_last_path(self._h))
 
+    def set_timing(self, per_launch=True):
+        """per-launch CUDA events on the tiled path (and no CUDA graph): see apm_gpu_set_timing"""
+        self._check(self._lib.apm_gpu_set_timing(self._h, C.c_int(int(bool(per_launch)))))
+
     def last_kernel_ms(self):
         a, n, t = C.c_double(), C.c_longlong(), C.c_double()
         self._check(self._lib.apm_gpu_last_kernel_ms(self._h, C.byref(a), C.byref(n), C.byref(t)))

@@ -112,6 +112,10 @@ struct DevState {
 	// trace of the current run
 	double * tr_prob, *tr_dl, *tr_params;
 	int tr_prob_every, tr_params_chains, tr_dumped;
+	// tiled path: the run's step counter lives on the device, so that a whole round of launches can be
+	// replayed as a CUDA graph without any per-step argument from the host.  run_ctr[0] = steps recorded
+	// so far in this apm_gpu_run call, run_ctr[1] = the control kernel's "blocks done" ticket.
+	unsigned long long * run_ctr;
 };
 
 // global number of chain g = its random stream (independent of how chains are spread over
@@ -123,9 +127,11 @@ APM_D uint32_t chain_rng_id(const DevState & S, int g) {
 // ---- proposal: reference src/markov_chain.c:226-270 (do_step_for) ------------------------
 // Kept out of line: Philox + log + sqrt + cos, called from several places of the fused / cluster
 // kernels, would otherwise be inlined into (and bloat) their step loops.
+// (first_attempt > 0: the caller has tried the attempts before it -- all outside the bounds of a
+// parameter that is not circular -- and the redraws carry on from there)
 __device__ __noinline__ double propose_coordinate_core(u64 seed, uint32_t id, u64 ctr, int i, double old_value,
-		double step, int proposal, bool wrap, double mn, double mx) {
-	unsigned attempt = 0;
+		double step, int proposal, bool wrap, double mn, double mx, unsigned first_attempt = 0) {
+	unsigned attempt = first_attempt;
 	double u0, u1, new_value;
 	philox_uniforms(seed, id, ctr, PURPOSE_JUMP, (uint32_t) i, attempt++, u0, u1);
 	new_value = old_value + jump_from_uniforms(proposal, step, u0, u1);
@@ -145,9 +151,9 @@ __device__ __noinline__ double propose_coordinate_core(u64 seed, uint32_t id, u6
 }
 
 APM_D double propose_coordinate(const DevState & S, int g, u64 ctr, int i, double old_value,
-		double step) {
+		double step, unsigned first_attempt = 0) {
 	return propose_coordinate_core(S.seed, chain_rng_id(S, g), ctr, i, old_value, step, S.proposal,
-			(S.circular_mask >> i) & 1u, S.pmin[i], S.pmax[i]);
+			(S.circular_mask >> i) & 1u, S.pmin[i], S.pmax[i], first_attempt);
 }
 
 // do_step (:272-277) / do_step_for for the pending kind; writes S.prop[g]
@@ -197,18 +203,13 @@ APM_D void chain_reset_accept_rejects(const DevState & S, int g) {
 // is known: set_prior/set_prob, check_accept (:282-311), bookkeeping.
 // `pre_logu`, when given, is log(u0) of this step's accept draw, computed ahead of time by another
 // warp from the same counter (the draw depends on the chain's id and step counter only).
-template<class M>
-APM_D void chain_finalize(const DevState & S, int g, double sum, const double * pre_logu = nullptr) {
+// (chain_finalize_value: the same from the point where the proposal's prob and prior are known)
+APM_D void chain_finalize_value(const DevState & S, int g, double prob_new, double prior_new, const double * pre_logu) {
 	const int n = S.n_par;
 	const int kind = S.pend[g];
 	const double * q = S.prop + (size_t) g * n;
 	double * p = S.params + (size_t) g * n;
 	const double prob_old = S.prob[g];
-	const double prior_old = S.prior[g];
-	double prior_new = prior_old;
-	if (M::HAS_PRIOR)
-		prior_new = M::prior(q, n, S.model_const);
-	const double prob_new = M::finish(S.beta[g], sum, prior_new, q, S.model_const);
 	int accepted;
 	if (prob_new == prob_old)
 		accepted = 1;
@@ -255,6 +256,15 @@ APM_D void chain_finalize(const DevState & S, int g, double sum, const double * 
 	S.pend[g] = PEND_NONE;
 }
 
+template<class M>
+APM_D void chain_finalize(const DevState & S, int g, double sum, const double * pre_logu = nullptr) {
+	const double * q = S.prop + (size_t) g * S.n_par;
+	double prior_new = S.prior[g];
+	if (M::HAS_PRIOR)
+		prior_new = M::prior(q, S.n_par, S.model_const);
+	chain_finalize_value(S, g, M::finish(S.beta[g], sum, prior_new, q, S.model_const), prior_new, pre_logu);
+}
+
 // the bookkeeping of one sampler iteration after the step (reference
 // src/parallel_tempering.c:396-401): check_best, append (n_iter++), the prob-chain
 // line and the parameter dump, plus the on-device accumulators
@@ -283,6 +293,55 @@ APM_D void chain_record(const DevState & S, int g, long long step_index) {
 	S.stat_sum_dl[g] += dl;
 	for (int i = 0; i < n; i++) {
 		double v = S.params[(size_t) g * n + i];
+		S.stat_sum_p[(size_t) g * n + i] += v;
+		S.stat_sum_p2[(size_t) g * n + i] += v * v;
+	}
+}
+
+// chain_finalize_value's state transition + chain_record for a FULL step whose outcome was decided
+// elsewhere (free_run_kernel: the lanes that play a chain hand each step's outcome to a
+// book-keeping thread, which writes it down one batch behind).  The chain's point after the step
+// (params_after, prob_after, prior_after) comes with the outcome; S.params / S.prob / S.prior
+// belong to the deciding lanes and are not touched here.
+APM_D void chain_book_step(const DevState & S, int g, int accepted, double prob_after, double prior_after,
+		const double * params_after, long long step_index) {
+	const int n = S.n_par;
+	if (accepted) {
+		S.accept[g]++;
+		for (int i = 0; i < n; i++)
+			S.pacc[(size_t) g * n + i]++;
+	} else {
+		S.reject[g]++;
+		for (int i = 0; i < n; i++)
+			S.prej[(size_t) g * n + i]++;
+	}
+	S.rng_ctr[g]++;
+	if (prob_after > S.prob_best[g]) { // mcmc_check_best
+		S.prob_best[g] = prob_after;
+		for (int i = 0; i < n; i++)
+			S.params_best[(size_t) g * n + i] = params_after[i];
+	}
+	S.n_iter[g]++;
+	const double dl = prob_after - prior_after;
+	if (S.tr_prob_every > 0 && S.tr_prob != nullptr && step_index % S.tr_prob_every == 0) {
+		long long row = step_index / S.tr_prob_every;
+		S.tr_prob[row * S.n_chains + g] = prob_after;
+		S.tr_dl[row * S.n_chains + g] = dl;
+	}
+	if (S.tr_params != nullptr) {
+		int slot = -1;
+		if (S.tr_params_chains == 2)
+			slot = g;
+		else if (S.tr_params_chains == 1 && S.k_offset + g % S.n_beta == 0)
+			slot = g / S.n_beta;
+		if (slot >= 0)
+			for (int i = 0; i < n; i++)
+				S.tr_params[((size_t) step_index * S.tr_dumped + slot) * n + i] = params_after[i];
+	}
+	S.stat_n[g]++;
+	S.stat_sum_dl[g] += dl;
+	for (int i = 0; i < n; i++) {
+		const double v = params_after[i];
 		S.stat_sum_p[(size_t) g * n + i] += v;
 		S.stat_sum_p2[(size_t) g * n + i] += v * v;
 	}

@@ -87,6 +87,8 @@ struct apm_gpu {
 	int tr_dumped = 0;
 	// calibration
 	unsigned char * d_select = nullptr;
+	int * d_sel_idx = nullptr;          // the selected chains, compacted (warp-group calibration kernel)
+	std::vector<int> sel_idx;           // host copy, filled by apm_gpu_calibrate / apm_gpu_steps
 	// timing / introspection
 	long long launches = 0;
 	std::vector<cudaEvent_t> ev;
@@ -102,6 +104,11 @@ struct apm_gpu {
 	bool ladder = false;
 	double * d_pack_first = nullptr, *d_pack_last = nullptr, *d_pack_prev = nullptr, *d_pack_next = nullptr;
 	std::vector<unsigned long long> host_draws; // per chain: uniforms handed out by apm_gpu_host_uniform
+	// tiled path: one round (n_swap x {likelihood, control} launches) as an instantiated CUDA graph,
+	// rebuilt only when something baked into the launches changes (the key = the bytes of the arguments)
+	cudaGraphExec_t round_graph = nullptr;
+	std::vector<unsigned char> round_graph_key;
+	int per_launch_timing = 0;          // 1: per-launch CUDA events (and no graph): apm_gpu_set_timing
 	std::string err;
 };
 
@@ -132,22 +139,41 @@ static cudaError_t dalloc(T ** p, size_t n) {
 }
 
 // ------------------------------------------------------------------ model dispatch
+#ifdef APM_ONLY_MODEL
+template<int ID> struct OnlyModel;
+template<> struct OnlyModel<APM_MODEL_SIMPLESIN> { typedef ModelSimplesin type; };
+template<> struct OnlyModel<APM_MODEL_SIMPLESIN5> { typedef ModelSimplesin5 type; };
+template<> struct OnlyModel<APM_MODEL_SIMPLESIN2> { typedef ModelSimplesin2 type; };
+template<> struct OnlyModel<APM_MODEL_NORMAL> { typedef ModelNormal type; };
+template<> struct OnlyModel<APM_MODEL_PULSE_VROT> { typedef ModelPulseVrot type; };
+template<> struct OnlyModel<APM_MODEL_PULSE> { typedef ModelPulse type; };
+template<> struct OnlyModel<APM_MODEL_BERNOULLI> { typedef ModelBernoulli type; };
+typedef OnlyModel<APM_ONLY_MODEL>::type APM_ONLY_MODEL_T;
+#endif
 #ifdef APM_USER_MODEL_HEADER
 #define APM_USER_CASE(FN, ...) case APM_MODEL_USER: return FN<UserModel>(__VA_ARGS__);
 #else
 #define APM_USER_CASE(FN, ...)
 #endif
+// (-DAPM_ONLY_MODEL=<id>: a build with one model's kernels only -- seconds instead of minutes, for
+// kernel experiments under build_variants/; the product library carries all of them)
+#ifdef APM_ONLY_MODEL
+#define APM_CASE(ID, MODEL, FN, ...) case ID: if (ID == APM_ONLY_MODEL) return FN<std::conditional_t<ID == APM_ONLY_MODEL, MODEL, APM_ONLY_MODEL_T>>(__VA_ARGS__); break;
+#else
+#define APM_CASE(ID, MODEL, FN, ...) case ID: return FN<MODEL>(__VA_ARGS__);
+#endif
 #define DISPATCH(model_id, FN, ...) \
 	switch (model_id) { \
-	case APM_MODEL_SIMPLESIN: return FN<ModelSimplesin>(__VA_ARGS__); \
-	case APM_MODEL_SIMPLESIN5: return FN<ModelSimplesin5>(__VA_ARGS__); \
-	case APM_MODEL_SIMPLESIN2: return FN<ModelSimplesin2>(__VA_ARGS__); \
-	case APM_MODEL_NORMAL: return FN<ModelNormal>(__VA_ARGS__); \
-	case APM_MODEL_PULSE_VROT: return FN<ModelPulseVrot>(__VA_ARGS__); \
-	case APM_MODEL_PULSE: return FN<ModelPulse>(__VA_ARGS__); \
-	case APM_MODEL_BERNOULLI: return FN<ModelBernoulli>(__VA_ARGS__); \
+	APM_CASE(APM_MODEL_SIMPLESIN, ModelSimplesin, FN, __VA_ARGS__) \
+	APM_CASE(APM_MODEL_SIMPLESIN5, ModelSimplesin5, FN, __VA_ARGS__) \
+	APM_CASE(APM_MODEL_SIMPLESIN2, ModelSimplesin2, FN, __VA_ARGS__) \
+	APM_CASE(APM_MODEL_NORMAL, ModelNormal, FN, __VA_ARGS__) \
+	APM_CASE(APM_MODEL_PULSE_VROT, ModelPulseVrot, FN, __VA_ARGS__) \
+	APM_CASE(APM_MODEL_PULSE, ModelPulse, FN, __VA_ARGS__) \
+	APM_CASE(APM_MODEL_BERNOULLI, ModelBernoulli, FN, __VA_ARGS__) \
 	APM_USER_CASE(FN, __VA_ARGS__) \
-	default: return fail(h, APM_EINVAL, "unknown model id %d", model_id); }
+	default: break; } \
+	return fail(h, APM_EINVAL, "unknown model id %d (or not in this build)", model_id);
 
 template<class M> static int model_npar_t(apm_gpu *) { return M::NPAR; }
 template<class M> static int model_ncols_t(apm_gpu *) { return M::HAS_DATA ? M::NCOLS : 0; } // -1: one per parameter
@@ -186,8 +212,12 @@ static int configure_kernels(apm_gpu * h) {
 		return fail(h, APM_ECUDA, "likelihood kernel does not fit on an SM");
 	h->ll_grid = h->sm_count * occ;
 	const int fused_smem = (int) FUSED_SMEM_LIMIT;
-	CU(cudaFuncSetAttribute(fused_run_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
+	if constexpr (M::HAS_DATA)
+		CU(cudaFuncSetAttribute(fused_run_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
+	else
+		CU(cudaFuncSetAttribute(free_run_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
 	CU(cudaFuncSetAttribute(fused_calibrate_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
+	CU(cudaFuncSetAttribute(group_calibrate_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
 	CU(cudaFuncSetAttribute(cluster_run_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
 	CU(cudaFuncSetAttribute(grid_run_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
 	CU(cudaFuncSetAttribute(grid_calibrate_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem));
@@ -264,8 +294,8 @@ extern "C" int apm_gpu_create(apm_gpu ** out, const apm_gpu_config * cfg) {
 		A(S.pmin, np); A(S.pmax, np); A(S.pend, n);
 		A(S.stat_n, n); A(S.stat_sum_dl, n); A(S.stat_sum_p, nv); A(S.stat_sum_p2, nv);
 		A(S.cal, n); A(S.progress_n, 1); A(S.n_active, 1);
-		A(h->d_select, n); A(h->d_shard_sum, n); A(h->d_xabsmax, 1);
-		A(S.act_idx, 2 * n); A(S.act_n, 2);
+		A(h->d_select, n); A(h->d_sel_idx, n); A(h->d_shard_sum, n); A(h->d_xabsmax, 1);
+		A(S.act_idx, 2 * n); A(S.act_n, 2); A(S.run_ctr, 2);
 #undef A
 		if (e != cudaSuccess) {
 			rc = fail(nullptr, APM_ENOMEM, "device allocation failed: %s", cudaGetErrorString(e));
@@ -304,7 +334,7 @@ extern "C" int apm_gpu_destroy(apm_gpu * h) {
 	void * ptrs[] = { S.params, S.params_best, S.steps, S.prop, S.prob, S.prior, S.prob_best, S.beta,
 			S.accept, S.reject, S.pacc, S.prej, S.n_iter, S.swapcount, S.rng_ctr, S.swap_round, S.pmin,
 			S.pmax, S.pend, S.partial, S.stat_n, S.stat_sum_dl, S.stat_sum_p, S.stat_sum_p2, S.cal,
-			S.progress, S.progress_n, S.n_active, S.act_idx, S.act_n, h->d_select, h->d_shard_sum,
+			S.progress, S.progress_n, S.n_active, S.act_idx, S.act_n, S.run_ctr, h->d_select, h->d_sel_idx, h->d_shard_sum,
 			h->d_pack_first, h->d_pack_last, h->d_pack_prev, h->d_pack_next, h->d_grid_partials, h->d_grid_draws, h->d_grid_active,
 			h->d_xabsmax, h->d_data, h->d_tr_prob, h->d_tr_dl, h->d_tr_params };
 	for (void * p : ptrs)
@@ -312,6 +342,8 @@ extern "C" int apm_gpu_destroy(apm_gpu * h) {
 			cudaFree(p);
 	for (cudaEvent_t e : h->ev)
 		cudaEventDestroy(e);
+	if (h->round_graph)
+		cudaGraphExecDestroy(h->round_graph);
 	if (h->comm && g_nccl.CommDestroy)
 		g_nccl.CommDestroy(h->comm);
 	if (h->stream)
@@ -749,7 +781,7 @@ static int choose_path(apm_gpu * h, int * path, bool for_run = false) {
 		return has_data;
 	const long long n_slots = has_data ? h->n_rows * (model_row_w(h, h->cfg.model_id) / 2) : 0; // 16-byte units
 	const size_t need = fused_table_bytes(n_slots) + fused_state_bytes(h->cfg.n_beta, h->cfg.n_par)
-			+ fused_draws_bytes(h->cfg.n_beta);
+			+ fused_draws_bytes(h->cfg.n_beta, has_data != 0);
 	const bool fits = need <= FUSED_SMEM_LIMIT && (!has_data || h->n_rows < (1ll << 24));
 	const bool rows_ok = !has_data || h->n_rows < (1ll << 24);
 	const int cl = for_run && rows_ok ? cluster_size_for(h, has_data != 0) : 0;
@@ -792,15 +824,35 @@ static int choose_path(apm_gpu * h, int * path, bool for_run = false) {
 	return APM_OK;
 }
 
+// warp-group calibration (group_calibrate_kernel): chains a CTA works on at a time for n_sel selected
+// chains, 0 = the kernel does not apply (data-free model, sharded likelihood, table + states do not
+// fit in shared memory, or so many chains that a group would be a single warp: the fused kernel's case)
+static int group_calibrate_ng(const apm_gpu * h, bool has_data, int n_sel) {
+	if (!has_data || h->comm || n_sel < 1 || h->n_rows >= (1ll << 24))
+		return 0;
+	if (getenv("APM_NO_GROUP_CALIBRATE"))
+		return 0;
+	const int per_cta = (n_sel + h->sm_count - 1) / h->sm_count;
+	if (per_cta > GROUP_MAX)
+		return 0;
+	int ng = 1;
+	while (ng < per_cta)
+		ng *= 2;
+	const long long n_slots = h->n_rows * (model_row_w(const_cast<apm_gpu *>(h), h->cfg.model_id) / 2);
+	if (fused_table_bytes(n_slots) + (size_t) ng * group_state_bytes(h->cfg.n_par) > FUSED_SMEM_LIMIT)
+		return 0;
+	return ng;
+}
+
 static void fused_geometry(const apm_gpu * h, bool has_data, int * threads, size_t * smem, FusedArgs * a) {
 	if (has_data) { // a warp per chain, the ladder dealt evenly over as few passes as possible
 		const int passes = (h->cfg.n_beta + FUSED_MAX_WARPS - 1) / FUSED_MAX_WARPS;
 		*threads = 32 * ((h->cfg.n_beta + passes - 1) / passes);
-	} else {        // a thread per chain
+	} else {        // free_run_kernel: groups of lanes per chain + warps that draw ahead; calibration: a thread per chain
 		*threads = std::min(FUSED_MAX_WARPS * 32, 32 * ((h->cfg.n_beta + 31) / 32));
 	}
 	*smem = fused_table_bytes(has_data ? h->n_rows * (model_row_w(const_cast<apm_gpu *>(h), h->cfg.model_id) / 2) : 0)
-			+ fused_state_bytes(h->cfg.n_beta, h->cfg.n_par) + fused_draws_bytes(h->cfg.n_beta);
+			+ fused_state_bytes(h->cfg.n_beta, h->cfg.n_par) + fused_draws_bytes(h->cfg.n_beta, has_data);
 	memset(a, 0, sizeof(*a));
 	a->data = has_data ? h->d_data : nullptr;
 	a->n_rows = has_data ? (int) h->n_rows : 0;
@@ -818,7 +870,10 @@ static int run_fused_t(apm_gpu * h, long long n_rounds, int n_swap) {
 	h->ev_used = 0;
 	cudaEvent_t t0 = next_event(h), t1 = next_event(h);
 	CU(cudaEventRecord(t0, h->stream));
-	fused_run_kernel<M><<<h->cfg.n_ensembles, threads, smem, h->stream>>>(h->S, a);
+	if constexpr (M::HAS_DATA)
+		fused_run_kernel<M><<<h->cfg.n_ensembles, threads, smem, h->stream>>>(h->S, a);
+	else
+		free_run_kernel<M><<<h->cfg.n_ensembles, FREE_THREADS, smem, h->stream>>>(h->S, a);
 	h->launches++;
 	CU(cudaEventRecord(t1, h->stream));
 	CU(cudaStreamSynchronize(h->stream));
@@ -975,28 +1030,18 @@ static int setup_trace(apm_gpu * h, long long n_steps, const apm_gpu_trace_cfg *
 	return APM_OK;
 }
 
+// one round of the tiled path on the engine's stream: n_swap x {likelihood of every pending proposal,
+// control kernel: finalise + record (+ the ensemble's swap after the round's last step) + next proposals}
 template<class M>
-static int run_tiled_t(apm_gpu * h, long long n_rounds, int n_swap) {
-	const long long total = n_rounds * n_swap;
+static int enqueue_round(apm_gpu * h, int n_swap, bool timed) {
 	AdvArgs a;
 	memset(&a, 0, sizeof(a));
-	int rc0 = replan(h, h->n_chains);
-	if (rc0 != APM_OK)
-		return rc0;
-	h->ev_used = 0;
-	cudaEvent_t t0 = next_event(h), t1 = next_event(h);
-	// ev[0], ev[1] are the run brackets; pairs from ev[2] on are likelihood launches
-	CU(cudaEventRecord(t0, h->stream));
-	a.flags = ADV_PROPOSE_RUN;
-	advance_kernel<M><<<h->cfg.n_ensembles, ADV_THREADS, 0, h->stream>>>(state_for_advance(h), a);
-	h->launches++;
-	for (long long step = 0; step < total; step++) {
-		int rc = step_likelihood<M>(h, true);
+	for (int sub = 0; sub < n_swap; sub++) {
+		int rc = step_likelihood<M>(h, timed);
 		if (rc != APM_OK)
 			return rc;
-		const bool swap_now = (step + 1) % n_swap == 0;
+		const bool swap_now = sub + 1 == n_swap;
 		a.flags = ADV_FINALIZE | ADV_RECORD;
-		a.step_index = step;
 		if (swap_now && h->ladder) {
 			// the pair may straddle two GPUs: finish the step, trade the boundary chains with the
 			// neighbours, then swap + propose with their copies at hand
@@ -1011,10 +1056,81 @@ static int run_tiled_t(apm_gpu * h, long long n_rounds, int n_swap) {
 		}
 		if (swap_now)
 			a.flags |= ADV_SWAP;
-		if (step + 1 < total)
-			a.flags |= ADV_PROPOSE_RUN;
+		// (the proposal drawn after a call's last step is drawn again, from the same counter, by the
+		// next call's first launch: a round is the same sequence of launches wherever it stands)
+		a.flags |= ADV_PROPOSE_RUN;
 		advance_kernel<M><<<h->cfg.n_ensembles, ADV_THREADS, 0, h->stream>>>(state_for_advance(h), a);
 		h->launches++;
+	}
+	return APM_OK;
+}
+
+template<class M>
+static int run_tiled_t(apm_gpu * h, long long n_rounds, int n_swap) {
+	AdvArgs a;
+	memset(&a, 0, sizeof(a));
+	int rc0 = replan(h, h->n_chains);
+	if (rc0 != APM_OK)
+		return rc0;
+	h->ev_used = 0;
+	cudaEvent_t t0 = next_event(h), t1 = next_event(h);
+	// ev[0], ev[1] are the run brackets; pairs from ev[2] on are likelihood launches (per-launch timing)
+	CU(cudaEventRecord(t0, h->stream));
+	CU(cudaMemsetAsync(h->S.run_ctr, 0, 2 * sizeof(unsigned long long), h->stream));
+	a.flags = ADV_PROPOSE_RUN;
+	advance_kernel<M><<<h->cfg.n_ensembles, ADV_THREADS, 0, h->stream>>>(state_for_advance(h), a);
+	h->launches++;
+	// Without per-launch timing and without a communicator in the step, a round is replayed as a
+	// CUDA graph: 2 n_swap launches for one cudaGraphLaunch, nothing for the host to do per step.
+	const bool use_graph = !h->per_launch_timing && !h->comm && getenv("APM_NO_GRAPH") == nullptr;
+	if (use_graph) {
+		// everything the captured launches carry by value: the device state struct (pointers, trace
+		// configuration, adapt settings), the likelihood plan and table geometry, the round's length
+		std::vector<unsigned char> key(sizeof(DevState) + 6 * sizeof(long long));
+		const DevState S_now = state_for_advance(h);
+		const long long extra[6] = { (long long) n_swap, (long long) h->plan_splits, (long long) h->plan_cps,
+				h->n_rows, (long long) h->n_chunks, (long long) (size_t) h->d_data };
+		memcpy(key.data(), &S_now, sizeof(DevState));
+		memcpy(key.data() + sizeof(DevState), extra, sizeof(extra));
+		if (h->round_graph == nullptr || key != h->round_graph_key) {
+			if (h->round_graph) {
+				cudaGraphExecDestroy(h->round_graph);
+				h->round_graph = nullptr;
+			}
+			cudaGraph_t graph = nullptr;
+			const long long launches_before = h->launches;
+			CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+			int rc = enqueue_round<M>(h, n_swap, false);
+			cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+			h->launches = launches_before; // captured, not launched
+			if (rc != APM_OK) {
+				if (graph)
+					cudaGraphDestroy(graph);
+				return rc;
+			}
+			if (ce != cudaSuccess)
+				return fail(h, APM_ECUDA, "capturing a round failed: %s", cudaGetErrorString(ce));
+			ce = cudaGraphInstantiate(&h->round_graph, graph, 0);
+			cudaGraphDestroy(graph);
+			if (ce != cudaSuccess) {
+				h->round_graph = nullptr;
+				return fail(h, APM_ECUDA, "instantiating the round graph failed: %s", cudaGetErrorString(ce));
+			}
+			h->round_graph_key = key;
+		}
+		const long long per_round = (M::HAS_DATA ? 2ll : 1ll) * n_swap;
+		for (long long round = 0; round < n_rounds; round++) {
+			CU(cudaGraphLaunch(h->round_graph, h->stream));
+			h->launches += per_round;
+		}
+	} else {
+		for (long long round = 0; round < n_rounds; round++) {
+			int rc = enqueue_round<M>(h, n_swap, h->per_launch_timing != 0);
+			if (rc != APM_OK) {
+				cudaStreamSynchronize(h->stream); // nothing of this call may still be in flight
+				return rc;
+			}
+		}
 	}
 	CU(cudaEventRecord(t1, h->stream));
 	CU(cudaStreamSynchronize(h->stream));
@@ -1110,7 +1226,30 @@ static int calibrate_t(apm_gpu * h, const apm_gpu_calib_cfg * cfg, int * status,
 	int rcp = choose_path(h, &path);
 	if (rcp != APM_OK)
 		return rcp;
-	if (path == APM_PATH_FUSED) {
+	// few selected chains and the table in shared memory: warp groups per chain, the chains dealt
+	// out over the SMs (AUTO, or asked for as APM_PATH_CLUSTER); otherwise a warp per chain
+	const int ng = (path == APM_PATH_FUSED && h->cfg.path != APM_PATH_FUSED) ? group_calibrate_ng(h, M::HAS_DATA, n_selected) : 0;
+	if (ng > 0) {
+		if constexpr (M::HAS_DATA) {
+			int threads = 0;
+			size_t smem = 0;
+			GroupArgs ga;
+			fused_geometry(h, true, &threads, &smem, &ga.f);
+			ga.f.cal = a.cal;
+			ga.f.select = h->d_select;
+			ga.sel_idx = h->d_sel_idx;
+			ga.n_sel = n_selected;
+			ga.ng = ng;
+			CU(cudaMemcpyAsync(h->d_sel_idx, h->sel_idx.data(), (size_t) n_selected * sizeof(int), cudaMemcpyHostToDevice,
+					h->stream));
+			const int grid = std::min(n_selected, h->sm_count);
+			smem = fused_table_bytes(h->n_rows * (M::ROW_W / 2)) + (size_t) ng * group_state_bytes(h->cfg.n_par);
+			group_calibrate_kernel<M><<<grid, FUSED_MAX_WARPS * 32, smem, h->stream>>>(h->S, ga);
+			h->launches++;
+		}
+		n_selected = 0;
+		path = APM_PATH_CLUSTER;
+	} else if (path == APM_PATH_FUSED) {
 		int threads = 0;
 		size_t smem = 0;
 		FusedArgs f;
@@ -1230,8 +1369,12 @@ extern "C" int apm_gpu_calibrate(apm_gpu * h, const unsigned char * select, cons
 		h->S.progress_cap = progress_capacity;
 	}
 	int n_selected = 0;
-	for (unsigned char c : sel)
-		n_selected += c != 0;
+	h->sel_idx.clear();
+	for (int g = 0; g < h->n_chains; g++)
+		if (sel[g]) {
+			n_selected++;
+			h->sel_idx.push_back(g);
+		}
 	auto go = [&]() -> int { DISPATCH(h->cfg.model_id, calibrate_t, h, cfg, status, n_selected, 0, 0) };
 	int rc = go();
 	if (rc != APM_OK && rc != APM_ECALIB)
@@ -1276,8 +1419,12 @@ extern "C" int apm_gpu_steps(apm_gpu * h, const unsigned char * select, int kind
 	h->S.progress = nullptr;
 	h->S.progress_cap = 0;
 	int n_selected = 0;
-	for (unsigned char c : sel)
-		n_selected += c != 0;
+	h->sel_idx.clear();
+	for (int g = 0; g < h->n_chains; g++)
+		if (sel[g]) {
+			n_selected++;
+			h->sel_idx.push_back(g);
+		}
 	const size_t log_bytes = (size_t) n_steps * h->n_chains;
 	unsigned char * d_log = nullptr;
 	CU(cudaMalloc((void **) &d_log, log_bytes));
@@ -1419,6 +1566,13 @@ extern "C" int apm_gpu_last_kernel_ms(const apm_gpu * h, double * loglik_ms, lon
 }
 
 extern "C" int apm_gpu_last_path(const apm_gpu * h) { return h ? h->last_path : 0; }
+
+extern "C" int apm_gpu_set_timing(apm_gpu * h, int per_launch) {
+	if (!h)
+		return APM_EINVAL;
+	h->per_launch_timing = per_launch ? 1 : 0;
+	return APM_OK;
+}
 
 extern "C" int apm_gpu_measure_fp64_peak(int device, double seconds, double * instr_per_s) {
 	apm_gpu * h = nullptr;

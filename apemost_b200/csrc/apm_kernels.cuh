@@ -359,7 +359,6 @@ enum {
 
 struct AdvArgs {
 	int flags;
-	long long step_index;
 	CalibCfgDev cal;
 	const unsigned char * select; // calibration selection (ADV_CALIB_BEGIN)
 	int act_w;                    // calibration: which active-list buffer this launch fills
@@ -412,6 +411,9 @@ __global__ void __launch_bounds__(ADV_THREADS) advance_kernel(const DevState S, 
 	}
 	if ((a.flags & ADV_CALIB) && blockIdx.x == 0 && threadIdx.x == 0)
 		S.act_n[1 - a.act_w] = 0; // consumed by the likelihood launch before this one
+	// the step of the run this launch records (the same for every block: the counter moves when
+	// the LAST block of the launch is done, see the end of the kernel)
+	const long long step_index = (a.flags & ADV_RECORD) ? (long long) *(volatile unsigned long long *) S.run_ctr : 0;
 	if (a.flags & ADV_FINALIZE) {
 		for (int k = threadIdx.x; k < S.n_beta; k += blockDim.x) {
 			const int g = base + k;
@@ -419,7 +421,7 @@ __global__ void __launch_bounds__(ADV_THREADS) advance_kernel(const DevState S, 
 				continue;
 			chain_finalize<M>(S, g, chain_gather_sum<M>(S, g));
 			if (a.flags & ADV_RECORD)
-				chain_record(S, g, a.step_index);
+				chain_record(S, g, step_index);
 			if (a.flags & ADV_CALIB) {
 				cal_after_step(S, g, a.cal);
 				int kind = cal_next_kind(S, g);
@@ -442,6 +444,19 @@ __global__ void __launch_bounds__(ADV_THREADS) advance_kernel(const DevState S, 
 		__syncthreads();
 		for (int k = threadIdx.x; k < S.n_beta; k += blockDim.x)
 			chain_propose(S, base + k, S.n_par);
+	}
+	if (a.flags & ADV_RECORD) {
+		// every block has read the counter by the time it takes its ticket; the last one advances it
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			__threadfence();
+			const unsigned long long t = atomicAdd(S.run_ctr + 1, 1ull);
+			if (t == gridDim.x - 1) {
+				S.run_ctr[1] = 0;
+				S.run_ctr[0] = (unsigned long long) step_index + 1;
+				__threadfence();
+			}
+		}
 	}
 }
 
@@ -497,8 +512,10 @@ __host__ __device__ inline size_t fused_state_bytes(int n_beta, int n_par) {
 }
 // (n_slots = table rows x ROW_W / 2: 16-byte units)
 // fused_run_kernel: per chain a batch of random draws (32 doubles) and its base counter
-__host__ __device__ inline size_t fused_draws_bytes(int n_beta) {
-	return (size_t) n_beta * (32 * sizeof(double) + sizeof(unsigned long long));
+// (data-free models, free_run_kernel: two such batches, one being drawn while the other is used, and
+// two batches of step outcomes, each of at most 64 doubles per chain)
+__host__ __device__ inline size_t fused_draws_bytes(int n_beta, bool has_data = true) {
+	return (size_t) n_beta * ((has_data ? 32 : 128 + 128) * sizeof(double) + sizeof(unsigned long long));
 }
 __host__ __device__ inline size_t fused_table_bytes(long long n_slots) {
 	return (((size_t) n_slots * 16 + 127) & ~(size_t) 127) + 16 /* mbarrier */;
@@ -541,14 +558,17 @@ __device__ __forceinline__ const Row<M> * fused_stage_table(const FusedArgs & a,
 // S.n_beta); the returned DevState addresses the copies with chain index = position in the block
 // and carries the ladder-split fields (n_beta_total, k_offset) that make chain ids, swap pairs
 // and trace slots those of the whole ladder
-__device__ inline DevState fused_localize_block(const DevState & S, int ens, int k0, int nb, unsigned char * mem) {
+// (the copy is made by the `nthr` threads numbered tid = 0 .. nthr - 1 -- a CTA, a warp -- and is
+// complete for them once they have synchronised among themselves)
+__device__ inline DevState fused_localize_block_by(const DevState & S, int ens, int k0, int nb, unsigned char * mem,
+		int tid, int nthr) {
 	DevState L = S;
 	const int n = S.n_par;
 	const size_t base = (size_t) ens * S.n_beta + k0;
 	size_t off = 0;
 #define X(name, type, width) { \
 		type * p = reinterpret_cast<type *>(mem + off); \
-		for (int i = threadIdx.x; i < nb * (width); i += blockDim.x) \
+		for (int i = tid; i < nb * (width); i += nthr) \
 			p[i] = S.name[base * (width) + i]; \
 		L.name = p; \
 		off += sizeof(type) * (size_t) nb * (width); }
@@ -558,21 +578,21 @@ __device__ inline DevState fused_localize_block(const DevState & S, int ens, int
 		constexpr int W = sizeof(CalState) / 8;
 		u64 * p = reinterpret_cast<u64 *>(mem + off);
 		const u64 * src = reinterpret_cast<const u64 *>(S.cal + base);
-		for (int i = threadIdx.x; i < nb * W; i += blockDim.x)
+		for (int i = tid; i < nb * W; i += nthr)
 			p[i] = src[i];
 		L.cal = reinterpret_cast<CalState *>(p);
 		off += sizeof(CalState) * (size_t) nb;
 	}
 	{
 		u64 * p = reinterpret_cast<u64 *>(mem + off);
-		if (threadIdx.x == 0)
+		if (tid == 0)
 			p[0] = S.swap_round[ens];
 		L.swap_round = p;
 		off += 8;
 	}
 	{
 		int * p = reinterpret_cast<int *>(mem + off);
-		for (int i = threadIdx.x; i < nb; i += blockDim.x)
+		for (int i = tid; i < nb; i += nthr)
 			p[i] = S.pend[base + i];
 		L.pend = p;
 	}
@@ -590,6 +610,11 @@ __device__ inline DevState fused_localize_block(const DevState & S, int ens, int
 	}
 	if (S.tr_params != nullptr)
 		L.tr_params = S.tr_params + (S.tr_params_chains == 2 ? base : (size_t) ens) * n;
+	return L;
+}
+
+__device__ inline DevState fused_localize_block(const DevState & S, int ens, int k0, int nb, unsigned char * mem) {
+	const DevState L = fused_localize_block_by(S, ens, k0, nb, mem, threadIdx.x, blockDim.x);
 	__syncthreads();
 	return L;
 }
@@ -599,13 +624,13 @@ __device__ inline DevState fused_localize(const DevState & S, int ens, unsigned 
 }
 
 // L = what fused_localize_block returned for (ens, k0); copies its L.n_beta chains back
-__device__ inline void fused_writeback_block(const DevState & S, const DevState & L, int ens, int k0,
-		bool write_swap_round) {
+// (_by: the copying threads have synchronised among themselves before the call)
+__device__ inline void fused_writeback_block_by(const DevState & S, const DevState & L, int ens, int k0,
+		bool write_swap_round, int tid, int nthr) {
 	const int nb = L.n_beta, n = S.n_par;
 	const size_t base = (size_t) ens * S.n_beta + k0;
-	__syncthreads();
 #define X(name, type, width) \
-		for (int i = threadIdx.x; i < nb * (width); i += blockDim.x) \
+		for (int i = tid; i < nb * (width); i += nthr) \
 			S.name[base * (width) + i] = L.name[i];
 	FUSED_ARRAYS(X)
 #undef X
@@ -613,13 +638,19 @@ __device__ inline void fused_writeback_block(const DevState & S, const DevState 
 		constexpr int W = sizeof(CalState) / 8;
 		u64 * dst = reinterpret_cast<u64 *>(S.cal + base);
 		const u64 * src = reinterpret_cast<const u64 *>(L.cal);
-		for (int i = threadIdx.x; i < nb * W; i += blockDim.x)
+		for (int i = tid; i < nb * W; i += nthr)
 			dst[i] = src[i];
 	}
-	if (threadIdx.x == 0 && write_swap_round)
+	if (tid == 0 && write_swap_round)
 		S.swap_round[ens] = L.swap_round[0];
-	for (int i = threadIdx.x; i < nb; i += blockDim.x)
+	for (int i = tid; i < nb; i += nthr)
 		S.pend[base + i] = L.pend[i];
+}
+
+__device__ inline void fused_writeback_block(const DevState & S, const DevState & L, int ens, int k0,
+		bool write_swap_round) {
+	__syncthreads();
+	fused_writeback_block_by(S, L, ens, k0, write_swap_round, threadIdx.x, blockDim.x);
 }
 
 __device__ inline void fused_writeback(const DevState & S, const DevState & L, int ens) {
@@ -682,7 +713,7 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_run_kernel(cons
 	const int nb = L.n_beta, n = L.n_par;
 	const double xub = M::HAS_DATA ? *a.xabsmax : 0.0;
 	long long step = 0;
-	if (M::HAS_DATA) {
+	{ // (data-free models run free_run_kernel below)
 		// per chain: a batch of K steps' random draws (lane-parallel, chain_draw_batch) and its base counter
 		const int K = 32 / (n + 1);
 		double * draws = reinterpret_cast<double *>(fused_smem + fused_table_bytes((long long) a.n_rows * (M::ROW_W / 2))
@@ -718,31 +749,339 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_run_kernel(cons
 				ensemble_swap(L, 0);
 			__syncthreads();
 		}
-	} else {
-		for (int k = threadIdx.x; k < nb; k += blockDim.x)
-			chain_propose(L, k, n);
-		for (long long round = 0; round < a.n_rounds; round++) {
-			for (int sub = 0; sub < a.n_swap; sub++, step++) {
-				for (int k = threadIdx.x; k < nb; k += blockDim.x) {
-					chain_finalize<M>(L, k, M::sum0(L.prop + (size_t) k * n));
-					chain_record(L, k, step);
-					if (sub + 1 < a.n_swap)
-						chain_propose(L, k, n);
+	}
+	fused_writeback(S, L, ens);
+}
+
+// ------------------------------------------------------------------ data-free models
+// apps/normal.c never touches the data table: a step is Philox + log + sqrt + cos for the jump, the
+// model's closed form, Philox + log for the accept test, and the step's book-keeping -- one long
+// chain of dependent instructions per Metropolis step and nothing to stream, so what counts is
+// how little of it sits between one step's proposal and the next.  One CTA per ensemble, 1024
+// threads in three roles that work on consecutive batches of K = 32 / (n_par + 1) steps at the
+// same time (one CTA barrier per batch):
+//   * PRODUCERS draw batch b + 1: the draws depend on the chain's id and step counter only;
+//   * DECIDERS play batch b.  A model may split its evaluation into independent terms
+//     (M::LANE_TERMS, term / reduce / finish_reduced: the ten bumps of apps/normal.c): a chain then
+//     has 8 lanes instead of one thread, the terms are dealt out over them and reduced with
+//     shuffles.  Every lane of the group forms the proposal, the new prob and the accept decision
+//     redundantly (same instructions on the same inputs: same bits); the group's first lane moves
+//     the chain (params, prob, prior, best) and leaves the step's outcome in a ring;
+//   * BOOK-KEEPERS write batch b - 1 down from the ring (chain_book_step: counters, n_iter, trace
+//     rows, accumulators), a thread per chain.
+// Values and order of operations are those of chain_propose / chain_finalize / chain_record.
+constexpr int FREE_THREADS = 1024, FREE_MAX_DECIDERS = 512, FREE_BOOK_WARPS = 2;
+
+template<class M, class = void> struct ModelLaneTerms { static constexpr int value = 0; };
+template<class M> struct ModelLaneTerms<M, std::void_t<decltype(M::LANE_TERMS)>> { static constexpr int value = M::LANE_TERMS; };
+
+constexpr int FREE_ATT = 2; // attempts of every jump drawn ahead (the truncated proposal redraws until inside the bounds)
+
+template<class M>
+__global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevState S, const FusedArgs a) {
+	extern __shared__ __align__(128) unsigned char fused_smem[];
+	constexpr int TERMS = ModelLaneTerms<M>::value;
+	constexpr int LPC = TERMS > 0 ? 8 : 1;             // lanes per chain
+	__shared__ DevState L_sh;
+	const int ens = blockIdx.x, tid = threadIdx.x;
+	{
+		const DevState L_tmp = fused_localize(S, ens, fused_smem + fused_table_bytes(0));
+		if (tid == 0)
+			L_sh = L_tmp;
+		__syncthreads();
+	}
+	const DevState & L = L_sh;
+	const int nb = L.n_beta, n = L.n_par, RW = n + 3;
+	const int NE = FREE_ATT * n + 1;                    // draws per step: FREE_ATT attempts per coordinate + the accept draw
+	const int K = max(1, min(64 / NE, 64 / RW));        // steps per batch
+	// after the state: draws [2][K NE <= 64][nb], outcome ring [2][K RW <= 64][nb], counters [nb]
+	double * dbuf = reinterpret_cast<double *>(fused_smem + fused_table_bytes(0) + fused_state_bytes(nb, n));
+	double * ring = dbuf + (size_t) 2 * nb * 64;
+	u64 * ctr0 = reinterpret_cast<u64 *>(ring + (size_t) 2 * nb * 64); // the chains' counters at the launch's start
+	const int n_dec = min((nb * LPC + 31) / 32 * 32, FREE_MAX_DECIDERS);
+	const int n_book = FREE_BOOK_WARPS * 32;
+	const int n_prod = (int) blockDim.x - n_dec - n_book;
+	const int n_slots = n_dec / LPC, slot = tid / LPC, sl = tid % LPC;
+	const unsigned gmask = LPC == 1 ? (1u << (tid & 31)) : (0xffu << ((tid & 31) & ~7));
+	const int proposal = L.proposal;
+	const unsigned circular = L.circular_mask, quirks = L.quirks;
+	for (int k = tid; k < nb; k += blockDim.x)
+		ctr0[k] = L.rng_ctr[k];
+	__syncthreads();
+	const long long total = a.n_rounds * a.n_swap;
+	// batch: steps [s0, s0 + ns) of the launch, never across a round's end (the swap needs every chain
+	// at the same step)
+	auto batch_len = [&](long long s0) -> int {
+		if (s0 >= total)
+			return 0;
+		const int left = a.n_swap - (int) (s0 % a.n_swap);
+		return left < K ? left : K;
+	};
+	// draws [j][e][k], k fastest: e = d * FREE_ATT + attempt the unit jump of coordinate d, e = NE - 1
+	// log(u) of the accept test.  The `count` drawing threads form a grid of (chains) x (draws of a
+	// chain): a thread keeps its chain and walks (j, e) in strides, no division per draw.
+	auto produce = [&](long long s0, int ns, double * buf, int t, int count) {
+		const int cols = min(nb, count), rows = count / cols;
+		const int pc = t % cols, pr = t / cols;
+		if (pr >= rows)
+			return;
+		for (int k = pc; k < nb; k += cols) {
+			const uint32_t id = chain_rng_id(L, k);
+			const u64 c0 = ctr0[k] + (u64) s0;
+			int j = 0, e = pr;
+			while (e >= NE) {
+				e -= NE;
+				j++;
+			}
+			while (j < ns) {
+				double u0, u1;
+				const bool is_jump = e < NE - 1;
+				const int d = e / FREE_ATT; // (a constant divisor)
+				philox_uniforms(L.seed, id, c0 + (u64) j, is_jump ? PURPOSE_JUMP : PURPOSE_ACCEPT,
+						is_jump ? (uint32_t) d : 0u, is_jump ? (uint32_t) (e - d * FREE_ATT) : 0u, u0, u1);
+				buf[(size_t) (j * NE + e) * nb + k] = is_jump ? jump_unit(proposal, u0, u1) : log(u0);
+				e += rows;
+				while (e >= NE) {
+					e -= NE;
+					j++;
 				}
 			}
-			__syncthreads();
-			if (L.adapt)
-				for (int k = threadIdx.x; k < nb; k += blockDim.x)
+		}
+	};
+	// do_step_for (reference src/markov_chain.c:226-270) with the first FREE_ATT attempts at hand:
+	// z = the unit jumps of this coordinate, strided by nb
+	auto propose_from = [&](int k, u64 ctr, int i, double x, double st, double lo, double hi, const double * z) -> double {
+		double v = x + jump_apply(proposal, st, z[0]);
+		if (v > hi || v < lo) {
+			bool inside = false;
+			if (!((circular >> i) & 1u)) {
+#pragma unroll
+				for (int t = 1; t < FREE_ATT; t++)
+					if (!inside) {
+						v = x + jump_apply(proposal, st, z[(size_t) t * nb]);
+						inside = !(v > hi || v < lo);
+					}
+			}
+			if (!inside) // the wrap of a circular parameter, or more redraws than were drawn ahead
+				v = propose_coordinate(L, k, ctr, i, x, st, ((circular >> i) & 1u) ? 0u : (unsigned) FREE_ATT);
+		}
+		return v;
+	};
+	// the book-keepers: book-keeping thread (w, l) has chains l * BOOK_WARPS + w, + 32 * BOOK_WARPS, ...
+	auto book = [&](long long s0, int ns, const double * rb, int t) {
+		for (int k = (t & 31) * FREE_BOOK_WARPS + (t >> 5); k < nb; k += n_book)
+			for (int j = 0; j < ns; j++) {
+				const double * e = rb + (size_t) j * RW * nb + k;
+				double pa[APM_MAX_PAR];
+				for (int i = 0; i < n; i++)
+					pa[i] = e[(size_t) (3 + i) * nb];
+				chain_book_step(L, k, e[0] != 0.0, e[(size_t) nb], e[(size_t) 2 * nb], pa, s0 + j);
+			}
+	};
+	long long s0 = 0, s_prev = 0;
+	int ns = batch_len(0), ns_prev = 0;
+	produce(0, ns, dbuf, tid, blockDim.x);
+	__syncthreads();
+	int cur = 0;
+	while (ns > 0) {
+		const long long s_next = s0 + ns;
+		const int ns_next = batch_len(s_next);
+		const double * buf = dbuf + (size_t) cur * nb * 64;
+		double * rb = ring + (size_t) cur * nb * 64;
+		if (tid >= n_dec + n_book) {
+			produce(s_next, ns_next, dbuf + (size_t) (1 - cur) * nb * 64, tid - n_dec - n_book, n_prod);
+		} else if (tid >= n_dec) {
+			book(s_prev, ns_prev, ring + (size_t) (1 - cur) * nb * 64, tid - n_dec);
+		} else if constexpr (TERMS > 0) {
+			// 8 lanes per chain; the chain's point, prob, prior and best stay in the lanes' registers
+			// for the batch (lane sl holds coordinate sl -- and sl + 8 when n_par > 8)
+			auto decide = [&](auto cpl_tag) {
+				constexpr int CPL = decltype(cpl_tag)::value;
+				const size_t step_stride = (size_t) NE * nb, ring_stride = (size_t) RW * nb;
+				for (int k = slot; k < nb; k += n_slots) {
+					double * q = L.prop + (size_t) k * n;
+					const double * mc = L.model_const;
+					double x[CPL], st[CPL], lo[CPL], hi[CPL], v[CPL];
+#pragma unroll
+					for (int c = 0; c < CPL; c++) {
+						const int i = sl + 8 * c;
+						const bool mine = i < n;
+						x[c] = mine ? L.params[(size_t) k * n + i] : 0.0;
+						st[c] = mine ? L.steps[(size_t) k * n + i] : 0.0;
+						lo[c] = mine ? L.pmin[i] : 0.0;
+						hi[c] = mine ? L.pmax[i] : 0.0;
+						v[c] = x[c];
+					}
+					double prob = L.prob[k], prior = L.prior[k], best = L.prob_best[k];
+					const double beta = L.beta[k];
+					const double * z = buf + k;   // this step's draws of chain k, strided by nb
+					double * e = rb + k;          // this step's outcome
+					u64 ctr = ctr0[k] + (u64) s0;
+					for (int j = 0; j < ns; j++, z += step_stride, e += ring_stride, ctr++) {
+#pragma unroll
+						for (int c = 0; c < CPL; c++) {
+							const int i = sl + 8 * c;
+							if (i < n) {
+								// do_step_for (reference src/markov_chain.c:226-270), the first FREE_ATT attempts at hand
+								const double * zi = z + (size_t) (i * FREE_ATT) * nb;
+								double w = x[c] + jump_apply(proposal, st[c], zi[0]);
+								if (w > hi[c] || w < lo[c]) {
+									bool inside = false;
+									const bool wraps = (circular >> i) & 1u;
+									if (!wraps) {
+#pragma unroll
+										for (int t = 1; t < FREE_ATT; t++)
+											if (!inside) {
+												w = x[c] + jump_apply(proposal, st[c], zi[(size_t) t * nb]);
+												inside = !(w > hi[c] || w < lo[c]);
+											}
+									}
+									if (!inside) // a circular parameter's wrap, or more redraws than were drawn ahead
+										w = propose_coordinate(L, k, ctr, i, x[c], st[c], wraps ? 0u : (unsigned) FREE_ATT);
+								}
+								v[c] = w;
+								q[i] = w;
+							}
+						}
+						__syncwarp(gmask);
+						double prior_new = prior;
+						if (M::HAS_PRIOR)
+							prior_new = M::prior(q, n, mc);
+						// the terms: lane sl takes sl, sl + 8, ... side by side
+						double r = M::reduce_init();
+#pragma unroll
+						for (int t0 = 0; t0 < TERMS; t0 += LPC) {
+							const int t = t0 + sl;
+							const double term = M::term(t < TERMS ? t : TERMS - 1, q, mc);
+							r = t < TERMS ? M::reduce(r, term) : r;
+						}
+#pragma unroll
+						for (int o = LPC / 2; o > 0; o >>= 1)
+							r = M::reduce(r, __shfl_xor_sync(gmask, r, o));
+						const double prob_new = M::finish_reduced(beta, r);
+						// check_accept (reference src/markov_chain.c:282-311), as in chain_finalize_value
+						bool accepted;
+						if (prob_new == prob)
+							accepted = true;
+						else if (prob_new > prob)
+							accepted = true;
+						else
+							accepted = z[(size_t) (NE - 1) * nb] < (prob_new - prob);
+						if (accepted) {
+#pragma unroll
+							for (int c = 0; c < CPL; c++)
+								x[c] = v[c];
+							prob = prob_new;
+							prior = prior_new;
+						} else if (quirks & 2u) {
+							prior = prior_new; // revert() restores prob only
+						}
+						const bool better = prob > best; // mcmc_check_best (chain_book_step sees it done)
+						best = better ? prob : best;
+#pragma unroll
+						for (int c = 0; c < CPL; c++) {
+							const int i = sl + 8 * c;
+							if (i < n) {
+								e[(size_t) (3 + i) * nb] = x[c];
+								if (better)
+									L.params_best[(size_t) k * n + i] = x[c];
+							}
+						}
+						if (sl == 0) {
+							e[0] = accepted ? 1.0 : 0.0;
+							e[(size_t) nb] = prob;
+							e[(size_t) 2 * nb] = prior;
+						}
+						__syncwarp(gmask);
+					}
+#pragma unroll
+					for (int c = 0; c < CPL; c++) {
+						const int i = sl + 8 * c;
+						if (i < n)
+							L.params[(size_t) k * n + i] = x[c];
+					}
+					if (sl == 0) {
+						L.prob[k] = prob;
+						L.prior[k] = prior;
+						L.prob_best[k] = best;
+					}
+				}
+			};
+			if (n <= 8)
+				decide(std::integral_constant<int, 1>());
+			else
+				decide(std::integral_constant<int, APM_MAX_PAR / 8>());
+		} else {
+			// a thread per chain
+			for (int k = slot; k < nb; k += n_slots) {
+				double * q = L.prop + (size_t) k * n;
+				double * p = L.params + (size_t) k * n;
+				for (int j = 0; j < ns; j++) {
+					for (int i = 0; i < n; i++)
+						q[i] = propose_from(k, ctr0[k] + (u64) (s0 + j), i, p[i], L.steps[(size_t) k * n + i], L.pmin[i],
+								L.pmax[i], buf + (size_t) (j * NE + i * FREE_ATT) * nb + k);
+					const double prob_old = L.prob[k], prior_old = L.prior[k];
+					double prior_new = prior_old;
+					if (M::HAS_PRIOR)
+						prior_new = M::prior(q, n, L.model_const);
+					const double prob_new = M::finish(L.beta[k], M::sum0(q), prior_new, q, L.model_const);
+					bool accepted;
+					if (prob_new == prob_old)
+						accepted = true;
+					else if (prob_new > prob_old)
+						accepted = true;
+					else
+						accepted = buf[(size_t) (j * NE + NE - 1) * nb + k] < (prob_new - prob_old);
+					double prob_after = prob_old, prior_after = prior_old;
+					if (accepted) {
+						for (int i = 0; i < n; i++)
+							p[i] = q[i];
+						prob_after = prob_new;
+						prior_after = prior_new;
+					} else if (quirks & 2u) {
+						prior_after = prior_new;
+					}
+					L.prob[k] = prob_after;
+					L.prior[k] = prior_after;
+					if (prob_after > L.prob_best[k]) {
+						L.prob_best[k] = prob_after;
+						for (int i = 0; i < n; i++)
+							L.params_best[(size_t) k * n + i] = p[i];
+					}
+					double * e = rb + (size_t) j * RW * nb + k;
+					e[0] = accepted ? 1.0 : 0.0;
+					e[(size_t) nb] = prob_after;
+					e[(size_t) 2 * nb] = prior_after;
+					for (int i = 0; i < n; i++)
+						e[(size_t) (3 + i) * nb] = p[i];
+				}
+			}
+		}
+		__syncthreads();
+		if (s_next % a.n_swap == 0) {
+			// round end: adapt (if compiled in: it reads the counters, so the books are brought up
+			// to date first), tempering_interaction for this ensemble
+			if (L.adapt) {
+				if (tid >= n_dec && tid < n_dec + n_book)
+					book(s0, ns, rb, tid - n_dec); // (the batch before was written down during this one)
+				ns = 0; // nothing left to write down for this batch
+				__syncthreads();
+				for (int k = tid; k < nb; k += blockDim.x)
 					chain_adapt(L, k);
-			__syncthreads();
-			if (threadIdx.x == 0)
+				__syncthreads();
+			}
+			if (tid == 0)
 				ensemble_swap(L, 0);
 			__syncthreads();
-			if (round + 1 < a.n_rounds)
-				for (int k = threadIdx.x; k < nb; k += blockDim.x)
-					chain_propose(L, k, n);
 		}
+		s_prev = s0;
+		ns_prev = ns;
+		s0 = s_next;
+		ns = ns_next;
+		cur = 1 - cur;
 	}
+	if (tid >= n_dec && tid < n_dec + n_book)
+		book(s_prev, ns_prev, ring + (size_t) (1 - cur) * nb * 64, tid - n_dec);
 	fused_writeback(S, L, ens);
 }
 
@@ -1416,6 +1755,106 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_calibrate_kerne
 		}
 	}
 	fused_writeback(S, L, ens);
+}
+
+// ------------------------------------------------------------------ calibration, warp groups per chain
+// markov_chain_calibrate (or apm_gpu_steps) when only a FEW chains are selected -- calibrate_first
+// is ONE chain, calibrate_rest with SKIP_CALIBRATE_ALLCHAINS one more (reference
+// src/parallel_tempering.c:78-207) -- and the table fits in shared memory.  The fused kernel above
+// gives a chain one warp of one SM; here the selected chains are dealt out over the SMs (sel_idx:
+// the host's compacted list) and a GROUP of WC = 16 / NG warps works on each (NG = chains a CTA
+// holds at a time): all of them walk the table (rows strided over the group's lanes, fp64 butterfly
+// per warp), the group's first warp adds the warps' sums in index order and plays the chain's
+// state machine of apm_chain.cuh -- finalise, cal_after_step, next proposal, its coordinates drawn
+// lane-parallel -- on a shared-memory copy of the chain's state.  Two named barriers per step.
+// Chains do not interact during calibration, so no cluster is needed: every CTA stages the table
+// itself (it is L2-resident after the first).
+constexpr int GROUP_MAX = 8; // chains a CTA works on concurrently (named barriers 1 .. 8)
+
+__host__ __device__ inline size_t group_state_bytes(int n_par) {
+	// the chain's state, the warps' partial sums [16], the pending kind
+	return fused_state_bytes(1, n_par) + 16 * sizeof(double) + 16;
+}
+
+struct GroupArgs {
+	FusedArgs f;
+	const int * sel_idx; // [n_sel] chains to calibrate, ascending
+	int n_sel;
+	int ng;              // chains per CTA at a time (1, 2, 4 or 8); warps per chain = 16 / ng
+};
+
+template<class M>
+__global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) group_calibrate_kernel(const DevState S, const GroupArgs ga) {
+	extern __shared__ __align__(128) unsigned char fused_smem[];
+	const FusedArgs & a = ga.f;
+	const Row<M> * sdata = fused_stage_table<M>(a, fused_smem);
+	__shared__ DevState L_grp[GROUP_MAX];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int G = gridDim.x, NG = ga.ng, WC = FUSED_MAX_WARPS / NG;
+	const int n = S.n_par;
+	const int q = warp / WC, wi = warp - q * WC;   // this warp's group, its place in the group
+	const int GL = WC * 32, gl = wi * 32 + lane;   // lanes of the group walking the table
+	const double xub = *a.xabsmax;
+	unsigned char * mem = fused_smem + fused_table_bytes((long long) a.n_rows * (M::ROW_W / 2)) + (size_t) q * group_state_bytes(n);
+	double * sums = reinterpret_cast<double *>(mem + fused_state_bytes(1, n));
+	volatile int * kind_s = reinterpret_cast<volatile int *>(sums + 16);
+	// chains that were not selected: the same marks the other calibration kernels leave
+	for (int g = blockIdx.x * blockDim.x + tid; g < S.n_chains; g += G * blockDim.x)
+		if (a.select != nullptr && !a.select[g]) {
+			S.pend[g] = PEND_NONE;
+			S.cal[g].phase = CAL_IDLE;
+			S.cal[g].status = -1;
+		}
+	// list position p goes to CTA p mod G, group (p / G) mod NG, one after the other
+	for (int p = blockIdx.x + q * G; p < ga.n_sel; p += G * NG) {
+		const int g = ga.sel_idx[p];
+		DevState & L = L_grp[q];
+		if (wi == 0) {
+			const DevState L_tmp = fused_localize_block_by(S, g / S.n_beta, g % S.n_beta, 1, mem, lane, 32);
+			if (lane == 0)
+				L = L_tmp;
+			__syncwarp();
+			if (lane == 0) {
+				L.pend[0] = PEND_NONE;
+				L.cal[0].phase = CAL_IDLE;
+				atomicAdd(L.n_active, 1);
+				cal_begin(L, 0, a.cal);
+			}
+			__syncwarp();
+			const int kind = cal_next_kind(L, 0);
+			if (kind != PEND_NONE)
+				chain_propose_warp(L, 0, kind, lane);
+			if (lane == 0)
+				*kind_s = kind;
+		}
+		group_bar(1 + q, GL);
+		while (*kind_s != PEND_NONE) {
+			const double part = group_loglik<M>(L, L.prop, sdata, a.n_rows, xub, gl, GL);
+			if (lane == 0)
+				sums[wi] = part;
+			group_bar(1 + q, GL);
+			if (wi == 0) {
+				double sum = sums[0];
+				for (int w = 1; w < WC; w++)
+					sum += sums[w];
+				chain_finalize_warp<M>(L, 0, M::sum0(L.prop) + sum, nullptr, lane);
+				if (lane == 0)
+					cal_after_step(L, 0, a.cal);
+				__syncwarp();
+				const int kind = cal_next_kind(L, 0);
+				if (kind != PEND_NONE)
+					chain_propose_warp(L, 0, kind, lane);
+				if (lane == 0)
+					*kind_s = kind;
+			}
+			group_bar(1 + q, GL);
+		}
+		if (wi == 0) {
+			__syncwarp();
+			fused_writeback_block_by(S, L, g / S.n_beta, g % S.n_beta, false, lane, 32);
+		}
+		group_bar(1 + q, GL); // the group's shared memory is free for its next chain
+	}
 }
 
 // ------------------------------------------------------------------ eval

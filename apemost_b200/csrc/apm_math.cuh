@@ -229,7 +229,7 @@ APM_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
 
 // Stream layout (shared, by construction, with the test oracle):
 //   key     = (seed lo, seed hi)
-//   counter = (id, step lo, step hi, purpose << 28 | idx << 20 | attempt)
+//   counter = (id, step lo, step hi ^ (attempt >> 20) << 20, purpose << 28 | idx << 20 | attempt & 0xfffff)
 //   id      = global chain id for per-chain draws, global ensemble id for swap draws
 //   u0, u1  = two 53-bit uniforms strictly inside (0, 1)
 enum {
@@ -239,13 +239,19 @@ enum {
 
 APM_HD void philox_uniforms(uint64_t seed, uint32_t id, uint64_t step, uint32_t purpose,
 		uint32_t idx, uint32_t attempt, double & u0, double & u1) {
-	Philox4 o = philox4x32_10(id, (uint32_t) step, (uint32_t) (step >> 32),
+	// attempts beyond 2^20 (a proposal redrawn a million times: a step width far beyond the
+	// parameter's range) spill into the top bits of the step's high word, so the stream of
+	// redraws does not repeat before 2^32 attempts
+	Philox4 o = philox4x32_10(id, (uint32_t) step, (uint32_t) (step >> 32) ^ ((attempt >> 20) << 20),
 			(purpose << 28) | ((idx & 0xffu) << 20) | (attempt & 0xfffffu),
 			(uint32_t) seed, (uint32_t) (seed >> 32));
-	u0 = ((double) (o.w[0] >> 5) * 67108864.0 + (double) (o.w[1] >> 6) + 0.5)
-			* (1.0 / 9007199254740992.0);
-	u1 = ((double) (o.w[2] >> 5) * 67108864.0 + (double) (o.w[3] >> 6) + 0.5)
-			* (1.0 / 9007199254740992.0);
+	// integer + 0.5 is not representable above 2^52 and rounds to even: the largest value would
+	// come out as exactly 1 (log(u / (1 - u)) = inf under PROPOSAL_LOGISTIC); clamp it below 1
+	const double BELOW_ONE = 0x1.fffffffffffffp-1;
+	u0 = fmin(((double) (o.w[0] >> 5) * 67108864.0 + (double) (o.w[1] >> 6) + 0.5)
+			* (1.0 / 9007199254740992.0), BELOW_ONE);
+	u1 = fmin(((double) (o.w[2] >> 5) * 67108864.0 + (double) (o.w[3] >> 6) + 0.5)
+			* (1.0 / 9007199254740992.0), BELOW_ONE);
 }
 
 // the proposal jump: reference src/mcmc_gettersetter.c:290-306 (Gaussian default;
@@ -256,6 +262,23 @@ APM_HD double jump_from_uniforms(int proposal, double sigma, double u0, double u
 	if (proposal == 2)
 		return (-sigma) * (1 - u0) + sigma * u0;
 	return sigma * (sqrt(-2.0 * log(u0)) * cos(2.0 * 3.14159265358979323846 * u1));
+}
+
+// The same jump in two halves, for draws made ahead of time: jump_unit() is everything that does
+// not depend on the step width (it can be drawn steps ahead, by any thread: the draw depends on the
+// chain's id and step counter only), jump_apply() the rest.  jump_apply(p, sigma, jump_unit(p, u0,
+// u1)) performs the very operations of jump_from_uniforms(p, sigma, u0, u1) in the same order.
+APM_HD double jump_unit(int proposal, double u0, double u1) {
+	if (proposal == 1)
+		return log(u0 / (1 - u0));
+	if (proposal == 2)
+		return u0;
+	return sqrt(-2.0 * log(u0)) * cos(2.0 * 3.14159265358979323846 * u1);
+}
+APM_HD double jump_apply(int proposal, double sigma, double z) {
+	if (proposal == 2)
+		return (-sigma) * (1 - z) + sigma * z;
+	return sigma * z;
 }
 
 // reference src/mcmc_internal.h:46-48

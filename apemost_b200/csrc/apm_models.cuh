@@ -160,6 +160,12 @@ struct ModelSimplesin2 {
 };
 
 // ---- apps/normal.c:8-34 (data-free) -------------------------------------------------------
+// pos = exp(i) (:20), i = 0..9: the correctly rounded values (what the C library returns), as
+// constants -- ten calls of exp() per step were half of a step of this model
+static __constant__ double NORMAL_EXP_I[10] = { 0x1.0000000000000p+0, 0x1.5bf0a8b145769p+1, 0x1.d8e64b8d4ddaep+2,
+		0x1.415e5bf6fb106p+4, 0x1.b4c902e273a58p+5, 0x1.28d389970338fp+7, 0x1.936dc5690c08fp+8,
+		0x1.122885aaeddaap+10, 0x1.749ea7d470c6ep+11, 0x1.fa7157c470f82p+12 };
+
 struct ModelNormal {
 	static constexpr int LL_C = 1, LL_U = 1;
 	static constexpr int NPAR = 1, NCOLS = 0;
@@ -174,25 +180,39 @@ struct ModelNormal {
 	APM_D static bool fast_ok(const Prep &, double) { return true; }
 	APM_D static double sum0(const double *) { return 0.0; }
 	APM_D static double prior(const double *, int, const double *) { return 0.0; }
-	APM_D static double finish(double beta, double, double, const double * p, const double *) {
+	// Data-free models may split one evaluation over lanes (the kernels then give a chain several
+	// lanes instead of one thread): LANE_TERMS independent terms, term(i, p), reduced by the
+	// ORDER-INDEPENDENT reduce() from reduce_init(), and finish_reduced(beta, r) -- finish() below is
+	// the same terms taken one after the other, so both give the same bits.
+	static constexpr int LANE_TERMS = 10;
+	// bump i of the loop (:19-33): pos = exp(i), height = 10 * pow(1.0, i) = 10, sigma = i.  One
+	// division either way: even i: -sigma * pow((x - pos) / sigma, 2) / 2 + height, odd i:
+	// -height * |x - pos| / sigma + height (the reference's two branches differ in the sign of the
+	// difference only).  i = 0 divides by sigma = 0: its a is NaN (0 * inf) for every x and never
+	// passes `a > b`, so it is handed out as NaN without the division (which would take the
+	// divide's slow path on every step).
+	APM_D static double term(int i, const double * p, const double *) {
 		const double x = p[0];
-		double b = 0;
-		for (int i = 0; i < 10; i++) {
-			double pos = exp((double) i);
-			double height = 10.0; // 10 * pow(1.0, i)
-			double sigma = (double) i;
-			double a;
-			if (i % 2 == 0) {
-				double t = (x - pos) / sigma; // i == 0: +-inf or NaN, never taken by a > b
-				a = -sigma * (t * t) / 2 + height;
-			} else if (x > pos)
-				a = -height * (x - pos) / sigma + height;
-			else
-				a = -height * (pos - x) / sigma + height;
-			if (a > b)
-				b = a;
-		}
-		return beta * b;
+		const double pos = NORMAL_EXP_I[i];
+		const double height = 10.0;
+		const double sigma = (double) i;
+		const bool even = i % 2 == 0;
+		const double d = x > pos ? x - pos : pos - x;
+		const double num = even ? x - pos : -height * d;
+		if (i == 0)
+			return __longlong_as_double(0x7ff8000000000000ll);
+		const double quo = num / sigma;
+		return even ? -sigma * (quo * quo) / 2 + height : quo + height;
+	}
+	APM_D static double reduce_init() { return 0.0; }                           // b = 0 (:11)
+	APM_D static double reduce(double b, double a) { return a > b ? a : b; }    // if (a > b) b = a (:31-32)
+	APM_D static double finish_reduced(double beta, double b) { return beta * b; } // (:34)
+	APM_D static double finish(double beta, double, double, const double * p, const double * mc) {
+		double b = reduce_init();
+#pragma unroll
+		for (int i = 0; i < LANE_TERMS; i++)
+			b = reduce(b, term(i, p, mc));
+		return finish_reduced(beta, b);
 	}
 };
 

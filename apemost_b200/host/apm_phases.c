@@ -399,6 +399,8 @@ static void calibrate_selected(apm_session * s, const unsigned char * select, in
 /* ------------------------------------------------------------------ calibrate_first
  * reference src/parallel_tempering.c:78-95 */
 void calibrate_first(void) {
+	const int timing = getenv("APM_HOST_TIMING") != NULL;
+	double t_mark = wall_s();
 	apm_session * s = apm_session_open();
 	unsigned char * select = (unsigned char *) calloc(s->n_chains, 1);
 	int * which = (int *) calloc(s->n_ens, sizeof(int));
@@ -412,8 +414,10 @@ void calibrate_first(void) {
 		which[e] = e * s->n_beta;
 		select[which[e]] = 1;
 	}
+	TIMING_MARK("start-up (files, CUDA, upload)");
 	apm_session_calc_model(s, which, s->n_ens);
 	calibrate_selected(s, select, 0, &rows, &n_rows);
+	TIMING_MARK("calibrating the first chain");
 	apm_session_pull(s, 0, s->n_chains);
 	for (e = 0; e < s->n_ens; e++) {
 		apm_set_output_dir(s->ens_first + e);
@@ -424,7 +428,9 @@ void calibrate_first(void) {
 	}
 	apm_set_output_dir(-1);
 	free(rows); free(select); free(which);
+	TIMING_MARK("writing the files");
 	apm_session_close(s);
+	TIMING_MARK("engine shutdown");
 }
 
 /* ------------------------------------------------------------------ calibrate_rest
@@ -911,9 +917,9 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 		t_read += wall_s() - t_b;
 		clock_gettime(CLOCK_MONOTONIC, &t1);
 		secs = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
-		if (secs < 0.25 && call_cap < (1ll << 40))
+		if (secs < 0.2 && call_cap < (1ll << 40))
 			call_cap *= 2;
-		else if (secs > 1.0 && call_cap > 1)
+		else if (secs > 0.5 && call_cap > 1) /* SIGINT / SIGUSR1 are honoured between calls: <= ~0.5 s */
 			call_cap /= 2;
 
 		/* hand the trace to the writer; the previous job (other buffer, same files) must be done */

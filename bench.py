@@ -19,7 +19,17 @@ Metropolis steps actually executed (rejected ones included, swaps excluded).
             on this box's cores, bounded sample
 
 Multi-GPU (torchrun, one rank per GPU): independent ensembles are sharded over the ranks, no
-data-path collective, weak scaling (4096 chains per GPU).
+data-path collective, weak scaling (4096 chains per GPU) -- that is `value`.  With more than one rank
+the line also carries, measured in the same process group right after the headline leg:
+  multi_gpu_parity  the engine's two NCCL data planes checked against a single-GPU run on rank 0:
+            data-sharded likelihood (per-step ncclAllReduce on the engine's own communicator;
+            decisions equal, values to 1e-9, ranks bit-identical) and the ladder split (boundary
+            chains traded with ncclSend/ncclRecv; bit-identical, both quirk modes)
+  extra.c5          config C5: the 100 M-row curve sharded over the ranks, 4096 replicated chains,
+            one all-reduce per Metropolis step (ms per step, all-reduce + control us per step,
+            the likelihood kernel's roofline fraction)
+  extra.c3_strong   config C3 as BASELINE.json words it -- 4096 chains IN TOTAL over the ranks --
+            strong scaling, with its efficiency against the weak leg of the same run and the limiter
 
 --impl reference times the reference's own CPU implementation on the host cores: the reference
 engine (src/*.c, OpenMP over chains) with apps/simplesin5.c, whose two stale lines (SURVEY.md D1:
@@ -232,6 +242,86 @@ def ncu_traffic_bytes():
     return None
 
 
+C5_TOTAL_ROWS = 100_000_000   # BASELINE.json config 5
+
+
+def multi_gpu_parity(rank, world, local):
+    """tools/shard_check.py and tools/ladder_check.py in this process group (e2, e3 of SURVEY.md 8):
+    the engine's own communicators, checked against a single-GPU run on rank 0"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import ladder_check
+    import shard_check
+    out, detail = {}, []
+    for key, fn in (("data_sharded", lambda: shard_check.check(rank, world, local)),
+                    ("ladder_split", lambda: [ladder_check.check(rank, world, local, quirks=q) for q in (3, 0)])):
+        try:
+            msg = fn()
+            out[key] = "ok"
+            detail += msg if isinstance(msg, list) else [msg]
+        except AssertionError as ex:   # raised on every rank together (the checks broadcast their verdict)
+            out[key] = "FAILED: " + str(ex)[:300]
+    out["detail"] = [d for d in detail if d]
+    return out
+
+
+def c5_leg(rank, world, local, peak):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import c5_bench
+    total = int(os.environ.get("APM_BENCH_C5_ROWS", C5_TOTAL_ROWS))
+    per_gpu = total // world
+    # ~57 ms per Metropolis step per 12.5 M rows: keep the leg near two seconds
+    n_steps = max(2, min(6, int(12.5e6 * 8 / per_gpu)))
+    return c5_bench.measure(rank, world, local, per_gpu, n_steps=n_steps, n_rounds=2, peak=peak)
+
+
+def c3_strong_leg(rank, world, local, peak, K, weak_value, barrier):
+    """config C3 with 4096 chains IN TOTAL: 64 / world ensembles per GPU, K rounds"""
+    import torch
+    import torch.distributed as dist
+    from apemost_b200 import capi
+    n_ens = N_ENS // world
+    eng = capi.Engine("simplesin5", n_ens, N_BETA, seed=1, device=local,
+                      chain_id_offset=rank * n_ens * N_BETA, ensemble_id_offset=rank * n_ens)
+    eng.set_data(light_curve())
+    eng.set_bounds(LO, HI)
+    st = chain_state(N_ENS, N_BETA, 1000)
+    mine = slice(rank * n_ens * N_BETA, (rank + 1) * n_ens * N_BETA)
+    eng.set_chains(0, eng.n_chains, **{k: v[mine] for k, v in st.items()})
+    eng.run(2, N_SWAP, prob_every=1, params_chains=1)
+    barrier()
+    eng.run(K, N_SWAP, prob_every=1, params_chains=1)
+    barrier()
+    _, _, total_ms = eng.last_kernel_ms()
+    eng.set_timing(True)       # second pass: the likelihood kernel's own time (see main)
+    eng.run(K, N_SWAP, prob_every=1, params_chains=1)
+    barrier()
+    ll_ms, ll_launches, _ = eng.last_kernel_ms()
+    t = torch.tensor([total_ms, ll_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, ll_ms_max = [float(v) for v in t.tolist()]
+    eng.close()
+    if rank != 0:
+        return None
+    value = N_ENS * N_BETA * N_SWAP * K / (total_ms * 1e-3)
+    per_launch = ll_ms / max(ll_launches, 1)
+    achieved = n_ens * N_BETA * N_ROWS * ALG_FP64_PER_ROW / (per_launch * 1e-3) if ll_launches else None
+    rec = {"workload": f"C3 strong: simplesin5, 1M rows, 4096 chains in total = {n_ens} ensembles x {N_BETA} rungs "
+                       f"on each of {world} GPUs, n_swap {N_SWAP}",
+           "n_gpus": world, "value": value, "unit": "chain-steps/s", "scaling": "strong", "steps": K,
+           "ms_per_step": total_ms / K,
+           "efficiency_vs_weak_leg": value / weak_value,
+           "efficiency_note": "ideal = the weak leg's whole-job rate (N GPUs x the rate of one GPU holding all 4096 chains)",
+           "kernel_share_of_step": (ll_ms_max / total_ms) if ll_launches else None,
+           "kernel_ms_per_launch": per_launch if ll_launches else None,
+           "limiter": "per Metropolis step one likelihood launch over 1/N of the chains plus one control kernel; "
+                      "what is lost is the likelihood kernel's tail (%d chain tiles x splits dealt to 148 SMs) and the "
+                      "control kernel + launch gaps, which do not shrink with N" % ((n_ens * N_BETA + 7) // 8)}
+    if achieved:
+        rec["roofline"] = {"bound": "fp64", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "GFP64-instr/s",
+                           "frac": achieved / peak}
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -240,6 +330,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="N > 1: skip the parity checks and the C5 / strong-scaling legs")
     args = ap.parse_args()
     rank, world, local = dist_env()
     K, W = args.steps, max(args.warmup, 0)
@@ -331,8 +422,16 @@ def main():
     eng.run(K, N_SWAP, prob_every=1, params_chains=1)   # K steps, device-timed inside the engine
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    ll_ms, ll_launches, total_ms = eng.last_kernel_ms()
+    _, _, total_ms = eng.last_kernel_ms()
     launches = eng.launch_count() - launches0
+    # the same K steps once more with every likelihood launch bracketed by CUDA events on the engine's
+    # stream (the timed run above replays each round as one CUDA graph and has no per-launch events):
+    # the dominant kernel's own launch duration, for the roofline
+    eng.set_timing(True)
+    eng.run(K, N_SWAP, prob_every=1, params_chains=1)
+    barrier()
+    ll_ms, ll_launches, instrumented_ms = eng.last_kernel_ms()
+    eng.set_timing(False)
     clocks = sampler.summary()
 
     # end to end through the C ABI with host buffers
@@ -361,13 +460,23 @@ def main():
     e2e_ms = float(np.mean(e2e_ms))
     e2e_parts = [float(v) for v in np.mean(np.array(e2e_parts), axis=0)]
 
-    steps_per_round = eng.n_chains * N_SWAP
+    n_chains = eng.n_chains
+    steps_per_round = n_chains * N_SWAP
     t = torch.tensor([total_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms, wall_ms = [float(v) for v in t.tolist()]
     value = world * steps_per_round * K / (total_ms * 1e-3)
     e2e = world * steps_per_round / (e2e_ms * 1e-3)
+
+    parity = extra = None
+    if world > 1 and not args.no_extras:
+        eng.close()
+        del flush
+        torch.cuda.empty_cache()
+        parity = multi_gpu_parity(rank, world, local)
+        extra = {"c5": c5_leg(rank, world, local, peak),
+                 "c3_strong": c3_strong_leg(rank, world, local, peak, K, value, barrier)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -376,9 +485,9 @@ def main():
         cpu = {"value": rate, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
-        row_evals_per_launch = eng.n_chains * N_ROWS
+        row_evals_per_launch = n_chains * N_ROWS
         achieved = row_evals_per_launch * ALG_FP64_PER_ROW / (ll_ms / max(ll_launches, 1) * 1e-3)
-        hbm_alg_bytes = N_ROWS * 16 * (eng.n_chains / 8)  # the table once per 8-chain work-item tile
+        hbm_alg_bytes = N_ROWS * 16 * (n_chains / 8)  # the table once per 8-chain work-item tile
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -396,11 +505,22 @@ def main():
                 "bound": "fp64", "kernel": "loglik_tiled_kernel<ModelSimplesin5>",
                 "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "GFP64-instr/s",
                 "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, read from the newest "
+                                  "committed ncu --set full summary under profiles/ (not measured in this run)",
+                "frac_vs_spec": (achieved / (148 * 64 * clocks["sm_mhz"] * 1e6)) if clocks.get("sm_mhz") else None,
+                "spec_peak": "148 SMs x 64 FP64 lanes x the SM clock sampled during the timed region",
+                "executed_per_row": 18,
+                "executed_note": "SASS FP64 instructions per row evaluation: the sine's argument is a separate DMUL + "
+                                 "DADD (rounded like the reference's), so 18 are issued for the 17 counted",
+                "frac_executed": achieved / peak * 18 / ALG_FP64_PER_ROW,
                 "peak_source": "measured live: fp64_peak_kernel DFMA issue rate on this GPU "
                                "(MEASURED_PEAKS.json has no fp64 entry)",
                 "algorithmic": "17 FP64 instr per row-evaluation x 4096 chains x 1e6 rows per launch",
                 "kernel_ms_per_launch": ll_ms / max(ll_launches, 1), "kernel_launches_timed": int(ll_launches),
                 "kernel_share_of_step": ll_ms / total_ms,
+                "kernel_timing": "CUDA events around every likelihood launch in a second pass over the same K steps "
+                                 "(%.3f ms per step with the events, %.3f ms in the timed region, where a round is one "
+                                 "CUDA graph launch)" % (instrumented_ms / K, total_ms / K),
                 "hbm": {"achieved": hbm_alg_bytes / (ll_ms / max(ll_launches, 1) * 1e-3) / 1e9,
                         "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                         "note": "algorithmic bytes = table once per 8-chain tile; it is served by L2 "
@@ -409,6 +529,9 @@ def main():
             "cpu_baseline": cpu, "clocks": clocks, "wall_ms_per_step": wall_ms / K,
             "row_evals_per_s": value * N_ROWS,
         }
+        if parity is not None:
+            line["multi_gpu_parity"] = parity
+            line["extra"] = extra
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

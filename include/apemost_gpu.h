@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define APM_GPU_ABI_VERSION 5
+#define APM_GPU_ABI_VERSION 6
 
 /* ---- error codes -------------------------------------------------------- */
 #define APM_OK          0
@@ -272,6 +272,12 @@ int apm_gpu_last_kernel_ms(const apm_gpu * h, double * loglik_ms,
 		long long * loglik_launches, double * total_ms);
 /* which path the last run used: APM_PATH_TILED, _FUSED, _CLUSTER or _GRID */
 int apm_gpu_last_path(const apm_gpu * h);
+/* per_launch != 0: bracket every likelihood launch of the tiled path with CUDA events (what
+ * apm_gpu_last_kernel_ms reports as loglik_ms / loglik_launches) and enqueue the launches one by one.
+ * Default 0: no per-launch events, and a round of the sampler (n_swap x {likelihood, control kernel})
+ * is replayed as one CUDA graph -- the step counter lives on the device, the host has nothing to do
+ * per step; loglik_launches is then reported as 0. */
+int apm_gpu_set_timing(apm_gpu * h, int per_launch);
 /* microbenchmark: sustained FP64 FMA issue rate of this device, in
  * FP64 instructions (lane-operations) per second; used as the roofline peak */
 int apm_gpu_measure_fp64_peak(int device, double seconds, double * instr_per_s);

@@ -357,23 +357,25 @@ void orc_philox4x32_10(const unsigned ctr[4], const unsigned key[2], unsigned ou
 /* Stream layout shared with the engine (apemost_b200/csrc/apm_rng.cuh):
  *   key     = (seed lo, seed hi)
  *   counter = (c0 = chain or ensemble id, c1 = step lo, c2 = step hi,
- *              c3 = purpose << 28 | idx << 20 | attempt)
+ *              c3 = purpose << 28 | idx << 20 | attempt & 0xfffff; attempt >> 20 is
+ *              xor-ed into the top 12 bits of c2)
  *   u0 = ((w0 >> 5) * 2^26 + (w1 >> 6) + 0.5) / 2^53, u1 likewise from w2, w3:
- *   53-bit uniforms strictly inside (0, 1). */
+ *   53-bit uniforms strictly inside (0, 1) (the one value that would round to 1.0 is clamped). */
 void orc_philox_uniforms(u64 seed, unsigned c0, u64 step, unsigned purpose,
 		unsigned idx, unsigned attempt, double * u0, double * u1) {
 	unsigned ctr[4], key[2], w[4];
 	ctr[0] = c0;
 	ctr[1] = (u32) step;
-	ctr[2] = (u32) (step >> 32);
+	ctr[2] = (u32) (step >> 32) ^ ((attempt >> 20) << 20); /* redraws beyond 2^20 spill here */
 	ctr[3] = (purpose << 28) | ((idx & 0xffu) << 20) | (attempt & 0xfffffu);
 	key[0] = (u32) seed;
 	key[1] = (u32) (seed >> 32);
 	orc_philox4x32_10(ctr, key, w);
-	*u0 = ((double) (w[0] >> 5) * 67108864.0 + (double) (w[1] >> 6) + 0.5)
-			* (1.0 / 9007199254740992.0);
-	*u1 = ((double) (w[2] >> 5) * 67108864.0 + (double) (w[3] >> 6) + 0.5)
-			* (1.0 / 9007199254740992.0);
+	/* integer + 0.5 rounds to even above 2^52: clamp the one value that would become 1.0 */
+	*u0 = fmin(((double) (w[0] >> 5) * 67108864.0 + (double) (w[1] >> 6) + 0.5)
+			* (1.0 / 9007199254740992.0), 0x1.fffffffffffffp-1);
+	*u1 = fmin(((double) (w[2] >> 5) * 67108864.0 + (double) (w[3] >> 6) + 0.5)
+			* (1.0 / 9007199254740992.0), 0x1.fffffffffffffp-1);
 }
 
 /* ===================================================================== */

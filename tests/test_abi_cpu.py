@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_model_table(lib):
-    assert lib.apm_gpu_abi_version() == 5
+    assert lib.apm_gpu_abi_version() == 6
     assert lib.apm_gpu_model_n_par(0) == 4 and lib.apm_gpu_model_n_par(1) == 4
     assert lib.apm_gpu_model_n_par(2) == 1 and lib.apm_gpu_model_n_par(3) == 7
     assert lib.apm_gpu_model_n_cols(2) == 0 and lib.apm_gpu_model_n_cols(3) == 2

@@ -189,7 +189,9 @@ def test_full_size_properties_c5_shard(capi):
 # APM_PATH_TILED / APM_PATH_FUSED / APM_PATH_CLUSTER / APM_PATH_GRID
 PATHS = [pytest.param(1, id="tiled"), pytest.param(2, id="fused"), pytest.param(3, id="cluster"),
          pytest.param(4, id="grid")]
-CALIBRATION_PATH = {1: 1, 2: 2, 3: 2, 4: 4}  # the cluster path is for runs: calibration takes the fused kernel
+# calibration asked for as "cluster" takes the warp-group kernel (group_calibrate_kernel: the selected chains
+# dealt out over the SMs, a group of warps per chain); data-free models have the fused kernel only
+CALIBRATION_PATH = {1: 1, 2: 2, 3: 3, 4: 4}
 
 
 def _pair(capi, model, n_ens, n_beta, n_par=None, seed=1, path=0, **kw):
@@ -581,7 +583,7 @@ def test_calibration_trajectory_equals_oracle(capi, name, path):
         status, prog = eng.calibrate(burn_in_iterations=600, progress_capacity=100000)
         res.append((status, prog, eng.get_chains()))
     (s_g, p_g, st_g), (s_c, p_c, st_c) = res
-    assert engines[0].last_path() == (2 if (path == 4 and fx["model"] == "normal") else CALIBRATION_PATH[path])
+    assert engines[0].last_path() == (2 if (path in (3, 4) and fx["model"] == "normal") else CALIBRATION_PATH[path])
     np.testing.assert_array_equal(s_g, s_c)
     assert (s_g == 0).all()
     _compare_state(st_g, st_c)
@@ -590,6 +592,66 @@ def test_calibration_trajectory_equals_oracle(capi, name, path):
     for a, b in zip(sorted(p_g, key=key), sorted(p_c, key=key)):
         assert a[:3] == b[:3]
         np.testing.assert_allclose(a[3:], b[3:], rtol=RTOL_TRAJ)
+
+
+@pytest.mark.parametrize("n_ens,n_beta,pick,ng", [(1, 20, [0], 1), (1, 20, [1], 1), (1, 20, None, 1), (45, 4, None, 2),
+                                                   (3, 7, [0, 7, 14], 1)])
+def test_group_calibration_geometries(capi, n_ens, n_beta, pick, ng):
+    """the warp-group calibration kernel (a few selected chains dealt out over the SMs, 16 / ng warps
+    per chain): calibrate_first's shape (ONE chain of a 20-rung ladder), calibrate_rest's (chain 1),
+    a whole ladder (a chain per CTA), more chains than SMs (two per CTA, one after the other per
+    group) and chain 0 of several ensembles -- final state and progress rows against the oracle"""
+    fx = load("c1_phases")
+    rows = [tuple(r) for r in fx["rows"]]
+    n_par = len(rows)
+    data = np.loadtxt(os.path.join(GOLDEN, fx["data_file"]))
+    n = n_ens * n_beta
+    sel = None
+    if pick is not None:
+        sel = np.zeros(n, dtype=np.uint8)
+        sel[pick] = 1
+    res = []
+    engines = _pair(capi, fx["model"], n_ens, n_beta, n_par=n_par, seed=29)
+    for eng in engines:
+        eng.set_data(data)
+        start, lo, hi, names, step = pt_flow.setup_chains(eng, rows)
+        beta = np.tile(pt_flow.chebyshev_ladder(n_beta, 0.02), n_ens)
+        eng.set_chains(0, n, beta=beta, steps=np.tile(step, (n, 1)) * beta[:, None] ** -0.5)
+        st = eng.get_chains(fields=("params", "beta"))
+        prob, prior = eng.eval(st["params"], st["beta"])
+        eng.set_chains(0, n, prob=prob, prior=prior)
+        status, prog = eng.calibrate(select=sel, burn_in_iterations=400, iter_readjust=40, no_rescaling_limit=3,
+                                     progress_capacity=200000, raise_on_failure=False)
+        res.append((status, prog, eng.get_chains()))
+    (s_g, p_g, st_g), (s_c, p_c, st_c) = res
+    assert engines[0].last_path() == 3
+    np.testing.assert_array_equal(s_g, s_c)
+    if sel is not None:
+        assert (s_g[sel == 0] == -1).all()
+    _compare_state(st_g, st_c)
+    assert len(p_g) == len(p_c) and len(p_g) > 0
+    key = lambda r: (r[0], r[2], r[1])
+    for a, b in zip(sorted(p_g, key=key), sorted(p_c, key=key)):
+        assert a[:3] == b[:3]
+        np.testing.assert_allclose(a[3:], b[3:], rtol=RTOL_TRAJ)
+
+
+@pytest.mark.parametrize("path", [pytest.param(1, id="tiled"), pytest.param(2, id="fused")])
+def test_redraws_beyond_a_million_attempts(capi, path):
+    """a step width a million times the parameter's range: the truncated proposal (reference
+    src/markov_chain.c:235-240, redraw until inside the bounds) needs ~2.5e6 redraws per coordinate;
+    the attempt counter has more than its 20 low bits, so the stream does not repeat
+    and the loop ends, on the device as in the oracle, with the same point"""
+    rows = [(100.0, -10.0, 10000.0, "x", -1.0)]
+    res = []
+    for eng in _pair(capi, "normal", 1, 3, seed=5, path=path):
+        eng.set_data(np.zeros((2, 2)))
+        pt_flow.setup_chains(eng, rows)
+        eng.set_chains(0, 3, beta=[1.0, 0.5, 0.25], steps=np.full((3, 1), 1e6 * 10010.0))
+        eng.run(1, 2)
+        res.append(eng.get_chains())
+    _compare_state(res[0], res[1])
+    assert (res[0]["params"] >= -10).all() and (res[0]["params"] <= 10000).all()
 
 
 @pytest.mark.parametrize("path", PATHS)
@@ -691,3 +753,90 @@ def test_evidence_and_posterior_match_reference_statistics(capi, name):
     assert abs(float(fx["evidence"]) - lnz_g.mean()) < 5 * lnz_g.std(ddof=1)
     se_p = np.sqrt(mp_g.var(axis=0, ddof=1) / n_ens + mp_c.var(axis=0, ddof=1) / n_ens)
     assert (np.abs(mp_g.mean(axis=0) - mp_c.mean(axis=0)) < 5 * se_p).all()
+
+
+STAT_N_ENS = 24
+STAT_TOL = 4.0   # standard errors of the difference of the two means (engine ensembles vs reference seeds)
+
+
+@pytest.mark.parametrize("name", ["c1_stats", "c4_stats"])
+def test_full_config_statistics_match_reference(capi, name):
+    """Statistical parity at the configurations' REAL sizes (north_star: "posterior means/variances and
+    the thermodynamic-integration log-evidence ... within stated statistical tolerances"):
+      c1_stats  C1: simplesin on tests/testlc.dat, N_BETA 20, 20 000 iterations
+      c4_stats  C4: pulse_vrot on the 2000-bin spectrum, N_BETA 20, 100 000 iterations
+    The fixture (tests/golden/make_stats_golden.py) holds 24 runs of the UNMODIFIED reference (one
+    thread, GSL_RNG_SEED 1..24) from ONE calibration_results: ln Z as its `analyse` prints it, and the
+    mean and variance of every parameter of chain 0 over the run.  The engine runs 24 independent
+    ensembles from the same calibration_results.  Stated tolerance: for ln Z, every posterior mean and
+    every posterior VARIANCE, |mean over ensembles - mean over reference seeds| < 4 standard errors
+    of that difference (sqrt(s_engine^2 / 24 + s_reference^2 / 24), s = scatter between runs)."""
+    fx = load(name)
+    rows = [tuple(r) for r in fx["rows"]]
+    n_par, n_beta, iters = len(rows), fx["config"]["N_BETA"], fx["config"]["MAX_ITERATIONS"]
+    n_ens = STAT_N_ENS
+    data = (np.loadtxt(os.path.join(GOLDEN, fx["data_file"])) if fx["data_file"]
+            else np.array(fx["data"], dtype=float).reshape(-1, 2))
+    cal = np.array(fx["calibration_results"].split(), dtype=float).reshape(n_beta, 1 + 2 * n_par)
+    n_swap = 2000 // n_beta
+    eng = capi.Engine(fx["model"], n_ens, n_beta, n_par=n_par, seed=20261018)
+    eng.set_data(data)
+    pt_flow.setup_chains(eng, rows)
+    pt_flow.apply_calibration(eng, 0, np.tile(cal[:, 0], n_ens), np.tile(cal[:, 1:1 + n_par], (n_ens, 1)),
+                              np.tile(cal[:, 1 + n_par:], (n_ens, 1)))
+    eng.reset_stats()
+    left = -(-iters // n_swap)
+    while left > 0:   # in calls of bounded device time
+        rounds = min(left, 50)
+        eng.run(rounds, n_swap)
+        left -= rounds
+    s = eng.get_stats()
+    assert (s["n"] == -(-iters // n_swap) * n_swap).all()
+    mean_dl = (s["sum_dl"] / s["n"]).reshape(n_ens, n_beta)
+    lnz = np.array([pt_flow.evidence(cal[:, 0], m) for m in mean_dl])
+    mean_p = (s["sum_params"] / s["n"][:, None]).reshape(n_ens, n_beta, n_par)[:, 0, :]
+    var_p = (s["sum_params_sq"] / s["n"][:, None]).reshape(n_ens, n_beta, n_par)[:, 0, :] - mean_p ** 2
+    runs = fx["runs"]
+    assert len(runs) >= 8
+    ref = dict(lnz=np.array([r["lnz"] for r in runs]), mean=np.array([r["mean"] for r in runs]),
+               var=np.array([r["var"] for r in runs]))
+    report = {}
+    for key, ours in (("lnz", lnz), ("mean", mean_p), ("var", var_p)):
+        theirs = ref[key]
+        se = np.sqrt(ours.var(axis=0, ddof=1) / len(ours) + theirs.var(axis=0, ddof=1) / len(theirs))
+        z = (ours.mean(axis=0) - theirs.mean(axis=0)) / se
+        report[key] = np.round(np.atleast_1d(z), 2).tolist()
+        assert (np.abs(z) < STAT_TOL).all(), (name, key, ours.mean(axis=0), theirs.mean(axis=0), se, z)
+    print(name, "z-scores (engine - reference, in standard errors):", report,
+          "ln Z engine %.4f +- %.4f reference %.4f +- %.4f" % (lnz.mean(), lnz.std(ddof=1) / np.sqrt(n_ens),
+                                                                ref["lnz"].mean(), ref["lnz"].std(ddof=1) / np.sqrt(len(runs))))
+
+
+def test_c3_shape_trajectory_equals_oracle(capi):
+    """BASELINE config C3's own shape -- 64 ensembles x 64 rungs = 4096 chains on the 1M-row light
+    curve, the tiled path's persistent likelihood kernel with its row splits -- against the oracle,
+    trajectory for trajectory: 2 rounds of 3 Metropolis steps + swap.  The oracle steps a sample of
+    the ensembles (a chain's stream depends on its global id only, so ensemble e of the engine =
+    an oracle built with that ensemble's id offsets)."""
+    bench = __import__("bench")
+    data = bench.light_curve()
+    n_ens, n_beta = bench.N_ENS, bench.N_BETA
+    st = bench.chain_state(n_ens, n_beta, 1000)
+    eng = capi.Engine("simplesin5", n_ens, n_beta, seed=1)
+    eng.set_data(data)
+    eng.set_bounds(bench.LO, bench.HI)
+    eng.set_chains(0, eng.n_chains, **st)
+    eng.run(2, 3, prob_every=1, params_chains=2)
+    assert eng.last_path() == 1
+    tr, out = eng.read_trace(), eng.get_chains()
+    for e in (0, 37, 63):
+        sl = slice(e * n_beta, (e + 1) * n_beta)
+        o = Oracle("simplesin5", 1, n_beta, seed=1, rng=RNG_PHILOX, chain_id_offset=e * n_beta, ensemble_id_offset=e)
+        o.set_data(data)
+        o.set_bounds(bench.LO, bench.HI)
+        o.set_chains(0, n_beta, **{k: v[sl] for k, v in st.items()})
+        o.run(2, 3, prob_every=1, params_chains=2)
+        tro, outo = o.read_trace(), o.get_chains()
+        _compare_state({k: v[sl] for k, v in out.items()}, outo)
+        np.testing.assert_allclose(tr["prob"][:, sl], tro["prob"], rtol=RTOL_TRAJ)
+        np.testing.assert_allclose(tr["params"][:, sl, :], tro["params"], rtol=RTOL_TRAJ)

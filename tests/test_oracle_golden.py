@@ -188,3 +188,31 @@ def test_philox_mode_is_reproducible_and_thread_independent():
     assert out[0][1]["n_iter"].tolist() == [150] * 8
     # the two ensembles use different streams
     assert not np.array_equal(out[0][0]["prob"][:, 0], out[0][0]["prob"][:, 4])
+
+
+def test_stats_fixture_run_is_reproduced_by_the_oracle():
+    """The full-configuration statistical fixture (tests/golden/c1_stats.json: 24 `run`s of the
+    unmodified reference at C1's real size, N_BETA 20 x 20 000 iterations, from one calibration)
+    is pinned like the phase fixtures: the oracle in MT19937 mode, seeded like the fixture's first
+    run, reproduces that run's evidence as `analyse` prints it and its posterior means / variances
+    of chain 0 (computed from "%.15e" text on the reference side)."""
+    fx = load("c1_stats")
+    rows = [tuple(r) for r in fx["rows"]]
+    n_par, n_beta, iters = len(rows), fx["config"]["N_BETA"], fx["config"]["MAX_ITERATIONS"]
+    data = np.loadtxt(os.path.join(GOLDEN, fx["data_file"]))
+    cal = np.array(fx["calibration_results"].split(), dtype=float).reshape(n_beta, 1 + 2 * n_par)
+    run = fx["runs"][0]
+    e = Oracle(fx["model"], 1, n_beta, n_par=n_par, seed=run["seed"], rng=RNG_MT19937, n_threads=1)
+    e.set_data(data)
+    pt_flow.setup_chains(e, rows)
+    pt_flow.apply_calibration(e, 0, cal[:, 0], cal[:, 1:1 + n_par], cal[:, 1 + n_par:])
+    n_swap = 2000 // n_beta
+    e.run(-(-iters // n_swap), n_swap, prob_every=1, params_chains=1)
+    tr = e.read_trace()
+    assert tr["params"].shape[0] == run["n"]
+    # the reference's analyse reads "%6e" text: 7 significant digits
+    dl_text = np.array([[float("%6e" % v) for v in col] for col in tr["prob_minus_prior"].T])
+    assert "%.5f" % evidence(cal[:, 0], dl_text.mean(axis=1)) == "%.5f" % run["lnz"]
+    p0 = tr["params"][:, 0, :]
+    np.testing.assert_allclose(p0.mean(axis=0), run["mean"], rtol=1e-12)
+    np.testing.assert_allclose(p0.var(axis=0), run["var"], rtol=1e-9)

@@ -37,15 +37,11 @@ def shard_rows(lo, hi, n_total, seed):
     return np.ascontiguousarray(np.stack([x, y], axis=1))
 
 
-def main():
-    rank, world, local = bench.dist_env()
-    per_gpu = int(os.environ.get("C5_ROWS_PER_GPU", "12500000"))
-    n_steps = int(os.environ.get("C5_STEPS", "6"))      # Metropolis steps per timed round
-    n_rounds = int(os.environ.get("C5_ROUNDS", "2"))
+def measure(rank, world, local, per_gpu, n_steps=6, n_rounds=2, peak=None):
+    """times n_rounds x (n_steps Metropolis steps + swap) of the 4096 replicated chains on a curve of
+    per_gpu x world rows (inside an initialised process group when world > 1); the record on rank 0,
+    None elsewhere"""
     n_total = per_gpu * world
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_ens, n_beta = bench.N_ENS, bench.N_BETA
     eng = capi.Engine("simplesin5", n_ens, n_beta, seed=1, device=local)
     if world > 1:
@@ -61,7 +57,9 @@ def main():
     st["params"] = np.clip(bench.TRUTH[None, :] + (st["params"] - bench.TRUTH[None, :]) * scale, bench.LO, bench.HI)
     st["params_best"] = st["params"].copy()
     eng.set_chains(0, eng.n_chains, **st)
-    peak = capi.measure_fp64_peak(local, 0.25)
+    eng.set_timing(True)   # per-launch events: the likelihood kernel's own time
+    if peak is None:
+        peak = capi.measure_fp64_peak(local, 0.25)
 
     def barrier():
         if world > 1:
@@ -80,28 +78,55 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, wall_ms, ll_ms_max = [float(v) for v in t.tolist()]
     out = eng.get_chains()
+    # the replicas must have stayed in lock-step: same state bits on every rank
+    same = True
+    if world > 1:
+        chk = torch.from_numpy(np.concatenate([out["params"].ravel(), out["prob"]])).cuda()
+        ref = chk.clone()
+        dist.broadcast(ref, src=0)
+        flags = [None] * world
+        dist.all_gather_object(flags, bool((chk == ref).all().item()))
+        same = all(flags)
     acc = float(out["accept"].sum()) / float((out["accept"] + out["reject"]).sum())
+    eng.close()
+    if rank != 0:
+        return None
+    steps = n_rounds * n_steps
+    per_launch = ll_ms / max(ll_launches, 1)
+    achieved = eng.n_chains * per_gpu * bench.ALG_FP64_PER_ROW / (per_launch * 1e-3)
+    value = eng.n_chains * steps / (total_ms * 1e-3)
+    return {
+        "workload": f"C5: simplesin5, {n_total}-row synthetic light curve sharded over {world} GPU(s) "
+                    f"({per_gpu} rows = {per_gpu * 16 / 1e6:.0f} MB each), 4096 replicated chains, "
+                    "per-step ncclAllReduce of the per-chain partial sums on the engine's own communicator"
+                    + ("" if world > 1 else " (none at 1 GPU)"),
+        "n_gpus": world, "n_rows_total": n_total, "rows_per_gpu": per_gpu, "metropolis_steps_timed": steps,
+        "chain_steps_per_s": value, "row_evals_per_s": value * n_total,
+        "ms_per_metropolis_step": total_ms / steps, "loglik_kernel_ms_per_launch": per_launch,
+        "loglik_share_of_step": ll_ms / total_ms,
+        "allreduce_plus_control_us_per_step": (total_ms - ll_ms_max) / steps * 1e3,
+        "allreduce_bytes_per_step": eng.n_chains * 8,
+        "replicas_bit_identical": same,
+        "roofline": {"bound": "fp64", "achieved": achieved / 1e9, "peak": peak / 1e9,
+                     "unit": "GFP64-instr/s", "frac": achieved / peak,
+                     "hbm_min_gbs": per_gpu * 16 / (per_launch * 1e-3) / 1e9,
+                     "note": "hbm_min_gbs = the shard read once per launch; the kernel is FP64-bound as long as "
+                             "DRAM traffic stays near that (see the ncu capture of this command)"},
+        "acceptance_rate": acc, "wall_ms": wall_ms,
+    }
+
+
+def main():
+    rank, world, local = bench.dist_env()
+    per_gpu = int(os.environ.get("C5_ROWS_PER_GPU", "12500000"))
+    n_steps = int(os.environ.get("C5_STEPS", "6"))      # Metropolis steps per timed round
+    n_rounds = int(os.environ.get("C5_ROUNDS", "2"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rec = measure(rank, world, local, per_gpu, n_steps, n_rounds)
     if rank == 0:
-        steps = n_rounds * n_steps
-        per_launch = ll_ms / max(ll_launches, 1)
-        achieved = eng.n_chains * per_gpu * bench.ALG_FP64_PER_ROW / (per_launch * 1e-3)
-        value = eng.n_chains * steps / (total_ms * 1e-3)
-        print(json.dumps({
-            "workload": f"C5: simplesin5, {n_total}-row synthetic light curve sharded over {world} GPU(s) "
-                        f"({per_gpu} rows = {per_gpu * 16 / 1e6:.0f} MB each), 4096 replicated chains, "
-                        "per-step ncclAllReduce of the per-chain partial sums" + ("" if world > 1 else " (none at 1 GPU)"),
-            "n_gpus": world, "n_rows_total": n_total, "rows_per_gpu": per_gpu, "metropolis_steps_timed": steps,
-            "chain_steps_per_s": value, "row_evals_per_s": value * n_total,
-            "ms_per_metropolis_step": total_ms / steps, "loglik_kernel_ms_per_launch": per_launch,
-            "loglik_share_of_step": ll_ms / total_ms,
-            "allreduce_plus_control_ms_per_step": (total_ms - ll_ms_max) / steps,
-            "roofline": {"bound": "fp64", "achieved": achieved / 1e9, "peak": peak / 1e9,
-                         "unit": "GFP64-instr/s", "frac": achieved / peak,
-                         "hbm_min_gbs": per_gpu * 16 / (per_launch * 1e-3) / 1e9,
-                         "note": "hbm_min_gbs = the shard read once per launch; the kernel is FP64-bound as long as "
-                                 "DRAM traffic stays near that (see the ncu capture of this command)"},
-            "acceptance_rate": acc, "wall_ms": wall_ms,
-        }))
+        print(json.dumps(rec))
     if world > 1:
         dist.destroy_process_group()
 

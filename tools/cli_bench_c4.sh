@@ -33,6 +33,9 @@ run_phases() { # $1 = label, $2 = executable
 	grep -a "on-device accumulators" $1.analyse.log || true
 }
 run_phases gpu ./pulse_vrot.exe
+# where the calibration phases' wall time goes (engine time versus CUDA start-up / shutdown)
+mkdir cal_timing && cp data params cal_timing/ && (cd cal_timing && for phase in calibrate_first calibrate_rest; do
+	echo "timing of $phase:"; GSL_RNG_SEED=1 APM_HOST_TIMING=1 ../pulse_vrot.exe $phase 2>&1 >/dev/null | grep timing || true; done)
 GSL_RNG_SEED=1 APM_HOST_TIMING=1 ./pulse_vrot.exe run 2>&1 >/dev/null | grep timing || true
 REF="$ROOT/oracle/_ref/pulse_vrot_c4.exe"
 if [ -x "$REF" ]; then

@@ -1,0 +1,6 @@
+set -x
+mkdir -p gpurun_out/r02c
+timeout 900 python -m pytest tests -m gpu -x -q -k "c2_phases or normal or redraws or adapt or continues or reproducible" > gpurun_out/r02c/pytest_c2.log 2>&1; tail -5 gpurun_out/r02c/pytest_c2.log
+SMALL_BENCH_ONLY="C2" timeout 600 python tools/small_bench.py > gpurun_out/r02c/small_c2.log 2>&1; tail -5 gpurun_out/r02c/small_c2.log
+cp gpurun_out/small_bench.json gpurun_out/r02c/small_c2.json
+ncu --set full --import-source on --clock-control none -k regex:free_run_kernel -s 1 -c 1 -o gpurun_out/r02c/c2_free python tools/prof_c2.py 1 50 > gpurun_out/r02c/ncu_c2.log 2>&1; tail -3 gpurun_out/r02c/ncu_c2.log

@@ -17,14 +17,13 @@ import bench  # noqa: E402
 from apemost_b200 import capi  # noqa: E402
 
 
-def main():
-    rank, world, local = bench.dist_env()
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n_rows = int(os.environ.get("LADDER_ROWS", "60000"))
+def check(rank, world, local, quirks=None, n_rows=None):
+    """the check proper, inside an initialised process group; returns a summary string on rank 0
+    (None elsewhere), raises AssertionError on a mismatch (every rank raises together)"""
+    n_rows = n_rows or int(os.environ.get("LADDER_ROWS", "60000"))
     data = bench.light_curve(n_rows)
-    n_ens, total = 5, 12
-    quirks = int(os.environ.get("LADDER_QUIRKS", "3"))
+    n_ens, total = 5, max(12, 2 * world)
+    quirks = int(os.environ.get("LADDER_QUIRKS", "3")) if quirks is None else quirks
     st = bench.chain_state(n_ens, total, 5)
     # flat steps so that swaps between neighbours are accepted often
     st["beta"] = np.tile(np.linspace(1.0, 0.9, total), n_ens)
@@ -42,27 +41,47 @@ def main():
     out, tr = e.get_chains(), e.read_trace()
     gathered = [None] * world
     dist.all_gather_object(gathered, (mine, out, tr["prob"]))
+    err, msg = None, None
     if rank == 0:
-        f = capi.Engine("simplesin5", n_ens, total, seed=3, device=local, path=1, quirks=quirks)
-        f.set_data(data)
-        f.set_bounds(bench.LO, bench.HI)
-        f.set_chains(0, f.n_chains, **st)
-        f.run(12, 5, prob_every=1, params_chains=0)
-        full, trf = f.get_chains(), f.read_trace()
-        straddling = 0
-        for idx, o, trp in gathered:
-            for k in o:
-                if k == "rng_counter" or k in full:
-                    assert np.array_equal(o[k], full[k][idx]), k
-            assert np.array_equal(trp, trf["prob"][:, idx])
-        # swaps across the GPU boundary did happen: the last rung of a block counts them
-        for r in range(world - 1):
-            idx, o, _ = gathered[r]
-            last = (np.arange(len(idx)) % (len(idx) // n_ens)) == len(idx) // n_ens - 1
-            straddling += int(o["swapcount"][last].sum())
-        assert straddling > 0, "no swap across a GPU boundary was accepted; the check is vacuous"
-        print(f"ladder_check ok: {world} ranks x {total // world} rungs == 1 GPU x {total} rungs, bit for bit; "
-              f"{int(full['swapcount'].sum())} swaps, {straddling} across a GPU boundary (quirks={quirks})")
+        try:
+            f = capi.Engine("simplesin5", n_ens, total, seed=3, device=local, path=1, quirks=quirks)
+            f.set_data(data)
+            f.set_bounds(bench.LO, bench.HI)
+            f.set_chains(0, f.n_chains, **st)
+            f.run(12, 5, prob_every=1, params_chains=0)
+            full, trf = f.get_chains(), f.read_trace()
+            f.close()
+            straddling = 0
+            for idx, o, trp in gathered:
+                for k in o:
+                    if k == "rng_counter" or k in full:
+                        assert np.array_equal(o[k], full[k][idx]), k
+                assert np.array_equal(trp, trf["prob"][:, idx])
+            # swaps across the GPU boundary did happen: the last rung of a block counts them
+            for r in range(world - 1):
+                idx, o, _ = gathered[r]
+                last = (np.arange(len(idx)) % (len(idx) // n_ens)) == len(idx) // n_ens - 1
+                straddling += int(o["swapcount"][last].sum())
+            assert straddling > 0, "no swap across a GPU boundary was accepted; the check is vacuous"
+            msg = (f"ladder_check ok: {world} ranks x {total / world:g} rungs == 1 GPU x {total} rungs, bit for bit; "
+                   f"{int(full['swapcount'].sum())} swaps, {straddling} across a GPU boundary (quirks={quirks})")
+        except AssertionError as ex:
+            err = "ladder-split run differs from the single-GPU run (quirks=%d): %s" % (quirks, str(ex)[:300])
+    e.close()
+    errs = [err]
+    dist.broadcast_object_list(errs, src=0)
+    if errs[0]:
+        raise AssertionError(errs[0])
+    return msg
+
+
+def main():
+    rank, world, local = bench.dist_env()
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    msg = check(rank, world, local)
+    if rank == 0:
+        print(msg)
     dist.destroy_process_group()
 
 

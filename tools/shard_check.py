@@ -17,11 +17,10 @@ import bench  # noqa: E402
 from apemost_b200 import capi  # noqa: E402
 
 
-def main():
-    rank, world, local = bench.dist_env()
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n_rows = int(os.environ.get("SHARD_ROWS", "400000"))
+def check(rank, world, local, n_rows=None):
+    """the check proper, inside an initialised process group; returns a summary string on rank 0
+    (None elsewhere), raises AssertionError on a mismatch (every rank raises together)"""
+    n_rows = n_rows or int(os.environ.get("SHARD_ROWS", "400000"))
     data = bench.light_curve(n_rows)
     n_ens, n_beta = 4, 8
     st = bench.chain_state(n_ens, n_beta, 5)
@@ -46,20 +45,40 @@ def main():
     flags = [None] * world
     dist.all_gather_object(flags, same)
     ok = all(flags)
+    err, msg = None, None
     if rank == 0:
-        f = capi.Engine("simplesin5", n_ens, n_beta, seed=3, device=local)
-        f.set_data(data)
-        f.set_bounds(bench.LO, bench.HI)
-        f.set_chains(0, f.n_chains, **st)
-        f.run(3, 7, prob_every=1, params_chains=1)
-        tr1, out1 = f.read_trace(), f.get_chains()
-        for k in ("accept", "reject", "swapcount", "n_iter"):
-            assert (out[k] == out1[k]).all(), k
-        np.testing.assert_allclose(tr["prob"], tr1["prob"], rtol=1e-9)
-        np.testing.assert_allclose(out["params"], out1["params"], rtol=1e-9)
-        assert ok, "ranks disagree"
-        print(f"shard_check ok: {world} ranks x {n_rows // world} rows == 1 GPU x {n_rows} rows; "
-              f"{int(out['n_iter'].sum())} chain-steps, ranks bit-identical")
+        try:
+            f = capi.Engine("simplesin5", n_ens, n_beta, seed=3, device=local)
+            f.set_data(data)
+            f.set_bounds(bench.LO, bench.HI)
+            f.set_chains(0, f.n_chains, **st)
+            f.run(3, 7, prob_every=1, params_chains=1)
+            tr1, out1 = f.read_trace(), f.get_chains()
+            for k in ("accept", "reject", "swapcount", "n_iter"):
+                assert (out[k] == out1[k]).all(), k
+            np.testing.assert_allclose(tr["prob"], tr1["prob"], rtol=1e-9)
+            np.testing.assert_allclose(out["params"], out1["params"], rtol=1e-9)
+            assert ok, "ranks disagree"
+            f.close()
+            msg = (f"shard_check ok: {world} ranks x {n_rows // world} rows == 1 GPU x {n_rows} rows; "
+                   f"{int(out['n_iter'].sum())} chain-steps, ranks bit-identical")
+        except AssertionError as ex:
+            err = "data-sharded run differs from the single-GPU run: %s" % (str(ex)[:300],)
+    e.close()
+    errs = [err]
+    dist.broadcast_object_list(errs, src=0)
+    if errs[0]:
+        raise AssertionError(errs[0])
+    return msg
+
+
+def main():
+    rank, world, local = bench.dist_env()
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    msg = check(rank, world, local)
+    if rank == 0:
+        print(msg)
     dist.destroy_process_group()
 
 
