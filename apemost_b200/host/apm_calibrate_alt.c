@@ -1,25 +1,22 @@
 /*
  * apm_calibrate_alt.c -- the reference's alternate step-width calibrator (-DCALIBRATE_ALTERNATE)
- * over the GPU engine:
+ * over the GPU engine (markov_chain_calibrate_alt, reference src/markov_chain_calibrate.c:916-1037).
  *
- *   assess_acceptance_rate        reference src/markov_chain.c:117-224
- *   markov_chain_calibrate_alt    reference src/markov_chain_calibrate.c:916-1037
+ * The scheme: sweep over the parameters; measure each one's acceptance rate at its current width
+ * (apm_assess.c, i.e. apm_gpu_steps on the device) and move the width by a fraction of the rate's
+ * distance from the target; ask for more accurate measurements from sweep to sweep (at most
+ * MAX_ACCURACY_IMPROVEMENT times better than the last sweep's average), skipping parameters that
+ * are already measured ten times better than that; stop when the largest distance seen in a
+ * sweep and the summed accuracies are both small.
  *
- * Both are sequential, data-dependent host algorithms around one inner loop -- "n more steps of
- * this kind, remember which were accepted" -- and that loop is what the engine provides
- * (apm_gpu_steps).  The host keeps the reference's control flow and arithmetic, including its
- * quirks: the acceptance rate is taken from the counter as it stood BEFORE the last step
- * (:146,161 assign `accepts` at the top of the loop body), and the deviation statistics go
- * through the integer abs() (:182-183).
- *
- * CALIBRATE_MULTILIN (apm_calibrate_multilin.c) sits on the same assessment plus a linear
- * regression; CALIBRATE_QUADRATIC is not built.
+ * Kept from the reference, since calibration_results and calibration_progress.data must match:
+ *  - the fraction is best * SCALE_LIN_WORST + SCALE_MIN where `best` starts at 1 and is replaced by
+ *    a sweep's SUMMED accuracy whenever that sweep's AVERAGE accuracy beats it (:1014-1016);
+ *  - a move below -1 becomes -0.9 (:1002-1003);
+ *  - the give-up test is iterations > iter_limit * n_par, answered with exit(1) (:1010-1013).
  */
 #include "apm_session.h"
 
-#ifndef ACCURACY_DEVIATION_FACTOR
-#define ACCURACY_DEVIATION_FACTOR 0.25 /* reference src/markov_chain.c:91-98 */
-#endif
 #ifndef MAX_ACCURACY_IMPROVEMENT
 #define MAX_ACCURACY_IMPROVEMENT 2.8   /* reference src/markov_chain_calibrate.c:916-925 */
 #endif
@@ -30,143 +27,87 @@
 #define SCALE_MIN 0.4
 #endif
 
-static double abs_double(double x) {
-	return x < 0 ? -x : x;
-}
+typedef struct {
+	apm_session * s;
+	int g;
+	mcmc * m;
+	unsigned int n_par, steps_used;
+	double target;
+	double * known_to;     /* [n_par] accuracy of each parameter's last measurement */
+	double sweep_average;  /* average accuracy of the previous sweep (0 before the first) */
+	double best;           /* see the header comment */
+	FILE * progress;
+} alt_state;
 
-unsigned int apm_assess_acceptance_rate(apm_session * s, int g, unsigned int param,
-		double desired_acceptance_rate, double min_accuracy, double max_accuracy,
-		double * acceptance_rate, double * accuracy) {
-	mcmc * m = s->chains[g];
-	const unsigned int n_par = get_n_par(m);
-	const int kind = param < n_par ? (int) param : (int) n_par;
-	unsigned int i = 0, j, n = 40, maxdev;
-	unsigned long accepts;
-	double stdev, accept_rate, required_accuracy;
-	unsigned char * acceptslog = NULL, * chunk = NULL;
-	unsigned char * select = (unsigned char *) calloc(s->n_chains, 1);
-	select[g] = 1;
+/* one sweep; returns the largest |rate - target| met and leaves the summed accuracy in *summed */
+static double alt_sweep(alt_state * a, double * summed) {
+	const double ask_for = a->sweep_average / MAX_ACCURACY_IMPROVEMENT;
+	double farthest = 0;
+	unsigned int i;
+	printf("calculating for up to %f accuracy\n", ask_for);
+	*summed = 0;
+	for (i = 0; i < a->n_par; i++) {
+		double rate, accuracy, off, move;
+		if (a->known_to[i] < 0.1 * a->sweep_average)
+			continue;
+		a->steps_used += apm_assess_acceptance_rate(a->s, a->g, i, a->target, ask_for, 1 /* no upper limit */,
+				&rate, &accuracy);
+		printf("%d: a/r: %f (+-%f); desired: %f; steps: %f\n", i, rate, accuracy, a->target,
+				get_steps_for_normalized(a->m, i));
+		if (a->progress != NULL)
+			fprintf(a->progress, "%d\t%d\t%f\t%f\t%f\n", i + 1, a->steps_used, get_steps_for_normalized(a->m, i),
+					rate, accuracy);
+		*summed += accuracy;
+		a->known_to[i] = accuracy;
 
-	reset_accept_rejects(m);
-	apm_session_push(s, g, 1);
-	while (1) {
-		acceptslog = (unsigned char *) realloc(acceptslog, n);
-		chunk = (unsigned char *) realloc(chunk, (size_t) (n - i) * s->n_chains);
-		assert(acceptslog != NULL && chunk != NULL);
-		/* for (; i < n; i++) { markov_chain_step[_for]; mcmc_check_best; log the outcome } */
-		apm_gpu_check(s, apm_gpu_steps(s->gpu, select, kind, (long long) (n - i), chunk), "stepping");
-		for (j = i; j < n; j++)
-			acceptslog[j] = chunk[(size_t) (j - i) * s->n_chains + g];
-		i = n;
-		/* `accepts` holds the counter read before the last step */
-		accepts = 0;
-		for (j = 0; j + 1 < n; j++)
-			accepts += acceptslog[j];
-		accept_rate = accepts / (double) n;
-
-		/* get max deviation */
-		accepts = 0;
-		stdev = 0;
-		maxdev = 0 + 1;
-		for (j = 0; j < n; j++) {
-			int dev;
-			if (acceptslog[j] != 0)
-				accepts++;
-			stdev += pow(accepts - accept_rate * j, 2);
-			dev = (int) (accepts - accept_rate * j); /* abs() takes an int */
-			if (dev < 0)
-				dev = -dev;
-			if ((unsigned int) dev > maxdev)
-				maxdev = (unsigned int) dev;
-		}
-		stdev = sqrt(stdev / n) * 2;
-		(void) stdev;
-
-		required_accuracy = abs_double(accept_rate - desired_acceptance_rate) * ACCURACY_DEVIATION_FACTOR;
-		if (required_accuracy < 0.005)
-			required_accuracy = 0.005;
-		if (required_accuracy < min_accuracy)
-			required_accuracy = min_accuracy;
-		if (required_accuracy > max_accuracy)
-			required_accuracy = max_accuracy;
-
-		*acceptance_rate = accept_rate;
-		*accuracy = maxdev / 1. / n;
-		if (*accuracy <= required_accuracy)
-			break;
-		assert(maxdev / required_accuracy >= n);
-		n = ((unsigned int) ((maxdev / 1. / required_accuracy) / 8) + 1) * 8;
+		off = rate - a->target;
+		move = off * (a->best * SCALE_LIN_WORST + SCALE_MIN);
+		if (move < -1)
+			move = -0.9;
+		if (farthest < (off < 0 ? -off : off))
+			farthest = off < 0 ? -off : off;
+		set_steps_for(a->m, get_steps_for(a->m, i) * (1 + move), i);
+		printf("%d: new steps: %f\n", i, get_steps_for_normalized(a->m, i));
 	}
-	apm_session_pull(s, g, 1);
-	free(acceptslog);
-	free(chunk);
-	free(select);
-	return n;
+	return farthest;
 }
 
 void apm_calibrate_alt(apm_session * s, int g, double desired_acceptance_rate, const double max_ar_deviation,
 		const unsigned int iter_limit) {
-	mcmc * m = s->chains[g];
-	unsigned int i, j;
-	double current_acceptance_rate, accuracy;
-	const unsigned int n_par = get_n_par(m);
-	double scale, movedirection, move, max_deviation;
-	double worst_accuracy = 0, worst_accuracy_previous = 0, best_worst_accuracy = 1;
-	unsigned int iter = 0;
-	FILE * progress_plot_file = fopen(apm_out_path("calibration_progress.data"), "w");
-	gsl_vector * accuracies = gsl_vector_alloc(n_par);
-	gsl_vector_set_all(accuracies, 0);
+	alt_state a;
+	unsigned int i;
+	a.s = s;
+	a.g = g;
+	a.m = s->chains[g];
+	a.n_par = get_n_par(a.m);
+	a.steps_used = 0;
+	a.target = desired_acceptance_rate;
+	a.known_to = (double *) calloc(a.n_par, sizeof(double));
+	a.sweep_average = 0;
+	a.best = 1;
+	a.progress = fopen(apm_out_path("calibration_progress.data"), "w");
+	assert(a.known_to != NULL);
+	for (i = 0; i < a.n_par; i++)
+		a.known_to[i] = 0;
 
-	/* a point in step-width space is assessed parameter by parameter; each step width moves in
-	 * proportion to how far its acceptance rate is from the target, less and less once the
-	 * assessments have settled down */
-	while (1) {
-		max_deviation = 0;
-		for (j = 0; j < 1; j++) {
-			printf("calculating for up to %f accuracy\n", worst_accuracy_previous / MAX_ACCURACY_IMPROVEMENT);
-			worst_accuracy = 0;
-			for (i = 0; i < n_par; i++) {
-				if (gsl_vector_get(accuracies, i) < 0.1 * worst_accuracy_previous)
-					continue;
-				iter += apm_assess_acceptance_rate(s, g, i, desired_acceptance_rate,
-						worst_accuracy_previous / MAX_ACCURACY_IMPROVEMENT, 1 /* no restriction */,
-						&current_acceptance_rate, &accuracy);
-				printf("%d: a/r: %f (+-%f); desired: %f; steps: %f\n", i, current_acceptance_rate, accuracy,
-						desired_acceptance_rate, get_steps_for_normalized(m, i));
-				if (progress_plot_file != NULL)
-					fprintf(progress_plot_file, "%d\t%d\t%f\t%f\t%f\n", i + 1, iter,
-							get_steps_for_normalized(m, i), current_acceptance_rate, accuracy);
-				worst_accuracy += accuracy;
-				gsl_vector_set(accuracies, i, accuracy);
-
-				movedirection = current_acceptance_rate - desired_acceptance_rate;
-				scale = best_worst_accuracy * SCALE_LIN_WORST + SCALE_MIN;
-				assert(scale > 0);
-				move = movedirection * scale;
-				if (move < -1)
-					move = -0.9;
-				if (max_deviation < abs_double(movedirection))
-					max_deviation = abs_double(movedirection);
-				set_steps_for(m, get_steps_for(m, i) * (1 + move), i);
-				printf("%d: new steps: %f\n", i, get_steps_for_normalized(m, i));
-			}
-			if (iter > iter_limit * n_par) {
-				fprintf(stderr, "calibration failed: iteration limit reached\n");
-				exit(1);
-			}
-			worst_accuracy_previous = worst_accuracy / n_par;
-			if (worst_accuracy_previous < best_worst_accuracy)
-				best_worst_accuracy = worst_accuracy;
+	for (;;) {
+		double summed, farthest = alt_sweep(&a, &summed);
+		if (a.steps_used > iter_limit * a.n_par) {
+			fprintf(stderr, "calibration failed: iteration limit reached\n");
+			exit(1);
 		}
-		printf("max deviation: %f; ", max_deviation);
-		if (max_deviation < max_ar_deviation && worst_accuracy < max_ar_deviation * 2) {
-			printf("small deviation: %f; quitting\n", max_deviation);
+		a.sweep_average = summed / a.n_par;
+		if (a.sweep_average < a.best)
+			a.best = summed;
+		printf("max deviation: %f; ", farthest);
+		if (farthest < max_ar_deviation && summed < max_ar_deviation * 2) {
+			printf("small deviation: %f; quitting\n", farthest);
 			break;
 		}
 	}
-	if (progress_plot_file != NULL)
-		fclose(progress_plot_file);
-	gsl_vector_free(accuracies);
-	/* the step widths chosen last live in the host struct only */
+	if (a.progress != NULL)
+		fclose(a.progress);
+	free(a.known_to);
+	/* the widths chosen last live in the host struct only */
 	apm_session_push(s, g, 1);
 }
