@@ -275,6 +275,27 @@ class EngineBase:
         return {"n": n, "sum_dl": sum_dl, "sum_params": sp, "sum_params_sq": sp2}
 
 
+    # -- marginal statistics (histograms, batch means) -----------------------------
+    def set_marginals(self, which_chains, n_bins=200, batch_size=0, max_batches=0):
+        f = self._fn("set_marginals")
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_ulonglong, C.c_int]
+        self._check(f(self._h, int(which_chains), int(n_bins), int(batch_size), int(max_batches)))
+        self._marg = (which_chains, n_bins, max_batches)
+
+    def get_marginals(self):
+        which, n_bins, cap = self._marg
+        slots = {1: self.n_ensembles, 2: self.n_chains}[which]
+        counts = np.zeros((slots, self.n_par, n_bins), dtype=np.uint64)
+        means = np.zeros((slots, self.n_par, max(cap, 1)))
+        n_values = np.zeros(slots, dtype=np.uint64)
+        n_batches = np.zeros(slots, dtype=np.uint64)
+        f = self._fn("get_marginals")
+        f.argtypes = [C.c_void_p] * 5
+        self._check(f(self._h, counts.ctypes.data, means.ctypes.data if cap > 0 else None, n_values.ctypes.data,
+                      n_batches.ctypes.data))
+        return {"counts": counts, "batch_means": means[:, :, :cap], "n_values": n_values, "n_batches": n_batches}
+
+
 # ---- the product library -------------------------------------------------------
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libapemost_gpu.so")
 _lib = None
@@ -362,3 +383,13 @@ def measure_fp64_peak(device=0, seconds=0.2) -> float:
     if rc != 0:
         raise EngineError(rc, "fp64 peak microbenchmark failed")
     return out.value
+
+
+def measure_fp64_per_clock(device=0):
+    """(FP64 lane-operations per SM per clock, number of SMs): the pipe's issue rate from clock64()."""
+    lib = load_library()
+    out, n_sm = C.c_double(), C.c_int()
+    rc = lib.apm_gpu_measure_fp64_per_clock(C.c_int(device), C.byref(out), C.byref(n_sm))
+    if rc != 0:
+        raise EngineError(rc, "fp64 per-clock microbenchmark failed")
+    return out.value, n_sm.value

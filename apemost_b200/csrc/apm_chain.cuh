@@ -112,6 +112,17 @@ struct DevState {
 	// trace of the current run
 	double * tr_prob, *tr_dl, *tr_params;
 	int tr_prob_every, tr_params_chains, tr_dumped;
+	// marginal statistics of the recorded chains (apm_gpu_set_marginals): what the
+	// reference's analyse derives from <name>-chain-<i>.prob.dump (src/analyse.c:115-247) -- per
+	// parameter a histogram of marg_bins uniform bins over [min, max] and the means of consecutive
+	// batches of marg_batch values.  marg_mode: 0 off, 1 rung 0 of every ensemble, 2 every chain.
+	int marg_mode, marg_bins, marg_cap;
+	unsigned long long marg_batch;
+	unsigned long long * marg_counts; // [slots][n_par][marg_bins]
+	double * marg_bsum;               // [slots][n_par]  running sum of the open batch
+	double * marg_means;              // [slots][n_par][marg_cap]
+	unsigned long long * marg_n;      // [slots] values seen
+	unsigned long long * marg_nb;     // [slots] batches closed
 	// tiled path: the run's step counter lives on the device, so that a whole round of launches can be
 	// replayed as a CUDA graph without any per-step argument from the host.  run_ctr[0] = steps recorded
 	// so far in this apm_gpu_run call, run_ctr[1] = the control kernel's "blocks done" ticket.
@@ -265,6 +276,65 @@ APM_D void chain_finalize(const DevState & S, int g, double sum, const double * 
 	chain_finalize_value(S, g, M::finish(S.beta[g], sum, prior_new, q, S.model_const), prior_new, pre_logu);
 }
 
+// ---- marginal statistics ---------------------------------------------------
+// which slot of the marg_* arrays chain g feeds (-1: none); same rule as the parameter dump
+APM_D int marg_slot(const DevState & S, int g) {
+	if (S.marg_mode == 2)
+		return g;
+	if (S.marg_mode == 1 && S.k_offset + g % S.n_beta == 0)
+		return g / S.n_beta;
+	return -1;
+}
+// edge k of gsl_histogram_set_ranges_uniform(h, lo, hi) with create_hist's widened last edge
+// (reference src/histogram.c:34-43): the same expressions, so the same doubles
+APM_D double marg_edge(int k, int nb, double lo, double hi) {
+	const double f1 = (double) (nb - k) / (double) nb, f2 = (double) k / (double) nb;
+	double e = add_rn(mul_rn(f1, lo), mul_rn(f2, hi));
+	if (k == nb)
+		e = add_rn(e, (hi - lo) / 10000);
+	return e;
+}
+// one value of parameter i of the chain in `slot`: gsl_histogram_increment (the bin with
+// edge[b] <= v < edge[b + 1]; outside all bins: not counted) and calc_mcmc_error's batches
+// (reference src/analyse.c:115-142: a batch closes when (values so far) % batch == batch - 1, its
+// mean is its sum over the batch SIZE).  seen / closed = the slot's counters before this step.
+APM_D void marg_add_value(const DevState & S, int slot, int i, double v, unsigned long long seen,
+		unsigned long long closed) {
+	const int nb = S.marg_bins, n = S.n_par;
+	const double lo = S.pmin[i], hi = S.pmax[i], top = marg_edge(nb, nb, lo, hi);
+	if (v >= lo && v < top) {
+		int b = (int) ((v - lo) / (top - lo) * nb);
+		b = b < 0 ? 0 : (b > nb - 1 ? nb - 1 : b);
+		while (b > 0 && v < marg_edge(b, nb, lo, hi))
+			b--;
+		while (b < nb - 1 && v >= marg_edge(b + 1, nb, lo, hi))
+			b++;
+		S.marg_counts[((size_t) slot * n + i) * nb + b]++;
+	}
+	double & bs = S.marg_bsum[(size_t) slot * n + i];
+	bs += v;
+	if (S.marg_batch > 0 && (seen + 1) % S.marg_batch == S.marg_batch - 1) {
+		if (closed < (unsigned long long) S.marg_cap)
+			S.marg_means[((size_t) slot * n + i) * S.marg_cap + closed] = bs / (double) S.marg_batch;
+		bs = 0;
+	}
+}
+// after all parameters of the step went in
+APM_D void marg_step_done(const DevState & S, int slot, unsigned long long seen, unsigned long long closed) {
+	S.marg_n[slot] = seen + 1;
+	if (S.marg_batch > 0 && (seen + 1) % S.marg_batch == S.marg_batch - 1)
+		S.marg_nb[slot] = closed + 1;
+}
+APM_D void chain_marginals(const DevState & S, int g, const double * params) {
+	const int slot = marg_slot(S, g);
+	if (slot < 0)
+		return;
+	const unsigned long long seen = S.marg_n[slot], closed = S.marg_nb[slot];
+	for (int i = 0; i < S.n_par; i++)
+		marg_add_value(S, slot, i, params[i], seen, closed);
+	marg_step_done(S, slot, seen, closed);
+}
+
 // the bookkeeping of one sampler iteration after the step (reference
 // src/parallel_tempering.c:396-401): check_best, append (n_iter++), the prob-chain
 // line and the parameter dump, plus the on-device accumulators
@@ -296,6 +366,8 @@ APM_D void chain_record(const DevState & S, int g, long long step_index) {
 		S.stat_sum_p[(size_t) g * n + i] += v;
 		S.stat_sum_p2[(size_t) g * n + i] += v * v;
 	}
+	if (S.marg_mode)
+		chain_marginals(S, g, S.params + (size_t) g * n);
 }
 
 // chain_finalize_value's state transition + chain_record for a FULL step whose outcome was decided
@@ -345,6 +417,8 @@ APM_D void chain_book_step(const DevState & S, int g, int accepted, double prob_
 		S.stat_sum_p[(size_t) g * n + i] += v;
 		S.stat_sum_p2[(size_t) g * n + i] += v * v;
 	}
+	if (S.marg_mode)
+		chain_marginals(S, g, params_after);
 }
 
 // ---- warp-cooperative forms of chain_finalize / chain_record (fused and cluster paths) ------
@@ -415,7 +489,16 @@ APM_D void chain_record_warp(const DevState & S, int g, long long step_index, in
 	const double prob = S.prob[g], dl = S.prob[g] - S.prior[g];
 	const bool better = prob > S.prob_best[g]; // mcmc_check_best
 	const double v = lane < n ? S.params[(size_t) g * n + lane] : 0.0;
+	const int mslot = S.marg_mode ? marg_slot(S, g) : -1;
+	const unsigned long long m_seen = mslot >= 0 ? S.marg_n[mslot] : 0, m_closed = mslot >= 0 ? S.marg_nb[mslot] : 0;
 	__syncwarp();
+	if (mslot >= 0) { // the marginal statistics: a parameter per lane, the counters by one lane afterwards
+		if (lane < n)
+			marg_add_value(S, mslot, lane, v, m_seen, m_closed);
+		__syncwarp();
+		if (lane == 0)
+			marg_step_done(S, mslot, m_seen, m_closed);
+	}
 	if (lane < n) {
 		if (better)
 			S.params_best[(size_t) g * n + lane] = v;

@@ -203,23 +203,37 @@ __global__ void __launch_bounds__(LL_THREADS, 1) loglik_tiled_kernel(const LLArg
 
 	// ---- producer (thread 0): walks this CTA's items chunk by chunk, LL_STAGES - 1 ahead
 	int p_item = blockIdx.x;
-	int p_k = 0;
 	uint32_t p_n = 0;
-	auto produce = [&]() {
-		if (p_item >= n_items)
-			return;
+	// (the producer's position is kept incrementally -- stage, phase, source address, chunks left in
+	// its item -- so that issuing a chunk is a dozen instructions: the issuing thread's warp stands
+	// still meanwhile, and the other warps wait for it at the end of every item)
+	uint32_t p_st = 0, p_phase = 1;          // stage of the next chunk; parity its `empty` barrier must have completed
+	int p_left = 0;                          // chunks left in the producer's current item
+	const double * p_src = nullptr;          // where the next chunk of that item starts
+	auto produce_item = [&]() {              // enter item p_item (one division per item)
 		const int k0 = (p_item / n_ctiles) * a.chunks_per_split;
-		const int nk = min(a.chunks_per_split, a.n_chunks - k0);
-		const uint32_t st = p_n % LL_STAGES;
-		if (p_n >= LL_STAGES) // chunk p_n - LL_STAGES must have been read by every warp
-			mbar_wait(&empty[st], ((p_n / LL_STAGES) + 1u) & 1u);
-		mbar_arrive_expect_tx(&full[st], CHUNK_BYTES);
-		tma_bulk_g2s(sdata + st * CHUNK, a.data + (size_t) (k0 + p_k) * CHUNK * M::ROW_W, CHUNK_BYTES,
-				&full[st]);
+		p_left = min(a.chunks_per_split, a.n_chunks - k0);
+		p_src = a.data + (size_t) k0 * CHUNK * M::ROW_W;
+	};
+	if (p_item < n_items)
+		produce_item();
+	auto produce = [&]() {
+		if (p_left == 0)
+			return;
+		if (p_n >= LL_STAGES) // the chunk that was in this stage must have been read by every warp
+			mbar_wait(&empty[p_st], p_phase);
+		mbar_arrive_expect_tx(&full[p_st], CHUNK_BYTES);
+		tma_bulk_g2s(sdata + p_st * CHUNK, p_src, CHUNK_BYTES, &full[p_st]);
+		p_src += (size_t) CHUNK * M::ROW_W;
 		p_n++;
-		if (++p_k == nk) {
-			p_k = 0;
+		if (++p_st == LL_STAGES) {
+			p_st = 0;
+			p_phase ^= 1u;
+		}
+		if (--p_left == 0) {
 			p_item += gridDim.x;
+			if (p_item < n_items)
+				produce_item();
 		}
 	};
 	if (tid == 0)
@@ -610,6 +624,14 @@ __device__ inline DevState fused_localize_block_by(const DevState & S, int ens, 
 	}
 	if (S.tr_params != nullptr)
 		L.tr_params = S.tr_params + (S.tr_params_chains == 2 ? base : (size_t) ens) * n;
+	if (S.marg_mode) { // slot 0 of the local view = this block's first chain (mode 2) or its ensemble (mode 1)
+		const size_t slot0 = S.marg_mode == 2 ? base : (size_t) ens;
+		L.marg_counts = S.marg_counts + slot0 * n * S.marg_bins;
+		L.marg_bsum = S.marg_bsum + slot0 * n;
+		L.marg_means = S.marg_means + slot0 * n * S.marg_cap;
+		L.marg_n = S.marg_n + slot0;
+		L.marg_nb = S.marg_nb + slot0;
+	}
 	return L;
 }
 
@@ -1896,6 +1918,34 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double * out, int iters,
 		}
 	}
 	out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+// the same per CLOCK: every block brackets its DFMA stream with clock64(), so the answer (FP64
+// lane-operations per SM per clock; 64 by the architecture) does not depend on what the clocks do
+// under a long pure-DFMA load (the per-second figure above sags with them: that load is the one
+// thing on this GPU that runs into the power limit)
+__global__ void __launch_bounds__(256) fp64_peak_clock_kernel(double * out, long long * cycles, int iters, double a, double b) {
+	double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
+	double x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+	__syncthreads();
+	const long long t0 = clock64();
+	for (int i = 0; i < iters; i++) {
+#pragma unroll
+		for (int u = 0; u < 32; u++) {
+			x0 = fma(x0, a, b);
+			x1 = fma(x1, a, b);
+			x2 = fma(x2, a, b);
+			x3 = fma(x3, a, b);
+			x4 = fma(x4, a, b);
+			x5 = fma(x5, a, b);
+			x6 = fma(x6, a, b);
+			x7 = fma(x7, a, b);
+		}
+	}
+	const long long t1 = clock64();
+	out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+	if (threadIdx.x == 0)
+		cycles[blockIdx.x] = t1 - t0;
 }
 
 } // namespace apm

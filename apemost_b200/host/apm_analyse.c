@@ -139,6 +139,14 @@ static int evidence_from_accumulators(mcmc ** chains, unsigned int n_beta, doubl
 	return ok ? 0 : 1;
 }
 
+static int file_exists(const char * name) {
+	FILE * f = fopen(apm_out_path(name), "r");
+	if (f == NULL)
+		return 0;
+	fclose(f);
+	return 1;
+}
+
 void analyse_data_probability(void) {
 	double sum = 0, sum2 = 0, acc_sum = 0;
 	int e, n_ok = 0, n_acc = 0;
@@ -147,7 +155,15 @@ void analyse_data_probability(void) {
 		double lnz;
 		apm_set_output_dir(e);
 		chains = chains_from_files();
-		if (evidence_from_dumps(chains, N_BETA, &lnz) == 0) {
+		if (!file_exists("prob-chain0.dump") && evidence_from_accumulators(chains, N_BETA, &lnz) == 0) {
+			/* a run without text dumps (APM_NO_DUMPS): the evidence block from the accumulators */
+			if (N_ENSEMBLES > 1)
+				printf("ensemble %d: ", e);
+			print_evidence(lnz);
+			sum += lnz;
+			sum2 += lnz * lnz;
+			n_ok++;
+		} else if (evidence_from_dumps(chains, N_BETA, &lnz) == 0) {
 			if (N_ENSEMBLES > 1)
 				printf("ensemble %d: ", e);
 			print_evidence(lnz);
@@ -226,10 +242,77 @@ static double batch_means_error(const double mean, const char * filename, unsign
 	return sqrt(errorsum / nbatches);
 }
 
+/* run_marginals: the histogram bins and batch means of the recorded chains as `run` took them from
+ * the on-device accumulators (format: apm_phases.c, write_run_marginals) */
+typedef struct {
+	int n_par, n_bins, n_slots;
+	unsigned long batch;
+	unsigned long long * n_values, * n_batches; /* [n_slots] */
+	unsigned long long * counts;                /* [n_slots][n_par][n_bins] */
+	double ** means;                            /* [n_slots * n_par] -> [n_batches] */
+} run_marginals;
+
+static void free_run_marginals(run_marginals * m) {
+	int i;
+	if (m == NULL)
+		return;
+	if (m->means != NULL)
+		for (i = 0; i < m->n_slots * m->n_par; i++)
+			free(m->means[i]);
+	free(m->means); free(m->counts); free(m->n_values); free(m->n_batches);
+	free(m);
+}
+
+static run_marginals * read_run_marginals(void) {
+	FILE * f = fopen(apm_out_path("run_marginals"), "r");
+	run_marginals * m;
+	int k, j, b, ok;
+	if (f == NULL)
+		return NULL;
+	m = (run_marginals *) calloc(1, sizeof(*m));
+	ok = fscanf(f, " marginals %d %d %lu %d", &m->n_par, &m->n_bins, &m->batch, &m->n_slots) == 4
+			&& m->n_par > 0 && m->n_bins > 0 && m->n_slots > 0;
+	if (ok) {
+		m->n_values = (unsigned long long *) calloc(m->n_slots, sizeof(*m->n_values));
+		m->n_batches = (unsigned long long *) calloc(m->n_slots, sizeof(*m->n_batches));
+		m->counts = (unsigned long long *) calloc((size_t) m->n_slots * m->n_par * m->n_bins, sizeof(*m->counts));
+		m->means = (double **) calloc((size_t) m->n_slots * m->n_par, sizeof(double *));
+	}
+	for (k = 0; ok && k < m->n_slots; k++) {
+		int chain;
+		ok = fscanf(f, " chain %d %llu %llu", &chain, &m->n_values[k], &m->n_batches[k]) == 3 && chain == k;
+		for (j = 0; ok && j < m->n_par; j++) {
+			double * bm = (double *) calloc(m->n_batches[k] + 1, sizeof(double));
+			m->means[k * m->n_par + j] = bm;
+			ok = fscanf(f, " counts") == 0;
+			for (b = 0; ok && b < m->n_bins; b++)
+				ok = fscanf(f, "%llu", &m->counts[((size_t) k * m->n_par + j) * m->n_bins + b]) == 1;
+			ok = ok && fscanf(f, " means") == 0;
+			for (b = 0; ok && b < (int) m->n_batches[k]; b++)
+				ok = fscanf(f, "%lf", &bm[b]) == 1;
+		}
+	}
+	fclose(f);
+	if (!ok) {
+		free_run_marginals(m);
+		return NULL;
+	}
+	return m;
+}
+
+/* calc_mcmc_error (reference src/analyse.c:115-142) with the batch means at hand */
+static double batch_means_error_from(const double mean, const double * batch_mean, unsigned long long nbatches) {
+	double errorsum = 0;
+	unsigned long long b;
+	for (b = 0; b < nbatches; b++)
+		errorsum += pow(batch_mean[b] - mean, 2);
+	return sqrt(errorsum / nbatches);
+}
+
 /* (called for all parameters side by side: what it has to say goes to `report`, printed in
  * parameter order by the caller) */
 static void marginal_distribution(mcmc ** chains, unsigned int n_beta, unsigned int param, char * report,
-		size_t report_size) {
+		size_t report_size, const run_marginals * acc) {
 	size_t used = 0;
 	const char * paramname = get_params_descr(chains[0])[param];
 	double lo = get_params_min_for(chains[0], param), hi = get_params_max_for(chains[0], param);
@@ -237,6 +320,7 @@ static void marginal_distribution(mcmc ** chains, unsigned int n_beta, unsigned 
 	gsl_histogram * h;
 	double iter, mean, sigma;
 	unsigned int i, filecount = 1;
+	int from_accumulators = 0;
 	FILE * out;
 #ifdef HISTOGRAMS_ALLCHAINS
 	filecount = n_beta;
@@ -255,9 +339,21 @@ static void marginal_distribution(mcmc ** chains, unsigned int n_beta, unsigned 
 	}
 #endif
 	h = uniform_histogram(NBINS, lo, hi);
-	for (i = 0; i < filecount; i++) {
-		snprintf(in_name, sizeof(in_name), "%s-chain-%d.prob.dump", paramname, i);
-		fill_from_file(h, apm_out_path(in_name), NULL, NULL);
+	/* the parameter dumps are there: read them, like the reference.  They are not (a run with
+	 * APM_NO_DUMPS): the same bins as `run` counted them on the device. */
+	snprintf(in_name, sizeof(in_name), "%s-chain-%d.prob.dump", paramname, 0);
+	if (acc != NULL && !file_exists(in_name) && acc->n_bins == NBINS && acc->n_slots >= (int) filecount
+			&& (int) param < acc->n_par) {
+		unsigned int b;
+		for (i = 0; i < filecount; i++)
+			for (b = 0; b < NBINS; b++)
+				h->bin[b] += (double) acc->counts[((size_t) i * acc->n_par + param) * NBINS + b];
+		from_accumulators = 1;
+	} else {
+		for (i = 0; i < filecount; i++) {
+			snprintf(in_name, sizeof(in_name), "%s-chain-%d.prob.dump", paramname, i);
+			fill_from_file(h, apm_out_path(in_name), NULL, NULL);
+		}
 	}
 	iter = gsl_histogram_sum(h);
 	gsl_histogram_scale(h, (hi - lo) / NBINS / iter);
@@ -271,7 +367,10 @@ static void marginal_distribution(mcmc ** chains, unsigned int n_beta, unsigned 
 	for (i = 0; i < filecount; i++) {
 		double err;
 		snprintf(in_name, sizeof(in_name), "%s-chain-%d.prob.dump", paramname, i);
-		err = batch_means_error(mean, apm_out_path(in_name), (unsigned long) sqrt(iter));
+		if (from_accumulators)
+			err = batch_means_error_from(mean, acc->means[(size_t) i * acc->n_par + param], acc->n_batches[i]);
+		else
+			err = batch_means_error(mean, apm_out_path(in_name), (unsigned long) sqrt(iter));
 		if (used < report_size)
 			used += snprintf(report + used, report_size - used, "mcmc error estimate of %s: %f %s\n", paramname, err,
 					err > sigma * 0.01 ? "** high!" : " (ok)");
@@ -293,16 +392,18 @@ void analyse_marginal_distributions(void) {
 		{
 			enum { REPORT = 256 * (N_BETA + 2) };
 			char * reports = (char *) calloc(n_par, REPORT);
+			run_marginals * acc = read_run_marginals();
 			int p;
 			for (i = 0; i < n_par; i++)
 				printf("reading values: chain %3d parameter %s   \r", 0, get_params_descr(chains[0])[i]);
 			fflush(stdout);
 #pragma omp parallel for schedule(dynamic, 1)
 			for (p = 0; p < (int) n_par; p++)
-				marginal_distribution(chains, N_BETA, (unsigned int) p, reports + (size_t) p * REPORT, REPORT);
+				marginal_distribution(chains, N_BETA, (unsigned int) p, reports + (size_t) p * REPORT, REPORT, acc);
 			for (i = 0; i < n_par; i++)
 				fputs(reports + (size_t) i * REPORT, stdout);
 			free(reports);
+			free_run_marginals(acc);
 		}
 		plot = fopen(apm_out_path("marginal_distributions.gnuplot"), "w");
 		assert(plot != NULL);

@@ -336,13 +336,10 @@ static void calibrate_selected(apm_session * s, const unsigned char * select, in
 	long long cap = 0, n_rows = 0;
 	apm_gpu_calib_progress * rows = NULL;
 	int g, rc, n_sel = 0;
-#if defined(CALIBRATE_QUADRATIC)
-#error "of the alternate calibrators CALIBRATE_ALTERNATE and CALIBRATE_MULTILIN are built, CALIBRATE_QUADRATIC is not"
-#endif
-#if defined(CALIBRATE_ALTERNATE) || defined(CALIBRATE_MULTILIN)
+#if defined(CALIBRATE_ALTERNATE) || defined(CALIBRATE_MULTILIN) || defined(CALIBRATE_QUADRATIC)
 	if (!skip) {
 		/* markov_chain_calibrate = burn_in + the alternate calibrator (the reference's precedence:
-		 * MULTILIN before ALTERNATE, src/markov_chain_calibrate.c:1190-1202), one chain after the
+		 * MULTILIN, then QUADRATIC, then ALTERNATE, src/markov_chain_calibrate.c:1190-1202), one chain after the
 		 * other like the reference's loop (src/parallel_tempering.c:173-197 with one thread) */
 		unsigned char * one = (unsigned char *) calloc(s->n_chains, 1);
 		for (g = 0; g < s->n_chains; g++) {
@@ -354,8 +351,10 @@ static void calibrate_selected(apm_session * s, const unsigned char * select, in
 			one[g] = 0;
 			apm_session_pull(s, g, 1);
 			apm_set_output_dir(s->ens_first + g / s->n_beta);
-#ifdef CALIBRATE_MULTILIN
+#if defined(CALIBRATE_MULTILIN)
 			apm_calibrate_multilin(s, g, TARGET_ACCEPTANCE_RATE, MAX_AR_DEVIATION, ITER_LIMIT);
+#elif defined(CALIBRATE_QUADRATIC)
+			apm_calibrate_quadratic(s, g, TARGET_ACCEPTANCE_RATE, MAX_AR_DEVIATION, ITER_LIMIT);
 #else
 			apm_calibrate_alt(s, g, TARGET_ACCEPTANCE_RATE, MAX_AR_DEVIATION, ITER_LIMIT);
 #endif
@@ -791,6 +790,49 @@ static void write_run_statistics(apm_session * s) {
 	free(cnt); free(sdl); free(sp); free(sp2);
 }
 
+/* the marginal statistics `analyse` needs -- per parameter the NBINS-bin histogram of the recorded
+ * chain(s) and the batch means behind the Monte Carlo error estimate -- from the on-device
+ * accumulators (reference src/analyse.c:115-247 derives them from the
+ * parameter dumps).  One file per ensemble:
+ *   marginals <n_par> <n_bins> <batch_size> <n_slots>
+ *   chain <k> <n_values> <n_batches>                    (once per slot)
+ *   counts <n_bins integers>                            (once per parameter)
+ *   means <n_batches values, %.17g>                     (once per parameter) */
+static void write_run_marginals(apm_session * s, int which_chains, unsigned long batch, int max_batches) {
+	const int per_ens = which_chains == 2 ? s->n_beta : 1;
+	const size_t slots = (size_t) s->n_ens * per_ens, np = s->n_par;
+	unsigned long long * counts = (unsigned long long *) calloc(slots * np * NBINS, sizeof(*counts));
+	double * means = (double *) calloc(slots * np * (max_batches > 0 ? max_batches : 1), sizeof(double));
+	unsigned long long * nv = (unsigned long long *) calloc(slots, sizeof(*nv)), * nb = (unsigned long long *) calloc(slots, sizeof(*nb));
+	int e, k, j, b;
+	apm_gpu_check(s, apm_gpu_get_marginals(s->gpu, counts, means, nv, nb), "reading the marginal statistics");
+	for (e = 0; e < s->n_ens; e++) {
+		FILE * f;
+		apm_set_output_dir(s->ens_first + e);
+		f = fopen(apm_out_path("run_marginals"), "w");
+		if (f == NULL)
+			continue;
+		fprintf(f, "marginals %d %d %lu %d\n", s->n_par, (int) NBINS, batch, per_ens);
+		for (k = 0; k < per_ens; k++) {
+			const size_t slot = (size_t) e * per_ens + k;
+			const unsigned long long kept = nb[slot] < (unsigned long long) max_batches ? nb[slot] : (unsigned long long) max_batches;
+			fprintf(f, "chain %d %llu %llu\n", k, nv[slot], kept);
+			for (j = 0; j < s->n_par; j++) {
+				fprintf(f, "counts");
+				for (b = 0; b < NBINS; b++)
+					fprintf(f, " %llu", counts[(slot * np + j) * NBINS + b]);
+				fprintf(f, "\nmeans");
+				for (b = 0; b < (int) kept; b++)
+					fprintf(f, " %.17g", means[(slot * np + j) * max_batches + b]);
+				fprintf(f, "\n");
+			}
+		}
+		fclose(f);
+	}
+	apm_set_output_dir(-1);
+	free(counts); free(means); free(nv); free(nb);
+}
+
 void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 	const int timing = getenv("APM_HOST_TIMING") != NULL;
 	double t_mark = wall_s(), t_a = 0, t_b = 0, t_engine = 0, t_read = 0, t_join = 0;
@@ -811,6 +853,11 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 	int cur = 0;
 	char name[64];
 	int e, i, n_dumped;
+	/* APM_NO_DUMPS=1: no prob-chain<k>.dump / <name>-chain-<i>.prob.dump text at all -- `analyse` then
+	 * works from run_statistics and run_marginals, the on-device accumulators */
+	const int no_dumps = getenv("APM_NO_DUMPS") != NULL;
+	int marg_which = 0, marg_cap = 0;
+	unsigned long marg_batch = 0;
 
 #ifdef DUMP_ALL_CHAINS
 	trace.params_chains = 2;
@@ -820,14 +867,19 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 	n_dumped = n_ens;
 #endif
 	trace.prob_every = 1;
+	if (no_dumps) {
+		trace.params_chains = 0;
+		trace.prob_every = 0;
+		n_dumped = 0;
+	}
 
 	for (e = 0; e < n_ens; e++) {
 		mcmc ** c = apm_ensemble(s, e);
 		apm_set_output_dir(s->ens_first + e);
 		read_calibration_file(c, n_beta);
-		for (i = 0; i < (trace.params_chains == 2 ? n_beta : 1); i++)
+		for (i = 0; i < (trace.params_chains == 2 ? n_beta : (trace.params_chains == 1 ? 1 : 0)); i++)
 			mcmc_open_dump_files(c[i], "-chain", i, mode);
-		for (i = 0; i < n_beta; i++) {
+		for (i = 0; i < (no_dumps ? 0 : n_beta); i++) {
 			snprintf(name, sizeof(name), "prob-chain%d.dump", i);
 			prob_files[e * n_beta + i] = fopen(apm_out_path(name), mode);
 			if (prob_files[e * n_beta + i] == NULL) {
@@ -859,6 +911,28 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 		if (n_swap < 1)
 			n_swap = 1;
 		printf("automatic n_swap: %d\n", n_swap);
+	}
+	/* marginal statistics on the device: the histogram bins and the batches analyse would form from
+	 * the parameter dumps.  calc_mcmc_error's batch size is sqrt(number of dumped values), known in
+	 * advance for a run of a fixed length that starts its files afresh; otherwise (open-ended or
+	 * appending) only the dumps can tell and none are kept here. */
+	for (e = 0; e < n_ens; e++) {
+		apm_set_output_dir(s->ens_first + e);
+		remove(apm_out_path("run_marginals"));
+	}
+	apm_set_output_dir(-1);
+	if (max_iterations != 0 && append != 1) {
+		const unsigned long total = (unsigned long) ((max_iterations + n_swap - 1) / n_swap) * n_swap;
+#ifdef HISTOGRAMS_ALLCHAINS
+		marg_which = 2; /* one histogram per parameter over all chains' values: that many values more */
+		marg_batch = (unsigned long) sqrt((double) total * n_beta);
+#else
+		marg_which = 1;
+		marg_batch = (unsigned long) sqrt((double) total);
+#endif
+		marg_cap = marg_batch > 0 ? (int) (total / marg_batch) + 2 : 0;
+		apm_gpu_check(s, apm_gpu_set_marginals(s->gpu, marg_which, NBINS, marg_batch, marg_cap),
+				"setting up the marginal statistics");
 	}
 	/* rounds between two acceptance_rate.dump rows: iter advances by n_swap per round and a
 	 * row is due whenever iter % PRINT_PROB_INTERVAL == 0 */
@@ -912,8 +986,9 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 			t_par[cur] = (double *) malloc(need * n_dumped * n_par * sizeof(double) + 8);
 			assert(t_prob[cur] != NULL && t_dl[cur] != NULL && t_par[cur] != NULL);
 		}
-		apm_gpu_check(s, apm_gpu_read_trace(s->gpu, t_prob[cur], t_dl[cur], t_par[cur], &n_prob_rows, &n_par_rows),
-				"reading the trace");
+		if (!no_dumps)
+			apm_gpu_check(s, apm_gpu_read_trace(s->gpu, t_prob[cur], t_dl[cur], t_par[cur], &n_prob_rows, &n_par_rows),
+					"reading the trace");
 		t_read += wall_s() - t_b;
 		clock_gettime(CLOCK_MONOTONIC, &t1);
 		secs = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
@@ -935,7 +1010,8 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 		job.n_par_rows = n_par_rows;
 		job.n_dumped = n_dumped;
 		job.params_chains = trace.params_chains;
-		writer_submit(&writer, &job);
+		if (!no_dumps)
+			writer_submit(&writer, &job);
 		cur ^= 1;
 		iter += (unsigned long) rounds * n_swap;
 
@@ -947,7 +1023,8 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 				dump_requested = 0;
 				writer_wait(&writer);
 				for (i = 0; i < n_chains; i++)
-					fflush(prob_files[i]);
+					if (prob_files[i] != NULL)
+						fflush(prob_files[i]);
 			}
 			for (e = 0; e < n_ens; e++) {
 				fprintf(accept_files[e], "%lu", iter);
@@ -973,10 +1050,13 @@ void prepare_and_run_sampler(const unsigned long max_iterations, int append) {
 	for (e = 0; e < n_ens; e++)
 		fclose(accept_files[e]);
 	for (i = 0; i < n_chains; i++)
-		fclose(prob_files[i]);
+		if (prob_files[i] != NULL)
+			fclose(prob_files[i]);
 	printf("handled %lu iterations on %d chains\n", iter, n_chains);
 	report(s);
 	write_run_statistics(s);
+	if (marg_which != 0 && iter == (unsigned long) ((max_iterations + n_swap - 1) / n_swap) * n_swap)
+		write_run_marginals(s, marg_which, marg_batch, marg_cap); /* (not after an interrupted run: wrong batch size) */
 	for (i = 0; i < 2; i++) {
 		free(t_prob[i]);
 		free(t_dl[i]);

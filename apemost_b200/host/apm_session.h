@@ -41,11 +41,16 @@ void apm_session_calc_model(apm_session * s, const int * which, int n);
 void apm_gpu_check(apm_session * s, int rc, const char * what);
 mcmc ** apm_ensemble(apm_session * s, int e); /* = &chains[e * n_beta] */
 
-/* apm_calibrate_alt.c: -DCALIBRATE_ALTERNATE (reference src/markov_chain.c:117-224,
- * src/markov_chain_calibrate.c:927-1037) for chain g, after its burn-in */
+/* apm_assess.c: assess_acceptance_rate (reference src/markov_chain.c:117-224) for chain g: the
+ * measurement the three alternate calibrators are built on; returns the steps it took */
 unsigned int apm_assess_acceptance_rate(apm_session * s, int g, unsigned int param, double desired_acceptance_rate,
 		double min_accuracy, double max_accuracy, double * acceptance_rate, double * accuracy);
+/* apm_calibrate_alt.c: -DCALIBRATE_ALTERNATE (reference src/markov_chain_calibrate.c:927-1037) for
+ * chain g, after its burn-in */
 void apm_calibrate_alt(apm_session * s, int g, double desired_acceptance_rate, const double max_ar_deviation,
+		const unsigned int iter_limit);
+/* apm_calibrate_quadratic.c: -DCALIBRATE_QUADRATIC (reference src/markov_chain_calibrate.c:239-914) */
+void apm_calibrate_quadratic(apm_session * s, int g, double desired_acceptance_rate, const double max_ar_deviation,
 		const unsigned int iter_limit);
 
 /* apm_calibrate_multilin.c: -DCALIBRATE_MULTILIN (reference src/markov_chain_calibrate.c:33-237,

@@ -408,7 +408,12 @@ def main():
     eng.set_bounds(LO, HI)
     eng.set_chains(0, eng.n_chains, **st)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    peak = capi.measure_fp64_peak(local, 0.25)
+    # roofline denominator: the FP64 pipe's issue rate per clock (clock64() inside a short DFMA kernel:
+    # 63.8 of the architecture's 64 lanes per SM per clock on this pool's B200s) x SMs x the SM clock
+    # sampled during the timed region.  The per-second DFMA microbenchmark of round 1 is kept beside it:
+    # a long pure-DFMA load is the one thing that pulls the clocks down (power), so it reads ~8 % low.
+    per_clock, n_sm = capi.measure_fp64_per_clock(local)
+    peak_sustained_dfma = capi.measure_fp64_peak(local, 0.25)
 
     # warm-up rounds (untimed)
     if W:
@@ -433,6 +438,8 @@ def main():
     ll_ms, ll_launches, instrumented_ms = eng.last_kernel_ms()
     eng.set_timing(False)
     clocks = sampler.summary()
+    sm_hz = (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
+    peak = per_clock * n_sm * sm_hz
 
     # end to end through the C ABI with host buffers
     h2d = h_data.nbytes + sum(v.nbytes for v in st.values())
@@ -513,8 +520,13 @@ def main():
                 "executed_note": "SASS FP64 instructions per row evaluation: the sine's argument is a separate DMUL + "
                                  "DADD (rounded like the reference's), so 18 are issued for the 17 counted",
                 "frac_executed": achieved / peak * 18 / ALG_FP64_PER_ROW,
-                "peak_source": "measured live: fp64_peak_kernel DFMA issue rate on this GPU "
-                               "(MEASURED_PEAKS.json has no fp64 entry)",
+                "peak_source": "measured live (MEASURED_PEAKS.json has no fp64 entry): %.2f FP64 lane-operations per SM per "
+                               "clock (clock64() around a DFMA stream, 2 warps per scheduler x 8 chains) x %d SMs x the "
+                               "%.0f MHz sampled during the timed region" % (per_clock, n_sm, sm_hz / 1e6),
+                "peak_sustained_dfma": peak_sustained_dfma / 1e9,
+                "frac_vs_sustained_dfma": achieved / peak_sustained_dfma,
+                "peak_sustained_dfma_note": "round 1's denominator: the per-second rate of a 0.25 s pure-DFMA launch, during "
+                                            "which the clocks sag (the kernel measured here runs at full clocks)",
                 "algorithmic": "17 FP64 instr per row-evaluation x 4096 chains x 1e6 rows per launch",
                 "kernel_ms_per_launch": ll_ms / max(ll_launches, 1), "kernel_launches_timed": int(ll_launches),
                 "kernel_share_of_step": ll_ms / total_ms,

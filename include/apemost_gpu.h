@@ -242,6 +242,25 @@ int apm_gpu_get_stats(apm_gpu * h, unsigned long long * n /*[n_chains]*/,
 		double * sum_dl /*[n_chains]*/, double * sum_params /*[n_chains][n_par]*/,
 		double * sum_params_sq /*[n_chains][n_par]*/);
 
+/* ---- marginal statistics on the device: what the reference's analyse
+ * derives from <name>-chain-<i>.prob.dump, accumulated while the sampler runs instead of parsed from
+ * hundreds of MB of text (calc_marginal_distribution + calc_mcmc_error, reference src/analyse.c:115-247,
+ * create_hist src/histogram.c:34-43).  For the chosen chains (which_chains: 0 off, 1 = chain 0 of every
+ * ensemble, 2 = every chain; one "slot" per chosen chain, in chain order) and every parameter:
+ *   counts       gsl_histogram_increment's bins: n_bins uniform bins over [params_min, params_max], the
+ *                last edge widened by (max - min) / 10000 like create_hist; edges are computed with
+ *                gsl_histogram_set_ranges_uniform's expressions, so a value lands in the same bin;
+ *   batch_means  the means calc_mcmc_error forms: a batch closes when (values so far) % batch_size ==
+ *                batch_size - 1 and its mean is its sum / batch_size (so the first batch holds
+ *                batch_size - 1 values; the reference's arithmetic, kept); the first max_batches are kept.
+ * set_marginals (re)allocates and zeroes the accumulators; they then collect every recorded step of
+ * every apm_gpu_run until the next call.  get_marginals: any pointer may be NULL.
+ *   counts [slots][n_par][n_bins], batch_means [slots][n_par][max_batches], n_values / n_batches [slots] */
+int apm_gpu_set_marginals(apm_gpu * h, int which_chains, int n_bins, unsigned long long batch_size,
+		int max_batches);
+int apm_gpu_get_marginals(apm_gpu * h, unsigned long long * counts, double * batch_means,
+		unsigned long long * n_values, unsigned long long * n_batches);
+
 /* ---- multi-GPU, data-sharded likelihood: every rank
  * holds all chains and a contiguous row shard; per step the per-chain partial
  * sums are all-reduced with NCCL (fp64 sum) and every rank takes the identical
@@ -281,6 +300,11 @@ int apm_gpu_set_timing(apm_gpu * h, int per_launch);
 /* microbenchmark: sustained FP64 FMA issue rate of this device, in
  * FP64 instructions (lane-operations) per second; used as the roofline peak */
 int apm_gpu_measure_fp64_peak(int device, double seconds, double * instr_per_s);
+/* the same per clock: FP64 lane-operations per SM per clock (64 by the architecture), from clock64()
+ * inside a short DFMA kernel -- independent of the clocks, which sag under the long pure-DFMA load the
+ * per-second microbenchmark applies; multiplied by the SM count and the SM clock during a run it is that
+ * run's FP64 issue peak */
+int apm_gpu_measure_fp64_per_clock(int device, double * lanes_per_sm_per_clock, int * n_sm);
 
 #ifdef __cplusplus
 }

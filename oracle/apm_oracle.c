@@ -404,6 +404,13 @@ struct orc_engine {
 	orc_config cfg;
 	int n_chains;
 	chain_t * chains;
+	/* marginal statistics of the recorded chains (orc_set_marginals): ref src/analyse.c:115-247 */
+	int marg_mode, marg_bins, marg_cap;
+	u64 marg_batch;
+	u64 * marg_counts;    /* [slots][n_par][bins] */
+	double * marg_bsum;   /* [slots][n_par] */
+	double * marg_means;  /* [slots][n_par][cap] */
+	u64 * marg_n, *marg_nb; /* [slots] */
 	double * pmin, *pmax;
 	double * data;
 	long long n_rows;
@@ -419,6 +426,8 @@ struct orc_engine {
 	long long tr_prob_rows, tr_param_rows;
 	int tr_dumped;
 };
+
+static void marginals_free(orc_engine * e);
 
 static void chain_eval(orc_engine * e, chain_t * c) {
 	/* the plugin call, ref: src/markov_chain.c:376 */
@@ -896,6 +905,7 @@ int orc_destroy(orc_engine * e) {
 		free(c->stat_sum_p);
 		free(c->stat_sum_p2);
 	}
+	marginals_free(e);
 	free(e->chains);
 	free(e->pmin);
 	free(e->pmax);
@@ -1048,6 +1058,52 @@ int orc_eval(orc_engine * e, int n, const double * params, const double * beta,
 	return 0;
 }
 
+/* ---- what analyse derives from <name>-chain-<i>.prob.dump, accumulated step by step ----------
+ * ref: calc_marginal_distribution src/analyse.c:159-247 (create_hist src/histogram.c:34-43 +
+ * gsl_histogram_increment) and calc_mcmc_error src/analyse.c:115-142 */
+static double marg_edge(int k, int nb, double lo, double hi) {
+	/* gsl_histogram_set_ranges_uniform's expressions; create_hist widens the last edge */
+	const double f1 = (double) (nb - k) / (double) nb, f2 = (double) k / (double) nb;
+	double e = f1 * lo + f2 * hi;
+	if (k == nb)
+		e += (hi - lo) / 10000;
+	return e;
+}
+
+static void marginals_add(orc_engine * e, int g, const double * params) {
+	const int n = e->cfg.n_par, nb = e->marg_bins;
+	int slot = -1, i;
+	u64 seen, closed;
+	if (e->marg_mode == 2)
+		slot = g;
+	else if (e->marg_mode == 1 && g % e->cfg.n_beta == 0)
+		slot = g / e->cfg.n_beta;
+	if (slot < 0)
+		return;
+	seen = e->marg_n[slot];
+	closed = e->marg_nb[slot];
+	for (i = 0; i < n; i++) {
+		const double v = params[i], lo = e->pmin[i], hi = e->pmax[i], top = marg_edge(nb, nb, lo, hi);
+		double * bs = &e->marg_bsum[(size_t) slot * n + i];
+		if (v >= lo && v < top) {
+			int b = 0;
+			while (b < nb - 1 && v >= marg_edge(b + 1, nb, lo, hi)) /* the bin with edge[b] <= v < edge[b + 1] */
+				b++;
+			e->marg_counts[((size_t) slot * n + i) * nb + b]++;
+		}
+		/* n++; batchsum += v; if (n % batchsize == batchsize - 1) { batchmean = batchsum / batchsize; ... } */
+		*bs += v;
+		if (e->marg_batch > 0 && (seen + 1) % e->marg_batch == e->marg_batch - 1) {
+			if (closed < (u64) e->marg_cap)
+				e->marg_means[((size_t) slot * n + i) * e->marg_cap + closed] = *bs / (double) e->marg_batch;
+			*bs = 0;
+		}
+	}
+	e->marg_n[slot] = seen + 1;
+	if (e->marg_batch > 0 && (seen + 1) % e->marg_batch == e->marg_batch - 1)
+		e->marg_nb[slot] = closed + 1;
+}
+
 /* ---- run_sampler hot loop: ref src/parallel_tempering.c:392-409 -------- */
 static void sampler_substep(orc_engine * e, int g, long long step_index,
 		const orc_trace_cfg * tr) {
@@ -1080,6 +1136,8 @@ static void sampler_substep(orc_engine * e, int g, long long step_index,
 		c->stat_sum_p[i] += c->params[i];
 		c->stat_sum_p2[i] += c->params[i] * c->params[i];
 	}
+	if (e->marg_mode)
+		marginals_add(e, g, c->params);
 }
 
 int orc_run(orc_engine * e, long long n_rounds, int n_swap, const orc_trace_cfg * trace) {
@@ -1198,6 +1256,58 @@ int orc_steps(orc_engine * e, const unsigned char * select, int kind, long long 
 				accepted[(size_t) i * e->n_chains + g] = (kind == n ? c->accept : c->pacc[kind]) != before;
 		}
 	}
+	return 0;
+}
+
+static void marginals_free(orc_engine * e) {
+	free(e->marg_counts);
+	free(e->marg_bsum);
+	free(e->marg_means);
+	free(e->marg_n);
+	free(e->marg_nb);
+	e->marg_counts = NULL;
+	e->marg_bsum = NULL;
+	e->marg_means = NULL;
+	e->marg_n = e->marg_nb = NULL;
+	e->marg_mode = 0;
+}
+
+/* mirrors apm_gpu_set_marginals / apm_gpu_get_marginals */
+int orc_set_marginals(orc_engine * e, int which_chains, int n_bins, u64 batch_size, int max_batches) {
+	size_t slots, np;
+	if (e == NULL || which_chains < 0 || which_chains > 2 || (which_chains && (n_bins < 1 || max_batches < 0)))
+		return -1;
+	marginals_free(e);
+	if (which_chains == 0)
+		return 0;
+	slots = which_chains == 2 ? (size_t) e->n_chains : (size_t) e->cfg.n_ensembles;
+	np = (size_t) e->cfg.n_par;
+	e->marg_counts = (u64 *) calloc(slots * np * n_bins, sizeof(u64));
+	e->marg_bsum = (double *) calloc(slots * np, sizeof(double));
+	e->marg_means = (double *) calloc(slots * np * (max_batches > 0 ? max_batches : 1), sizeof(double));
+	e->marg_n = (u64 *) calloc(slots, sizeof(u64));
+	e->marg_nb = (u64 *) calloc(slots, sizeof(u64));
+	e->marg_mode = which_chains;
+	e->marg_bins = n_bins;
+	e->marg_batch = batch_size;
+	e->marg_cap = max_batches;
+	return 0;
+}
+
+int orc_get_marginals(orc_engine * e, u64 * counts, double * batch_means, u64 * n_values, u64 * n_batches) {
+	size_t slots, np;
+	if (e == NULL || !e->marg_mode)
+		return -5;
+	slots = e->marg_mode == 2 ? (size_t) e->n_chains : (size_t) e->cfg.n_ensembles;
+	np = (size_t) e->cfg.n_par;
+	if (counts)
+		memcpy(counts, e->marg_counts, slots * np * e->marg_bins * sizeof(u64));
+	if (batch_means && e->marg_cap > 0)
+		memcpy(batch_means, e->marg_means, slots * np * e->marg_cap * sizeof(double));
+	if (n_values)
+		memcpy(n_values, e->marg_n, slots * sizeof(u64));
+	if (n_batches)
+		memcpy(n_batches, e->marg_nb, slots * sizeof(u64));
 	return 0;
 }
 

@@ -133,6 +133,9 @@ int orc_steps(orc_engine * e, const unsigned char * select, int kind, long long 
  * (ref src/parallel_tempering_interaction.c:47-65,130-131) */
 int orc_set_adapt(orc_engine * e, int enabled, double target_acceptance_rate);
 int orc_set_random_swap(orc_engine * e, int enabled);
+int orc_set_marginals(orc_engine * e, int which_chains, int n_bins, unsigned long long batch_size, int max_batches);
+int orc_get_marginals(orc_engine * e, unsigned long long * counts, double * batch_means,
+		unsigned long long * n_values, unsigned long long * n_batches); /* mirror apm_gpu_*_marginals */
 int orc_reset_stats(orc_engine * e);
 int orc_get_stats(orc_engine * e, unsigned long long * n, double * sum_dl,
 		double * sum_params, double * sum_params_sq);

@@ -191,38 +191,39 @@ C1_ROWS = [(1.0, 0.0, 3.0, "amplitude", -1.0), (15.2, 4.0, 24.0, "frequency", 0.
            (0.25, 0.0, 1.0, "phase", -1.0), (0.0, -1.0, 1.0, "offset", -1.0)]
 
 
-def all_phase_fixtures():
+def all_phase_fixtures(wanted=None):
+    """name -> fixture for every phase fixture (or the wanted ones): each entry below is a recipe"""
     fx = {}
     small = dict(N_BETA=4, BURN_IN_ITERATIONS=1000, MAX_ITERATIONS=3000, GSL_RNG_SEED=7)
     # config C1 in small: simplesin on the reference's own light curve
-    fx["c1_phases"] = phases_fixture("simplesin", C1_ROWS, "testlc.dat", None, small)
+    fx["c1_phases"] = lambda: phases_fixture("simplesin", C1_ROWS, "testlc.dat", None, small)
     # circular phase parameter (CIRCULAR_PARAMS lists parameter 3 = phase)
-    fx["c1_circular_phases"] = phases_fixture(
+    fx["c1_circular_phases"] = lambda: phases_fixture(
         "simplesin", C1_ROWS, "testlc.dat", None, dict(small, GSL_RNG_SEED=11),
         ccflags_extra="-DCIRCULAR_PARAMS=3", suffix="_pin_circ", engine_opts=dict(circular_mask=4))
     # alternative proposal distributions
-    fx["c1_logistic_phases"] = phases_fixture(
+    fx["c1_logistic_phases"] = lambda: phases_fixture(
         "simplesin", C1_ROWS, "testlc.dat", None, dict(small, GSL_RNG_SEED=3),
         ccflags_extra="-DPROPOSAL_LOGISTIC", suffix="_pin_logi", engine_opts=dict(proposal=1))
-    fx["c1_uniform_phases"] = phases_fixture(
+    fx["c1_uniform_phases"] = lambda: phases_fixture(
         "simplesin", C1_ROWS, "testlc.dat", None, dict(small, GSL_RNG_SEED=5),
         ccflags_extra="-DPROPOSAL_UNIFORM", suffix="_pin_unif", engine_opts=dict(proposal=2))
     # config C4 in small: pulse_vrot (has a prior: pins the stale-prior and swap-ratio quirks)
     rng = np.random.default_rng(4242)
-    fx["c4_phases"] = phases_fixture(
+    fx["c4_phases"] = lambda: phases_fixture(
         "pulse_vrot", MODELS["pulse_vrot"]["rows"], None, pulse_spectrum(200, rng),
         dict(N_BETA=3, BURN_IN_ITERATIONS=1000, MAX_ITERATIONS=2000, GSL_RNG_SEED=9), suffix="_pin4")
     # config C2 in small: normal (data-free)
-    fx["c2_phases"] = phases_fixture(
+    fx["c2_phases"] = lambda: phases_fixture(
         "normal", [(20.0, 0.0, 60.0, "x", -1.0)], None, np.array([[0.0, 0.0], [1.0, 1.0]]),
         dict(N_BETA=3, BURN_IN_ITERATIONS=1000, MAX_ITERATIONS=4000, BETA_0=0.5, GSL_RNG_SEED=2),
         suffix="_pin2b", engine_opts=dict(beta_0=0.5))
     # -DADAPT: long enough for the 1 % rescalings (counter sums >= 20000) and a counter reset
     # (> 100000) to happen; -DRANDOMSWAP: one more uniform per round
-    fx["c1_adapt_phases"] = phases_fixture(
+    fx["c1_adapt_phases"] = lambda: phases_fixture(
         "simplesin", C1_ROWS, "testlc.dat", None, dict(small, MAX_ITERATIONS=30000, GSL_RNG_SEED=13),
         ccflags_extra="-DADAPT", suffix="_pin_adapt", engine_opts=dict(adapt=0.5))
-    fx["c1_randomswap_phases"] = phases_fixture(
+    fx["c1_randomswap_phases"] = lambda: phases_fixture(
         "simplesin", C1_ROWS, "testlc.dat", None, dict(small, GSL_RNG_SEED=17),
         ccflags_extra="-DRANDOMSWAP", suffix="_pin_rswap", engine_opts=dict(random_swap=1))
     # -DCALIBRATE_ALTERNATE: assess_acceptance_rate + markov_chain_calibrate_alt replace _orig
@@ -230,17 +231,26 @@ def all_phase_fixtures():
     # alternate calibrator often gives up on the hot chains ("iteration limit reached", exit 1), so
     # the fixture calibrates chains 0 and 1 with it and only burns the others in
     # (-DSKIP_CALIBRATE_ALLCHAINS), with a seed for which it converges.
-    fx["c1_altcal_phases"] = phases_fixture(
+    fx["c1_altcal_phases"] = lambda: phases_fixture(
         "simplesin", C1_ROWS, "testlc.dat", None, dict(small, GSL_RNG_SEED=23),
         ccflags_extra="-DCALIBRATE_ALTERNATE -DSKIP_CALIBRATE_ALLCHAINS", suffix="_pin_altskip",
         engine_opts=dict(host_only=1))
     # -DCALIBRATE_MULTILIN: markov_chain_calibrate_multilinear_regression for every chain (pins
     # apm_calibrate_multilin.c and the host-side uniform draws).  On the hottest chain the
     # reference's regression walks one step width below zero -- kept: it is what the reference does.
-    fx["c1_multilin_phases"] = phases_fixture(
+    fx["c1_multilin_phases"] = lambda: phases_fixture(
         "simplesin", C1_ROWS, "testlc.dat", None, dict(small, GSL_RNG_SEED=29),
         ccflags_extra="-DCALIBRATE_MULTILIN", suffix="_pin_multilin", engine_opts=dict(host_only=1))
-    return fx
+    # -DCALIBRATE_QUADRATIC: markov_chain_calibrate_quadratic + markov_chain_calibrate_linear_regression
+    # (pins apm_calibrate_quadratic.c).  The reference's parabola search leaves wild step widths
+    # (1e-14 .. 1e21 of the range) and for most seeds ends in an assertion or a GSL range error on a
+    # hot chain, so the fixture calibrates chains 0 and 1 with it (-DSKIP_CALIBRATE_ALLCHAINS) with a
+    # seed for which both survive.
+    fx["c1_quadratic_phases"] = lambda: phases_fixture(
+        "simplesin", C1_ROWS, "testlc.dat", None, dict(small, GSL_RNG_SEED=4),
+        ccflags_extra="-DCALIBRATE_QUADRATIC -DSKIP_CALIBRATE_ALLCHAINS", suffix="_pin_quad",
+        engine_opts=dict(host_only=1))
+    return {name: recipe() for name, recipe in fx.items() if wanted is None or name in wanted}
 
 
 def main():
@@ -265,5 +275,18 @@ def main():
         print("wrote %s.json" % name)
 
 
+def only(names):
+    """regenerate some of the phase fixtures: python make_golden.py c1_quadratic_phases ..."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), os.path.join(ROOT, "oracle", "_build", "gsl_compat.o")],
+                   check=True)
+    fxs = all_phase_fixtures(set(names))
+    for name in names:
+        json.dump(fxs[name], open(os.path.join(HERE, name + ".json"), "w"), indent=1)
+        print("wrote %s.json" % name)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1:
+        only(sys.argv[1:])
+    else:
+        main()

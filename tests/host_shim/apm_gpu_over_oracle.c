@@ -111,3 +111,10 @@ int apm_gpu_get_stats(apm_gpu * h, unsigned long long * n, double * sum_dl, doub
 		double * sum_params_sq) {
 	return orc_get_stats(h->e, n, sum_dl, sum_params, sum_params_sq);
 }
+int apm_gpu_set_marginals(apm_gpu * h, int which_chains, int n_bins, unsigned long long batch_size, int max_batches) {
+	return orc_set_marginals(h->e, which_chains, n_bins, batch_size, max_batches);
+}
+int apm_gpu_get_marginals(apm_gpu * h, unsigned long long * counts, double * batch_means,
+		unsigned long long * n_values, unsigned long long * n_batches) {
+	return orc_get_marginals(h->e, counts, batch_means, n_values, n_batches);
+}

@@ -135,7 +135,7 @@ def test_benchmark_exe_reproduces_and_matches_fixture(tmp_path):
     assert r.returncode == 1 and "SYNOPSIS" in r.stderr
 
 
-@pytest.mark.parametrize("fixture", ["c1_altcal_phases", "c1_multilin_phases"])
+@pytest.mark.parametrize("fixture", ["c1_altcal_phases", "c1_multilin_phases", "c1_quadratic_phases"])
 def test_alternate_calibrator_on_gpu_equals_oracle_flow(tmp_path, fixture):
     """-DCALIBRATE_ALTERNATE (assess_acceptance_rate + markov_chain_calibrate_alt, reference
     src/markov_chain.c:117-224, src/markov_chain_calibrate.c:927-1037) and -DCALIBRATE_MULTILIN
@@ -170,6 +170,24 @@ def test_alternate_calibrator_on_gpu_equals_oracle_flow(tmp_path, fixture):
     assert out["gpu"][0] == out["cpu"][0] and out["gpu"][0][0][1] == 0, out["gpu"][0]
     np.testing.assert_allclose(out["gpu"][1], out["cpu"][1], rtol=1e-9, atol=1e-300)
     assert out["gpu"][2] == out["cpu"][2] and len(out["gpu"][2]) > 0
+
+
+@pytest.mark.parametrize("name", ["c1_phases", "c4_phases"])
+def test_analyse_from_device_accumulators_equals_analyse_from_dumps(name, tmp_path):
+    """SURVEY.md 8 f1 on the device: the 200-bin histograms and the batch means `run` accumulates in
+    its kernels (apm_gpu_set_marginals) give the same <name>.histogram files, byte for byte, and the
+    same error estimates as analyse's pass over the parameter dumps of the same run"""
+    from test_host_cpu import check_analyse_from_accumulators
+    fx = json.load(open(os.path.join(GOLDEN, name + ".json")))
+    cfg = fx["config"]
+    flags = " ".join(f"-D{k}={v}" for k, v in cfg.items() if k != "GSL_RNG_SEED")
+    exe = make(fx["model"] + ".exe", flags, str(tmp_path / "bin"))
+    wd = str(tmp_path / "wd")
+    setup_workdir(wd, fx)
+    env = dict(os.environ, GSL_RNG_SEED=str(cfg["GSL_RNG_SEED"]))
+    for phase in ("calibrate_first", "calibrate_rest"):
+        subprocess.run([exe, phase], cwd=wd, env=env, check=True, capture_output=True)
+    check_analyse_from_accumulators(exe, wd, env, [r[3] for r in fx["rows"]])
 
 
 def test_several_ensembles_side_by_side(tmp_path):

@@ -245,6 +245,40 @@ def test_run_trajectory_equals_oracle(capi, name, kw, quirks, path):
     assert st_g["swapcount"].sum() > 0, "the test must exercise accepted swaps"
 
 
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("name,which", [("c1_phases", 2), ("c4_phases", 1), ("c2_phases", 2)])
+def test_marginal_statistics_equal_oracle(capi, name, which, path):
+    """apm_gpu_set_marginals: the per-parameter histograms (gsl_histogram_increment's
+    bins, create_hist's edges) and calc_mcmc_error's batch means, accumulated in the kernels of every
+    path, against the oracle's: counts equal, batch means to 1e-9, over two run calls"""
+    fx = load(name)
+    if path in (3, 4) and fx["model"] == "normal":
+        pytest.skip("the cluster and grid paths are for models with data")
+    rows = [tuple(r) for r in fx["rows"]]
+    n_par, n_beta, n_ens = len(rows), fx["config"]["N_BETA"], 3
+    data = (np.loadtxt(os.path.join(GOLDEN, fx["data_file"])) if fx["data_file"]
+            else np.array(fx["data"], dtype=float).reshape(-1, 2))
+    cal = np.array(fx["phases"]["calibrate_rest"].split(), dtype=float).reshape(n_beta, 1 + 2 * n_par)
+    res = []
+    for eng in _pair(capi, fx["model"], n_ens, n_beta, n_par=n_par, seed=41, path=path):
+        eng.set_data(data)
+        pt_flow.setup_chains(eng, rows)
+        pt_flow.apply_calibration(eng, 0, np.tile(cal[:, 0], n_ens), np.tile(cal[:, 1:1 + n_par], (n_ens, 1)),
+                                  np.tile(cal[:, 1 + n_par:], (n_ens, 1)))
+        eng.set_marginals(which, n_bins=50, batch_size=7, max_batches=40)
+        eng.run(4, 30)
+        eng.run(3, 30, prob_every=1, params_chains=1)
+        res.append((eng.get_marginals(), eng.get_chains()))
+    (m_g, st_g), (m_c, st_c) = res
+    _compare_state(st_g, st_c)
+    assert (m_g["n_values"] == 210).all() and (m_g["n_batches"] == 30).all()
+    np.testing.assert_array_equal(m_g["n_values"], m_c["n_values"])
+    np.testing.assert_array_equal(m_g["n_batches"], m_c["n_batches"])
+    np.testing.assert_array_equal(m_g["counts"], m_c["counts"])
+    assert (m_g["counts"].sum(axis=2) == 210).all()
+    np.testing.assert_allclose(m_g["batch_means"][:, :, :30], m_c["batch_means"][:, :, :30], rtol=RTOL_TRAJ, atol=1e-300)
+
+
 def _logistic_table(n_rows, n_cols, seed):
     rng = np.random.default_rng(seed)
     X = rng.normal(size=(n_rows, n_cols - 1))

@@ -24,7 +24,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 HOST = os.path.join(ROOT, "apemost_b200", "host")
 BUILD = os.path.join(ROOT, "oracle", "_build")
 FIXTURES = ["c1_phases", "c1_circular_phases", "c1_logistic_phases", "c1_uniform_phases", "c4_phases", "c2_phases",
-            "c1_adapt_phases", "c1_randomswap_phases", "c1_altcal_phases", "c1_multilin_phases"]
+            "c1_adapt_phases", "c1_randomswap_phases", "c1_altcal_phases", "c1_multilin_phases", "c1_quadratic_phases"]
 MODEL_IDS = {"simplesin": 0, "simplesin5": 1, "normal": 2, "pulse_vrot": 3, "simplesin2": 4, "pulse": 5}
 
 
@@ -33,7 +33,8 @@ def build_host_over_oracle(name, model, ccflags):
     build_oracle()
     exe = os.path.join(BUILD, f"host_{name}.exe")
     src = [os.path.join(HOST, f) for f in ("apm_main.c", "apm_chainobj.c", "apm_files.c", "apm_phases.c",
-                                           "apm_analyse.c", "apm_calibrate_alt.c", "apm_calibrate_multilin.c", "apm_fastfmt.c")]
+                                           "apm_analyse.c", "apm_assess.c", "apm_calibrate_alt.c", "apm_calibrate_multilin.c",
+                                           "apm_calibrate_quadratic.c", "apm_fastfmt.c")]
     src += [os.path.join(ROOT, "apemost_b200", "compat", "gsl", "gsl_compat.c"),
             os.path.join(ROOT, "tests", "host_shim", "apm_gpu_over_oracle.c")]
     cmd = ["gcc", "-O2", "-std=gnu99", "-fopenmp", "-pthread", "-I", os.path.join(HOST, "include"), "-I", os.path.join(ROOT, "include"),
@@ -90,6 +91,72 @@ def test_host_layer_files_byte_identical_to_reference(name, tmp_path):
     # new: the evidence from the accumulators of `run` agrees with the one from the 7-digit dumps
     m2 = re.search(r"on-device accumulators \(full precision\): (-?[\d.]+)", r.stdout)
     assert m2 and abs(float(m2.group(1)) - float(fx["evidence"])) < 2e-4 * max(1.0, abs(float(fx["evidence"])))
+
+
+def check_analyse_from_accumulators(exe, wd, env, n_par_names):
+    """after calibrate_first / calibrate_rest in `wd`: `run` with the text dumps, `analyse` from them
+    (the reference's way); then the dumps are moved away and `analyse` runs again, from run_marginals
+    and run_statistics (the on-device accumulators): the same <name>.histogram files
+    byte for byte, the same error estimates; then a `run` with APM_NO_DUMPS=1 leaves the same
+    accumulator files and no dump at all"""
+    import glob
+    import hashlib
+    import shutil
+    subprocess.run([exe, "run"], cwd=wd, env=env, check=True, capture_output=True)
+    assert os.path.exists(os.path.join(wd, "run_marginals"))
+    r1 = subprocess.run([exe, "analyse"], cwd=wd, env=env, check=True, capture_output=True, text=True)
+    hist1 = {n: open(os.path.join(wd, n + ".histogram")).read() for n in n_par_names}
+    est1 = re.findall(r"mcmc error estimate of .*", r1.stdout)
+    ev1 = float(re.search(r"Model probability ln\(p\(D\|M, I\)\): \[about 10\^(-?\d+)\] (-?[\d.]+)", r1.stdout).group(2))
+    marg1 = open(os.path.join(wd, "run_marginals")).read()
+    stash = os.path.join(wd, "dumps_moved_away")
+    os.makedirs(stash)
+    dumps = glob.glob(os.path.join(wd, "*.dump"))
+    assert len(dumps) > len(n_par_names)
+    for f in dumps:
+        shutil.move(f, stash)
+    for n in n_par_names:
+        os.remove(os.path.join(wd, n + ".histogram"))
+    r2 = subprocess.run([exe, "analyse"], cwd=wd, env=env, check=True, capture_output=True, text=True)
+    for n in n_par_names:
+        assert open(os.path.join(wd, n + ".histogram")).read() == hist1[n], n
+    assert re.findall(r"mcmc error estimate of .*", r2.stdout) == est1 and len(est1) == len(n_par_names)
+    ev2 = float(re.search(r"Model probability ln\(p\(D\|M, I\)\): \[about 10\^(-?\d+)\] (-?[\d.]+)", r2.stdout).group(2))
+    assert abs(ev2 - ev1) < 2e-4 * max(1.0, abs(ev1))   # 7-digit text against full-precision sums
+    # the same run without any text dump
+    os.remove(os.path.join(wd, "run_marginals"))
+    subprocess.run([exe, "run"], cwd=wd, env=dict(env, APM_NO_DUMPS="1"), check=True, capture_output=True)
+    assert not [f for f in glob.glob(os.path.join(wd, "*.dump")) if "acceptance_rate" not in f]
+    assert open(os.path.join(wd, "run_marginals")).read() == marg1
+    r3 = subprocess.run([exe, "analyse"], cwd=wd, env=env, check=True, capture_output=True, text=True)
+    for n in n_par_names:
+        assert open(os.path.join(wd, n + ".histogram")).read() == hist1[n], n
+    assert re.findall(r"mcmc error estimate of .*", r3.stdout) == est1
+
+
+@pytest.mark.parametrize("name", ["c1_phases", "c4_phases"])
+def test_analyse_from_accumulators_equals_analyse_from_dumps(name, tmp_path):
+    """marginal histograms, batch-means error estimates and the evidence from the
+    engine's accumulators instead of the text dumps (here: the host layer over the oracle shim)"""
+    import numpy as np
+    fx = json.load(open(os.path.join(GOLDEN, name + ".json")))
+    cfg = fx["config"]
+    flags = [f"-D{k}={v}" for k, v in cfg.items() if k != "GSL_RNG_SEED"] + fx["ccflags_extra"].split()
+    exe = build_host_over_oracle(name, fx["model"], flags)
+    wd = str(tmp_path)
+    write_params_file(os.path.join(wd, "params"), [tuple(r) for r in fx["rows"]])
+    if fx["data_file"]:
+        open(os.path.join(wd, "data"), "wb").write(open(os.path.join(GOLDEN, fx["data_file"]), "rb").read())
+    else:
+        write_data_file(os.path.join(wd, "data"), np.array(fx["data"], dtype=float).reshape(-1, fx["n_cols"]))
+    env = dict(os.environ, GSL_RNG_SEED=str(cfg["GSL_RNG_SEED"]), APM_TEST_ORACLE_RNG="mt19937")
+    for phase in ("calibrate_first", "calibrate_rest"):
+        subprocess.run([exe, phase], cwd=wd, env=env, check=True, capture_output=True)
+    check_analyse_from_accumulators(exe, wd, env, [r[3] for r in fx["rows"]])
+    # and the histograms are the reference's own
+    for fname, want in fx["files"].items():
+        if fname.endswith(".histogram"):
+            assert sha(os.path.join(wd, fname)) == want["sha256"], fname
 
 
 def test_fast_e6_formatter_writes_printf_bytes(tmp_path):

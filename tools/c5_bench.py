@@ -58,8 +58,9 @@ def measure(rank, world, local, per_gpu, n_steps=6, n_rounds=2, peak=None):
     st["params_best"] = st["params"].copy()
     eng.set_chains(0, eng.n_chains, **st)
     eng.set_timing(True)   # per-launch events: the likelihood kernel's own time
-    if peak is None:
-        peak = capi.measure_fp64_peak(local, 0.25)
+    if peak is None:   # FP64 issue peak: lanes per SM per clock (measured) x SMs x the nominal SM clock
+        per_clock, n_sm = capi.measure_fp64_per_clock(local)
+        peak = per_clock * n_sm * torch.cuda.get_device_properties(local).clock_rate * 1e3
 
     def barrier():
         if world > 1:
