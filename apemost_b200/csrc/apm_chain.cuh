@@ -426,8 +426,11 @@ APM_D void chain_book_step(const DevState & S, int g, int accepted, double prob_
 // lanes 0..n-1 of the calling warp and the scalar work on lane 0, so that the serial tail of a
 // step is a few dozen instructions instead of several hundred.  `sum` and `pre_logu` need to be
 // valid on lane 0 only.  All 32 lanes must call.
+// (pre_prior, when given: the proposal's prior, computed ahead by another warp -- it depends on the
+// proposal only)
 template<class M>
-APM_D void chain_finalize_warp(const DevState & S, int g, double sum, const double * pre_logu, int lane) {
+APM_D void chain_finalize_warp(const DevState & S, int g, double sum, const double * pre_logu, int lane,
+		const double * pre_prior = nullptr) {
 	const int n = S.n_par;
 	const int kind = S.pend[g];
 	const double * q = S.prop + (size_t) g * n;
@@ -438,7 +441,7 @@ APM_D void chain_finalize_warp(const DevState & S, int g, double sum, const doub
 		const double prior_old = S.prior[g];
 		double prior_new = prior_old;
 		if (M::HAS_PRIOR)
-			prior_new = M::prior(q, n, S.model_const);
+			prior_new = pre_prior != nullptr ? *pre_prior : M::prior(q, n, S.model_const);
 		const double prob_new = M::finish(S.beta[g], sum, prior_new, q, S.model_const);
 		if (prob_new == prob_old)
 			accepted = 1;

@@ -1794,8 +1794,8 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_calibrate_kerne
 constexpr int GROUP_MAX = 8; // chains a CTA works on concurrently (named barriers 1 .. 8)
 
 __host__ __device__ inline size_t group_state_bytes(int n_par) {
-	// the chain's state, the warps' partial sums [16], the pending kind
-	return fused_state_bytes(1, n_par) + 16 * sizeof(double) + 16;
+	// the chain's state, the warps' partial sums [16], the pending kind, the draws and the prior made ahead [APM_MAX_PAR + 2]
+	return fused_state_bytes(1, n_par) + 16 * sizeof(double) + 16 + (APM_MAX_PAR + 2) * sizeof(double);
 }
 
 struct GroupArgs {
@@ -1815,11 +1815,20 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) group_calibrate_kerne
 	const int G = gridDim.x, NG = ga.ng, WC = FUSED_MAX_WARPS / NG;
 	const int n = S.n_par;
 	const int q = warp / WC, wi = warp - q * WC;   // this warp's group, its place in the group
-	const int GL = WC * 32, gl = wi * 32 + lane;   // lanes of the group walking the table
+	// The group's last warp walks no rows: while the others do, it draws what the step's tail needs
+	// and what does not depend on the step's outcome -- log(u) of this step's accept test and the
+	// unit jumps of EVERY coordinate for the next step (its kind is not known yet; a chain's draws
+	// depend on its id and step counter only) -- so that the first warp's serial tail is the sum,
+	// the accept decision, the state machine and a multiply-add per coordinate.
+	const int LW = WC - 1;                         // warps that walk the table (WC >= 2)
+	const bool drawer = wi == WC - 1;
+	const int GT = WC * 32;                        // threads of the group (named barrier)
+	const int GL = LW * 32, gl = wi * 32 + lane;   // lanes walking the table
 	const double xub = *a.xabsmax;
 	unsigned char * mem = fused_smem + fused_table_bytes((long long) a.n_rows * (M::ROW_W / 2)) + (size_t) q * group_state_bytes(n);
 	double * sums = reinterpret_cast<double *>(mem + fused_state_bytes(1, n));
 	volatile int * kind_s = reinterpret_cast<volatile int *>(sums + 16);
+	double * draws = sums + 18;                    // [0, n) unit jumps for counter + 1, [n] log(u) for counter, [n + 1] the proposal's prior
 	// chains that were not selected: the same marks the other calibration kernels leave
 	for (int g = blockIdx.x * blockDim.x + tid; g < S.n_chains; g += G * blockDim.x)
 		if (a.select != nullptr && !a.select[g]) {
@@ -1827,6 +1836,24 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) group_calibrate_kerne
 			S.cal[g].phase = CAL_IDLE;
 			S.cal[g].status = -1;
 		}
+	// the next proposal from the unit jumps at hand (do_step_for, reference src/markov_chain.c:226-270);
+	// a first attempt outside the bounds goes the regular way (wrap or redraws)
+	auto propose_ahead = [&](const DevState & L, int kind) {
+		if (lane < n) {
+			const double x = L.params[lane];
+			double v = x;
+			if (kind == n || kind == lane) {
+				const double st = L.steps[lane];
+				v = x + jump_apply(L.proposal, st, draws[lane]);
+				if (v > L.pmax[lane] || v < L.pmin[lane])
+					v = propose_coordinate(L, 0, L.rng_ctr[0], lane, x, st);
+			}
+			L.prop[lane] = v;
+		}
+		if (lane == 0)
+			L.pend[0] = kind;
+		__syncwarp();
+	};
 	// list position p goes to CTA p mod G, group (p / G) mod NG, one after the other
 	for (int p = blockIdx.x + q * G; p < ga.n_sel; p += G * NG) {
 		const int g = ga.sel_idx[p];
@@ -1849,33 +1876,46 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) group_calibrate_kerne
 			if (lane == 0)
 				*kind_s = kind;
 		}
-		group_bar(1 + q, GL);
+		group_bar(1 + q, GT);
 		while (*kind_s != PEND_NONE) {
-			const double part = group_loglik<M>(L, L.prop, sdata, a.n_rows, xub, gl, GL);
-			if (lane == 0)
-				sums[wi] = part;
-			group_bar(1 + q, GL);
+			if (drawer) {
+				if (lane <= n) {
+					const u64 ctr = L.rng_ctr[0];
+					const bool is_jump = lane < n;
+					double u0, u1;
+					philox_uniforms(L.seed, chain_rng_id(L, 0), is_jump ? ctr + 1 : ctr, is_jump ? PURPOSE_JUMP : PURPOSE_ACCEPT,
+							is_jump ? (uint32_t) lane : 0u, 0, u0, u1);
+					draws[lane] = is_jump ? jump_unit(L.proposal, u0, u1) : log(u0);
+				} else if (M::HAS_PRIOR && lane == n + 1) {
+					draws[n + 1] = M::prior(L.prop, n, L.model_const); // the pending proposal's prior
+				}
+			} else {
+				const double part = group_loglik<M>(L, L.prop, sdata, a.n_rows, xub, gl, GL);
+				if (lane == 0)
+					sums[wi] = part;
+			}
+			group_bar(1 + q, GT);
 			if (wi == 0) {
 				double sum = sums[0];
-				for (int w = 1; w < WC; w++)
+				for (int w = 1; w < LW; w++)
 					sum += sums[w];
-				chain_finalize_warp<M>(L, 0, M::sum0(L.prop) + sum, nullptr, lane);
+				chain_finalize_warp<M>(L, 0, M::sum0(L.prop) + sum, draws + n, lane, M::HAS_PRIOR ? draws + n + 1 : nullptr);
 				if (lane == 0)
 					cal_after_step(L, 0, a.cal);
 				__syncwarp();
 				const int kind = cal_next_kind(L, 0);
 				if (kind != PEND_NONE)
-					chain_propose_warp(L, 0, kind, lane);
+					propose_ahead(L, kind);
 				if (lane == 0)
 					*kind_s = kind;
 			}
-			group_bar(1 + q, GL);
+			group_bar(1 + q, GT);
 		}
 		if (wi == 0) {
 			__syncwarp();
 			fused_writeback_block_by(S, L, g / S.n_beta, g % S.n_beta, false, lane, 32);
 		}
-		group_bar(1 + q, GL); // the group's shared memory is free for its next chain
+		group_bar(1 + q, GT); // the group's shared memory is free for its next chain
 	}
 }
 
