@@ -211,7 +211,7 @@ static int configure_kernels(apm_gpu * h) {
 	CU(cudaFuncSetAttribute(loglik_tiled_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 			(int) LL_SMEM_BYTES));
 	int occ = 0;
-	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loglik_tiled_kernel<M>, LL_THREADS,
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loglik_tiled_kernel<M>, LL_LAUNCH_THREADS,
 			LL_SMEM_BYTES));
 	if (occ < 1)
 		return fail(h, APM_ECUDA, "likelihood kernel does not fit on an SM");
@@ -617,7 +617,7 @@ static int launch_loglik(apm_gpu * h, const double * prop, const int * act_idx, 
 	timed = timed && h->ev_used + 2 <= 2 * MAX_TIMED_LAUNCHES;
 	if (timed)
 		cudaEventRecord(next_event(h), h->stream);
-	loglik_tiled_kernel<M><<<grid, LL_THREADS, LL_SMEM_BYTES, h->stream>>>(a);
+	loglik_tiled_kernel<M><<<grid, LL_LAUNCH_THREADS, LL_SMEM_BYTES, h->stream>>>(a);
 	if (timed)
 		cudaEventRecord(next_event(h), h->stream);
 	h->launches++;
@@ -1106,7 +1106,10 @@ template<class M>
 static int run_tiled_t(apm_gpu * h, long long n_rounds, int n_swap) {
 	AdvArgs a;
 	memset(&a, 0, sizeof(a));
-	int rc0 = replan(h, h->n_chains);
+	// (ladder split: the row splits are planned for the WHOLE ladder's chain count, as the single-GPU
+	// run of the same ensembles plans them -- a chain's sum then has the same summation order on
+	// both, which is what makes the split run equal to it bit for bit)
+	int rc0 = replan(h, h->ladder ? h->cfg.n_ensembles * h->S.n_beta_total : h->n_chains);
 	if (rc0 != APM_OK)
 		return rc0;
 	h->ev_used = 0;

@@ -56,6 +56,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity) {
 			"DONE_%=:\n\t"
 			"}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// the same for a thread that has nothing else to do (the likelihood kernel's producer lane): between
+// polls it sleeps, so that it does not take issue slots from the compute warps of its scheduler
+__device__ __forceinline__ void mbar_wait_idle(uint64_t * bar, uint32_t parity) {
+	uint32_t done = 0;
+	while (!done) {
+		asm volatile(
+				"{\n\t"
+				".reg .pred p;\n\t"
+				"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 2000;\n\t"
+				"selp.u32 %0, 1, 0, p;\n\t"
+				"}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+		if (!done)
+			__nanosleep(128);
+	}
+}
 // 1-D bulk copy global -> shared by the TMA engine (SASS: UBLKCP), completion on an mbarrier
 __device__ __forceinline__ void tma_bulk_g2s(void * dst_smem, const void * src_gmem, uint32_t bytes,
 		uint64_t * bar) {
@@ -173,8 +188,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t * bar) {
 // CTA-wide barrier exists in the chunk loop; the ring runs ahead across work-item boundaries
 // (the producer walks the CTA's item list on its own), so the first chunk of the next item
 // is already resident when the fold of the current one ends.
+// Warp-specialised: LL_THREADS compute threads (two warpgroups) + one producer warpgroup, of which a
+// single lane talks to the TMA engine.  (With the copies issued from inside a compute warp that warp
+// fell behind the other seven by the issue time of every chunk, and the seven waited for it at the
+// barrier that ends every item.)  The kernel is launched with 384 threads x 168 registers; the
+// producer warpgroup hands its registers back (setmaxnreg.dec) and the compute warpgroups take them
+// (setmaxnreg.inc), so the row loop keeps its 8 x 2 register tile.
+constexpr int LL_LAUNCH_THREADS = LL_THREADS + 128;
+__device__ __forceinline__ void group_bar_compute() {
+	asm volatile("bar.sync 1, %0;" :: "n"(LL_THREADS) : "memory");
+}
+
 template<class M>
-__global__ void __launch_bounds__(LL_THREADS, 1) loglik_tiled_kernel(const LLArgs a) {
+__global__ void __launch_bounds__(LL_LAUNCH_THREADS, 1) loglik_tiled_kernel(const LLArgs a) {
 	constexpr int C = M::LL_C, U = M::LL_U;
 	constexpr int RPT = ll_rpt<M>(), CHUNK = ll_chunk<M>(); // rows per thread per chunk, rows per chunk
 	static_assert(C <= LL_MAX_C && RPT % U == 0, "tile shape");
@@ -201,44 +227,32 @@ __global__ void __launch_bounds__(LL_THREADS, 1) loglik_tiled_kernel(const LLArg
 	const double xub = *a.xabsmax;
 	constexpr uint32_t CHUNK_BYTES = CHUNK * sizeof(Row<M>);
 
-	// ---- producer (thread 0): walks this CTA's items chunk by chunk, LL_STAGES - 1 ahead
-	int p_item = blockIdx.x;
-	uint32_t p_n = 0;
-	// (the producer's position is kept incrementally -- stage, phase, source address, chunks left in
-	// its item -- so that issuing a chunk is a dozen instructions: the issuing thread's warp stands
-	// still meanwhile, and the other warps wait for it at the end of every item)
-	uint32_t p_st = 0, p_phase = 1;          // stage of the next chunk; parity its `empty` barrier must have completed
-	int p_left = 0;                          // chunks left in the producer's current item
-	const double * p_src = nullptr;          // where the next chunk of that item starts
-	auto produce_item = [&]() {              // enter item p_item (one division per item)
-		const int k0 = (p_item / n_ctiles) * a.chunks_per_split;
-		p_left = min(a.chunks_per_split, a.n_chunks - k0);
-		p_src = a.data + (size_t) k0 * CHUNK * M::ROW_W;
-	};
-	if (p_item < n_items)
-		produce_item();
-	auto produce = [&]() {
-		if (p_left == 0)
-			return;
-		if (p_n >= LL_STAGES) // the chunk that was in this stage must have been read by every warp
-			mbar_wait(&empty[p_st], p_phase);
-		mbar_arrive_expect_tx(&full[p_st], CHUNK_BYTES);
-		tma_bulk_g2s(sdata + p_st * CHUNK, p_src, CHUNK_BYTES, &full[p_st]);
-		p_src += (size_t) CHUNK * M::ROW_W;
-		p_n++;
-		if (++p_st == LL_STAGES) {
-			p_st = 0;
-			p_phase ^= 1u;
+	// ---- producer warpgroup: gives its registers back; its first lane walks this CTA's items chunk by
+	// chunk, as far ahead as the ring allows (a stage is free again once every compute warp has
+	// arrived on its `empty` barrier); the rest of it is done at once
+	if (warp >= LL_WARPS) {
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+		if (warp == LL_WARPS && lane == 0) {
+			uint32_t p_st = 0, p_phase = 1, p_n = 0;
+			for (int p_item = blockIdx.x; p_item < n_items; p_item += gridDim.x) {
+				const int k0 = (p_item / n_ctiles) * a.chunks_per_split;
+				const int nk = min(a.chunks_per_split, a.n_chunks - k0);
+				const double * src = a.data + (size_t) k0 * CHUNK * M::ROW_W;
+				for (int p_k = 0; p_k < nk; p_k++, p_n++, src += (size_t) CHUNK * M::ROW_W) {
+					if (p_n >= LL_STAGES) // the chunk that was in this stage must have been read by every warp
+						mbar_wait_idle(&empty[p_st], p_phase);
+					mbar_arrive_expect_tx(&full[p_st], CHUNK_BYTES);
+					tma_bulk_g2s(sdata + p_st * CHUNK, src, CHUNK_BYTES, &full[p_st]);
+					if (++p_st == LL_STAGES) {
+						p_st = 0;
+						p_phase ^= 1u;
+					}
+				}
+			}
 		}
-		if (--p_left == 0) {
-			p_item += gridDim.x;
-			if (p_item < n_items)
-				produce_item();
-		}
-	};
-	if (tid == 0)
-		for (int s = 0; s < LL_STAGES - 1; s++)
-			produce();
+		return;
+	}
+	asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
 
 	uint32_t it = 0; // chunks consumed so far: stage = it % STAGES, parity = (it / STAGES) & 1
 	for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -268,8 +282,6 @@ __global__ void __launch_bounds__(LL_THREADS, 1) loglik_tiled_kernel(const LLArg
 		for (int k = 0; k < nk; k++, it++) {
 			const uint32_t st = it % LL_STAGES;
 			mbar_wait(&full[st], (it / LL_STAGES) & 1u);
-			if (tid == 0)
-				produce(); // chunk it + STAGES - 1 goes where chunk it - 1 was
 			const Row<M> * srow = sdata + st * CHUNK + tid;
 			const long long row0 = (long long) (k0 + k) * CHUNK;
 			const int n_valid = (int) min((long long) CHUNK, a.n_rows - row0);
@@ -325,7 +337,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) loglik_tiled_kernel(const LLArg
 				v = ModelAcc<M>::merge(v, acc[c][u]);
 			sacc[c * LL_THREADS + tid] = ModelAcc<M>::value(v);
 		}
-		__syncthreads();
+		group_bar_compute();
 		for (int c = warp; c < C; c += LL_WARPS) {
 			double v = 0.0;
 #pragma unroll
@@ -336,7 +348,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) loglik_tiled_kernel(const LLArg
 			if (lane == 0 && g >= 0)
 				a.partial[(size_t) g * a.n_splits + split] = v;
 		}
-		__syncthreads();
+		group_bar_compute();
 	}
 }
 
@@ -387,7 +399,7 @@ APM_D void act_push(const DevState & S, int w, int g) {
 	S.act_idx[(size_t) w * S.n_chains + slot] = g;
 }
 
-constexpr int ADV_THREADS = 128;
+constexpr int ADV_THREADS = 256;
 
 template<class M>
 APM_D double chain_gather_sum(const DevState & S, int g) {
@@ -455,9 +467,17 @@ __global__ void __launch_bounds__(ADV_THREADS) advance_kernel(const DevState S, 
 			ensemble_swap(S, ens, a.pack_prev, a.pack_next);
 	}
 	if (a.flags & ADV_PROPOSE_RUN) {
+		// do_step for every chain of the ensemble, a thread per (chain, coordinate): a coordinate's
+		// draw (Philox + log + sqrt + cos, redraws) depends on nothing but the chain's counter
 		__syncthreads();
-		for (int k = threadIdx.x; k < S.n_beta; k += blockDim.x)
-			chain_propose(S, base + k, S.n_par);
+		const int n = S.n_par;
+		for (int idx = threadIdx.x; idx < S.n_beta * n; idx += blockDim.x) {
+			const int g = base + idx / n, i = idx - (idx / n) * n;
+			S.prop[(size_t) g * n + i] = propose_coordinate(S, g, S.rng_ctr[g], i, S.params[(size_t) g * n + i],
+					S.steps[(size_t) g * n + i]);
+			if (i == 0)
+				S.pend[g] = n;
+		}
 	}
 	if (a.flags & ADV_RECORD) {
 		// every block has read the counter by the time it takes its ticket; the last one advances it
