@@ -421,6 +421,84 @@ APM_D void chain_book_step(const DevState & S, int g, int accepted, double prob_
 		chain_marginals(S, g, params_after);
 }
 
+// chain_book_step for a whole batch of `ns` consecutive full steps of chain g (free_run_kernel's
+// book-keepers): the counters move once per batch, the accumulators are carried in registers over
+// the batch -- added to in step order, so the sums are the ones step-by-step book-keeping gives.
+// Step j's outcome: ring[j * stride_j + f * stride_f], f = 0 accepted, 1 prob, 2 prior, 3 + i the
+// point after the step.  mcmc_check_best has been done by whoever decided the steps.
+APM_D void chain_book_batch(const DevState & S, int g, int ns, const double * ring, size_t stride_j, size_t stride_f,
+		long long step0) {
+	const int n = S.n_par;
+	constexpr int NR = 4; // parameters whose sums are carried in registers
+	unsigned long long acc = 0;
+	double sum_dl = S.stat_sum_dl[g];
+	double sp[NR], sp2[NR];
+#pragma unroll
+	for (int i = 0; i < NR; i++) {
+		sp[i] = i < n ? S.stat_sum_p[(size_t) g * n + i] : 0.0;
+		sp2[i] = i < n ? S.stat_sum_p2[(size_t) g * n + i] : 0.0;
+	}
+	int slot = -1;
+	if (S.tr_params != nullptr) {
+		if (S.tr_params_chains == 2)
+			slot = g;
+		else if (S.tr_params_chains == 1 && S.k_offset + g % S.n_beta == 0)
+			slot = g / S.n_beta;
+	}
+	const bool trace_prob = S.tr_prob_every > 0 && S.tr_prob != nullptr;
+	for (int j = 0; j < ns; j++) {
+		const double * e = ring + (size_t) j * stride_j;
+		const long long step_index = step0 + j;
+		const double prob = e[stride_f], prior = e[2 * stride_f], dl = prob - prior;
+		acc += e[0] != 0.0;
+		if (trace_prob && step_index % S.tr_prob_every == 0) {
+			const long long row = step_index / S.tr_prob_every;
+			S.tr_prob[row * S.n_chains + g] = prob;
+			S.tr_dl[row * S.n_chains + g] = dl;
+		}
+		sum_dl += dl;
+#pragma unroll
+		for (int i = 0; i < NR; i++)
+			if (i < n) {
+				const double v = e[(size_t) (3 + i) * stride_f];
+				sp[i] += v;
+				sp2[i] += v * v;
+				if (slot >= 0)
+					S.tr_params[((size_t) step_index * S.tr_dumped + slot) * n + i] = v;
+			}
+		for (int i = NR; i < n; i++) {
+			const double v = e[(size_t) (3 + i) * stride_f];
+			S.stat_sum_p[(size_t) g * n + i] += v;
+			S.stat_sum_p2[(size_t) g * n + i] += v * v;
+			if (slot >= 0)
+				S.tr_params[((size_t) step_index * S.tr_dumped + slot) * n + i] = v;
+		}
+		if (S.marg_mode) {
+			double pa[APM_MAX_PAR];
+			for (int i = 0; i < n; i++)
+				pa[i] = e[(size_t) (3 + i) * stride_f];
+			chain_marginals(S, g, pa);
+		}
+	}
+	const unsigned long long rej = (unsigned long long) ns - acc;
+	S.accept[g] += acc;
+	S.reject[g] += rej;
+	for (int i = 0; i < n; i++) {
+		S.pacc[(size_t) g * n + i] += acc;
+		S.prej[(size_t) g * n + i] += rej;
+	}
+	S.rng_ctr[g] += (unsigned long long) ns;
+	S.n_iter[g] += (unsigned long long) ns;
+	S.stat_n[g] += (unsigned long long) ns;
+	S.stat_sum_dl[g] = sum_dl;
+#pragma unroll
+	for (int i = 0; i < NR; i++)
+		if (i < n) {
+			S.stat_sum_p[(size_t) g * n + i] = sp[i];
+			S.stat_sum_p2[(size_t) g * n + i] = sp2[i];
+		}
+}
+
 // ---- warp-cooperative forms of chain_finalize / chain_record (fused and cluster paths) ------
 // The same state transitions, element for element, with the per-parameter work spread over
 // lanes 0..n-1 of the calling warp and the scalar work on lane 0, so that the serial tail of a

@@ -817,7 +817,7 @@ constexpr int FREE_THREADS = 1024, FREE_MAX_DECIDERS = 512, FREE_BOOK_WARPS = 2;
 template<class M, class = void> struct ModelLaneTerms { static constexpr int value = 0; };
 template<class M> struct ModelLaneTerms<M, std::void_t<decltype(M::LANE_TERMS)>> { static constexpr int value = M::LANE_TERMS; };
 
-constexpr int FREE_ATT = 2; // attempts of every jump drawn ahead (the truncated proposal redraws until inside the bounds)
+constexpr int FREE_ATT = 3; // attempts of every jump drawn ahead (the truncated proposal redraws until inside the bounds)
 
 template<class M>
 __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevState S, const FusedArgs a) {
@@ -911,14 +911,9 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 	};
 	// the book-keepers: book-keeping thread (w, l) has chains l * BOOK_WARPS + w, + 32 * BOOK_WARPS, ...
 	auto book = [&](long long s0, int ns, const double * rb, int t) {
-		for (int k = (t & 31) * FREE_BOOK_WARPS + (t >> 5); k < nb; k += n_book)
-			for (int j = 0; j < ns; j++) {
-				const double * e = rb + (size_t) j * RW * nb + k;
-				double pa[APM_MAX_PAR];
-				for (int i = 0; i < n; i++)
-					pa[i] = e[(size_t) (3 + i) * nb];
-				chain_book_step(L, k, e[0] != 0.0, e[(size_t) nb], e[(size_t) 2 * nb], pa, s0 + j);
-			}
+		if (ns > 0)
+			for (int k = (t & 31) * FREE_BOOK_WARPS + (t >> 5); k < nb; k += n_book)
+				chain_book_batch(L, k, ns, rb + k, (size_t) RW * nb, (size_t) nb, s0);
 	};
 	long long s0 = 0, s_prev = 0;
 	int ns = batch_len(0), ns_prev = 0;

@@ -167,6 +167,16 @@ APM_HD double div_pos(double a, double b) {
 	double q = a * y;
 	return fma(fma(-b, q, a), y, q);
 }
+// a / b, correctly rounded, for a divisor whose correctly rounded reciprocal y = rn(1 / b) is at hand:
+// q0 = rn(a y), the residual a - b q0 is exact in one fma, q = rn(q0 + r y) is the IEEE quotient
+// (Markstein's theorem; it needs b's mantissa not all ones -- true of the small integers this is
+// used for).  3 FP64 instructions instead of the library division's ~45 with its slow-path branch,
+// and the same bits: tests/test_math_cpu.py checks 1e7 quotients per divisor 1..9 against `/`.
+APM_HD double div_by_known(double a, double b, double y) {
+	const double q0 = a * y;
+	const double r = fma(-b, q0, a);
+	return fma(r, y, q0);
+}
 APM_HD double log_pos(double x) {
 	const double LN2_HI = 0x1.62e42fefa39efp-1, LN2_LO = 0x1.abc9e3b39803fp-56;
 	int hi = hi32(x);

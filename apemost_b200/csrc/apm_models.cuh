@@ -166,6 +166,11 @@ static __constant__ double NORMAL_EXP_I[10] = { 0x1.0000000000000p+0, 0x1.5bf0a8
 		0x1.415e5bf6fb106p+4, 0x1.b4c902e273a58p+5, 0x1.28d389970338fp+7, 0x1.936dc5690c08fp+8,
 		0x1.122885aaeddaap+10, 0x1.749ea7d470c6ep+11, 0x1.fa7157c470f82p+12 };
 
+// 1 / i, correctly rounded, for div_by_known (entry 0 is never used)
+static __constant__ double NORMAL_INV_I[10] = { 0.0, 0x1.0000000000000p+0, 0x1.0000000000000p-1, 0x1.5555555555555p-2,
+		0x1.0000000000000p-2, 0x1.999999999999ap-3, 0x1.5555555555555p-3, 0x1.2492492492492p-3, 0x1.0000000000000p-3,
+		0x1.c71c71c71c71cp-4 };
+
 struct ModelNormal {
 	static constexpr int LL_C = 1, LL_U = 1;
 	static constexpr int NPAR = 1, NCOLS = 0;
@@ -189,8 +194,8 @@ struct ModelNormal {
 	// division either way: even i: -sigma * pow((x - pos) / sigma, 2) / 2 + height, odd i:
 	// -height * |x - pos| / sigma + height (the reference's two branches differ in the sign of the
 	// difference only).  i = 0 divides by sigma = 0: its a is NaN (0 * inf) for every x and never
-	// passes `a > b`, so it is handed out as NaN without the division (which would take the
-	// divide's slow path on every step).
+	// passes `a > b`, so it is handed out as NaN without the division.  The divisions by 1 .. 9 are
+	// div_by_known (apm_math.cuh): the IEEE quotient in three instructions.
 	APM_D static double term(int i, const double * p, const double *) {
 		const double x = p[0];
 		const double pos = NORMAL_EXP_I[i];
@@ -201,7 +206,7 @@ struct ModelNormal {
 		const double num = even ? x - pos : -height * d;
 		if (i == 0)
 			return __longlong_as_double(0x7ff8000000000000ll);
-		const double quo = num / sigma;
+		const double quo = div_by_known(num, sigma, NORMAL_INV_I[i]); // = num / sigma, bit for bit
 		return even ? -sigma * (quo * quo) / 2 + height : quo + height;
 	}
 	APM_D static double reduce_init() { return 0.0; }                           // b = 0 (:11)

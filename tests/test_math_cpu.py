@@ -20,6 +20,13 @@ void t_sin_full(const double * x, double * y, long n) { for (long i = 0; i < n; 
 void t_log_pos(const double * x, double * y, long n) { for (long i = 0; i < n; i++) y[i] = apm::log_pos(x[i]); }
 void t_div_pos(const double * a, const double * b, double * y, long n) { for (long i = 0; i < n; i++) y[i] = apm::div_pos(a[i], b[i]); }
 double t_mod_double(double x, double d) { return apm::mod_double(x, d); }
+long t_div_by_known_mismatches(const double * a, long n, int b) {
+	long bad = 0;
+	const double d = (double) b, y = 1.0 / d;
+	for (long i = 0; i < n; i++)
+		bad += apm::div_by_known(a[i], d, y) != a[i] / d;
+	return bad;
+}
 void t_philox(const unsigned * c, const unsigned * k, unsigned * o) {
 	apm::Philox4 r = apm::philox4x32_10(c[0], c[1], c[2], c[3], k[0], k[1]);
 	for (int i = 0; i < 4; i++) o[i] = r.w[i];
@@ -134,3 +141,16 @@ def test_mod_double_reference_values(lib):
     """the six values of the reference's tests/tests.c:152-160"""
     for x, d, want in [(5.0, 3.0, 2.0), (-1.0, 3.0, 2.0), (3.5, 1.0, 0.5), (-0.25, 1.0, 0.75)]:
         assert abs(lib.t_mod_double(x, d) - want) < 1e-12
+
+
+def test_div_by_known_is_the_ieee_quotient(lib):
+    """div_by_known (three fp64 instructions, used for apps/normal.c's divisions by sigma = 1 .. 9) gives
+    the bits of `/`: wide-range values, differences x - pos, products -height * d, zero"""
+    rng = np.random.default_rng(5)
+    a = np.concatenate([rng.normal(0, 1, 2_000_000) * 10.0 ** rng.uniform(-12, 12, 2_000_000),
+                        rng.uniform(-1e4, 1e4, 4_000_000), -10.0 * rng.uniform(0, 1e4, 4_000_000), [0.0, -0.0]])
+    a = np.ascontiguousarray(a)
+    lib.t_div_by_known_mismatches.restype = C.c_long
+    for b in range(1, 10):
+        assert lib.t_div_by_known_mismatches(a.ctypes.data_as(C.POINTER(C.c_double)), C.c_long(a.size), C.c_int(b)) == 0
+
