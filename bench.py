@@ -14,7 +14,10 @@ Metropolis steps actually executed (rejected ones included, swaps excluded).
   roofline  dominant kernel = loglik_tiled_kernel<simplesin5>; FP64-pipe bound (the likelihood
             is a transcendental map-reduce).  achieved = row-evaluations/s x 17
             FP64 instructions (4 arithmetic + 13 for sin, the ALGORITHMIC count) over the
-            kernel's CUDA-event time; peak = DFMA issue rate measured live on this GPU
+            kernel's CUDA-event time (a second pass over the same K steps with events around every
+            likelihood launch); peak = FP64 lanes per SM per clock measured live (clock64() around
+            a DFMA stream) x SMs x the SM clock sampled during the timed region; frac_vs_spec,
+            the executed count (18) and round 1's per-second DFMA denominator are printed beside it
   cpu_baseline  the CPU oracle (reference semantics, OpenMP over chains like the reference)
             on this box's cores, bounded sample
 
