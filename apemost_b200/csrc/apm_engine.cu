@@ -900,10 +900,30 @@ static int run_fused_t(apm_gpu * h, long long n_rounds, int n_swap) {
 	h->ev_used = 0;
 	cudaEvent_t t0 = next_event(h), t1 = next_event(h);
 	CU(cudaEventRecord(t0, h->stream));
-	if constexpr (M::HAS_DATA)
+	if constexpr (M::HAS_DATA) {
 		fused_run_kernel<M><<<h->cfg.n_ensembles, threads, smem, h->stream>>>(h->S, a);
-	else
-		free_run_kernel<M><<<h->cfg.n_ensembles, FREE_THREADS, smem, h->stream>>>(h->S, a);
+	} else {
+		// a cluster of two CTAs per ensemble: one plays the chains, one draws (free_run_kernel)
+		cudaLaunchConfig_t lc;
+		memset(&lc, 0, sizeof(lc));
+		lc.gridDim = dim3((unsigned) (h->cfg.n_ensembles * FREE_CLUSTER));
+		lc.blockDim = dim3((unsigned) FREE_THREADS);
+		lc.dynamicSmemBytes = smem;
+		lc.stream = h->stream;
+		cudaLaunchAttribute attr[1];
+		attr[0].id = cudaLaunchAttributeClusterDimension;
+		attr[0].val.clusterDim.x = (unsigned) FREE_CLUSTER;
+		attr[0].val.clusterDim.y = 1;
+		attr[0].val.clusterDim.z = 1;
+		lc.attrs = attr;
+		lc.numAttrs = 1;
+		int max_clusters = 0;
+		CU(cudaOccupancyMaxActiveClusters(&max_clusters, free_run_kernel<M>, &lc));
+		if (max_clusters < 1)
+			return fail(h, APM_ENOTAPPLICABLE, "a cluster of %d CTAs x %d threads x %zu bytes cannot be scheduled",
+					FREE_CLUSTER, FREE_THREADS, smem);
+		CU(cudaLaunchKernelEx(&lc, free_run_kernel<M>, h->S, a));
+	}
 	h->launches++;
 	CU(cudaEventRecord(t1, h->stream));
 	CU(cudaStreamSynchronize(h->stream));

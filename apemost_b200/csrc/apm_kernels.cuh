@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_run_kernel(cons
 //   * BOOK-KEEPERS write batch b - 1 down from the ring (chain_book_step: counters, n_iter, trace
 //     rows, accumulators), a thread per chain.
 // Values and order of operations are those of chain_propose / chain_finalize / chain_record.
-constexpr int FREE_THREADS = 1024, FREE_MAX_DECIDERS = 512, FREE_BOOK_WARPS = 2;
+constexpr int FREE_THREADS = 768, FREE_MAX_DECIDERS = 512, FREE_BOOK_WARPS = 2, FREE_CLUSTER = 2;
 
 template<class M, class = void> struct ModelLaneTerms { static constexpr int value = 0; };
 template<class M> struct ModelLaneTerms<M, std::void_t<decltype(M::LANE_TERMS)>> { static constexpr int value = M::LANE_TERMS; };
@@ -825,7 +825,12 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 	constexpr int TERMS = ModelLaneTerms<M>::value;
 	constexpr int LPC = TERMS > 0 ? 8 : 1;             // lanes per chain
 	__shared__ DevState L_sh;
-	const int ens = blockIdx.x, tid = threadIdx.x;
+	// a cluster of two CTAs (two SMs) per ensemble: CTA 0 plays the chains and keeps their books, CTA 1
+	// only draws, straight into CTA 0's shared memory (distributed shared memory) -- the draws are
+	// two thirds of a step's instructions and most of its fp64 work, and on one SM they competed
+	// with the deciders for issue slots and the fp64 pipe
+	const unsigned rank = cooperative_groups::this_cluster().block_rank();
+	const int ens = blockIdx.x / FREE_CLUSTER, tid = threadIdx.x;
 	{
 		const DevState L_tmp = fused_localize(S, ens, fused_smem + fused_table_bytes(0));
 		if (tid == 0)
@@ -833,7 +838,9 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 		__syncthreads();
 	}
 	const DevState & L = L_sh;
-	const int nb = L.n_beta, n = L.n_par, RW = n + 3;
+	// (a model with a fixed number of parameters -- apps/normal.c has one -- makes n a compile-time
+	// constant: the strides and the per-coordinate loops below fold away)
+	const int nb = L.n_beta, n = M::NPAR > 0 ? M::NPAR : L.n_par, RW = n + 3;
 	const int NE = FREE_ATT * n + 1;                    // draws per step: FREE_ATT attempts per coordinate + the accept draw
 	const int K = max(1, min(64 / NE, 64 / RW));        // steps per batch
 	// after the state: draws [2][K NE <= 64][nb], outcome ring [2][K RW <= 64][nb], counters [nb]
@@ -842,7 +849,7 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 	u64 * ctr0 = reinterpret_cast<u64 *>(ring + (size_t) 2 * nb * 64); // the chains' counters at the launch's start
 	const int n_dec = min((nb * LPC + 31) / 32 * 32, FREE_MAX_DECIDERS);
 	const int n_book = FREE_BOOK_WARPS * 32;
-	const int n_prod = (int) blockDim.x - n_dec - n_book;
+	double * dbuf_w = cooperative_groups::this_cluster().map_shared_rank(dbuf, 0); // CTA 0's draw buffers
 	const int n_slots = n_dec / LPC, slot = tid / LPC, sl = tid % LPC;
 	const unsigned gmask = LPC == 1 ? (1u << (tid & 31)) : (0xffu << ((tid & 31) & ~7));
 	const int proposal = L.proposal;
@@ -917,16 +924,19 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 	};
 	long long s0 = 0, s_prev = 0;
 	int ns = batch_len(0), ns_prev = 0;
-	produce(0, ns, dbuf, tid, blockDim.x);
-	__syncthreads();
+	if (rank == 1)
+		produce(0, ns, dbuf_w, tid, blockDim.x);
+	cooperative_groups::this_cluster().sync();
 	int cur = 0;
 	while (ns > 0) {
 		const long long s_next = s0 + ns;
 		const int ns_next = batch_len(s_next);
 		const double * buf = dbuf + (size_t) cur * nb * 64;
 		double * rb = ring + (size_t) cur * nb * 64;
-		if (tid >= n_dec + n_book) {
-			produce(s_next, ns_next, dbuf + (size_t) (1 - cur) * nb * 64, tid - n_dec - n_book, n_prod);
+		if (rank == 1) {
+			produce(s_next, ns_next, dbuf_w + (size_t) (1 - cur) * nb * 64, tid, blockDim.x);
+		} else if (tid >= n_dec + n_book) {
+			// (nothing: the third of CTA 0 that neither decides nor keeps books)
 		} else if (tid >= n_dec) {
 			book(s_prev, ns_prev, ring + (size_t) (1 - cur) * nb * 64, tid - n_dec);
 		} else if constexpr (TERMS > 0) {
@@ -1094,8 +1104,8 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 				}
 			}
 		}
-		__syncthreads();
-		if (s_next % a.n_swap == 0) {
+		cooperative_groups::this_cluster().sync(); // batch b is decided, batch b + 1 is drawn (and visible in CTA 0), batch b - 1 is written down
+		if (rank == 0 && s_next % a.n_swap == 0) {
 			// round end: adapt (if compiled in: it reads the counters, so the books are brought up
 			// to date first), tempering_interaction for this ensemble
 			if (L.adapt) {
@@ -1117,6 +1127,8 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 		ns = ns_next;
 		cur = 1 - cur;
 	}
+	if (rank != 0)
+		return;
 	if (tid >= n_dec && tid < n_dec + n_book)
 		book(s_prev, ns_prev, ring + (size_t) (1 - cur) * nb * 64, tid - n_dec);
 	fused_writeback(S, L, ens);
