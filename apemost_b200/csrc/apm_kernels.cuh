@@ -548,8 +548,15 @@ __host__ __device__ inline size_t fused_state_bytes(int n_beta, int n_par) {
 // fused_run_kernel: per chain a batch of random draws (32 doubles) and its base counter
 // (data-free models, free_run_kernel: two such batches, one being drawn while the other is used, and
 // two batches of step outcomes, each of at most 64 doubles per chain)
+#ifndef APM_FREE_ATT
+#define APM_FREE_ATT 3
+#endif
+#ifndef APM_FREE_DRAW_SLOTS
+#define APM_FREE_DRAW_SLOTS 64
+#endif
+constexpr int FREE_DRAW_SLOTS = APM_FREE_DRAW_SLOTS, FREE_RING_SLOTS = 64; // doubles per chain and batch
 __host__ __device__ inline size_t fused_draws_bytes(int n_beta, bool has_data = true) {
-	return (size_t) n_beta * ((has_data ? 32 : 128 + 128) * sizeof(double) + sizeof(unsigned long long));
+	return (size_t) n_beta * ((has_data ? 32 : 2 * FREE_DRAW_SLOTS + 2 * FREE_RING_SLOTS) * sizeof(double) + sizeof(unsigned long long));
 }
 __host__ __device__ inline size_t fused_table_bytes(long long n_slots) {
 	return (((size_t) n_slots * 16 + 127) & ~(size_t) 127) + 16 /* mbarrier */;
@@ -817,7 +824,8 @@ constexpr int FREE_THREADS = 768, FREE_MAX_DECIDERS = 512, FREE_BOOK_WARPS = 2, 
 template<class M, class = void> struct ModelLaneTerms { static constexpr int value = 0; };
 template<class M> struct ModelLaneTerms<M, std::void_t<decltype(M::LANE_TERMS)>> { static constexpr int value = M::LANE_TERMS; };
 
-constexpr int FREE_ATT = 3; // attempts of every jump drawn ahead (the truncated proposal redraws until inside the bounds)
+constexpr int FREE_REG_NPAR = 4; // up to so many compile-time parameters stay in every lane's registers
+constexpr int FREE_ATT = APM_FREE_ATT; // attempts of every jump drawn ahead (the truncated proposal redraws until inside the bounds)
 
 template<class M>
 __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevState S, const FusedArgs a) {
@@ -842,11 +850,11 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 	// constant: the strides and the per-coordinate loops below fold away)
 	const int nb = L.n_beta, n = M::NPAR > 0 ? M::NPAR : L.n_par, RW = n + 3;
 	const int NE = FREE_ATT * n + 1;                    // draws per step: FREE_ATT attempts per coordinate + the accept draw
-	const int K = max(1, min(64 / NE, 64 / RW));        // steps per batch
+	const int K = max(1, min(FREE_DRAW_SLOTS / NE, FREE_RING_SLOTS / RW));        // steps per batch
 	// after the state: draws [2][K NE <= 64][nb], outcome ring [2][K RW <= 64][nb], counters [nb]
 	double * dbuf = reinterpret_cast<double *>(fused_smem + fused_table_bytes(0) + fused_state_bytes(nb, n));
-	double * ring = dbuf + (size_t) 2 * nb * 64;
-	u64 * ctr0 = reinterpret_cast<u64 *>(ring + (size_t) 2 * nb * 64); // the chains' counters at the launch's start
+	double * ring = dbuf + (size_t) 2 * nb * FREE_DRAW_SLOTS;
+	u64 * ctr0 = reinterpret_cast<u64 *>(ring + (size_t) 2 * nb * FREE_RING_SLOTS); // the chains' counters at the launch's start
 	const int n_dec = min((nb * LPC + 31) / 32 * 32, FREE_MAX_DECIDERS);
 	const int n_book = FREE_BOOK_WARPS * 32;
 	double * dbuf_w = cooperative_groups::this_cluster().map_shared_rank(dbuf, 0); // CTA 0's draw buffers
@@ -860,10 +868,11 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 	const long long total = a.n_rounds * a.n_swap;
 	// batch: steps [s0, s0 + ns) of the launch, never across a round's end (the swap needs every chain
 	// at the same step)
-	auto batch_len = [&](long long s0) -> int {
+	// (pos = the batch's first step within its round, carried along: no 64-bit remainder per batch)
+	auto batch_len = [&](long long s0, int pos) -> int {
 		if (s0 >= total)
 			return 0;
-		const int left = a.n_swap - (int) (s0 % a.n_swap);
+		const int left = a.n_swap - pos;
 		return left < K ? left : K;
 	};
 	// draws [j][e][k], k fastest: e = d * FREE_ATT + attempt the unit jump of coordinate d, e = NE - 1
@@ -923,22 +932,24 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 				chain_book_batch(L, k, ns, rb + k, (size_t) RW * nb, (size_t) nb, s0);
 	};
 	long long s0 = 0, s_prev = 0;
-	int ns = batch_len(0), ns_prev = 0;
+	int pos = 0;
+	int ns = batch_len(0, 0), ns_prev = 0;
 	if (rank == 1)
 		produce(0, ns, dbuf_w, tid, blockDim.x);
 	cooperative_groups::this_cluster().sync();
 	int cur = 0;
 	while (ns > 0) {
 		const long long s_next = s0 + ns;
-		const int ns_next = batch_len(s_next);
-		const double * buf = dbuf + (size_t) cur * nb * 64;
-		double * rb = ring + (size_t) cur * nb * 64;
+		const int pos_next = pos + ns == a.n_swap ? 0 : pos + ns;
+		const int ns_next = batch_len(s_next, pos_next);
+		const double * buf = dbuf + (size_t) cur * nb * FREE_DRAW_SLOTS;
+		double * rb = ring + (size_t) cur * nb * FREE_RING_SLOTS;
 		if (rank == 1) {
-			produce(s_next, ns_next, dbuf_w + (size_t) (1 - cur) * nb * 64, tid, blockDim.x);
+			produce(s_next, ns_next, dbuf_w + (size_t) (1 - cur) * nb * FREE_DRAW_SLOTS, tid, blockDim.x);
 		} else if (tid >= n_dec + n_book) {
 			// (nothing: the third of CTA 0 that neither decides nor keeps books)
 		} else if (tid >= n_dec) {
-			book(s_prev, ns_prev, ring + (size_t) (1 - cur) * nb * 64, tid - n_dec);
+			book(s_prev, ns_prev, ring + (size_t) (1 - cur) * nb * FREE_RING_SLOTS, tid - n_dec);
 		} else if constexpr (TERMS > 0) {
 			// 8 lanes per chain; the chain's point, prob, prior and best stay in the lanes' registers
 			// for the batch (lane sl holds coordinate sl -- and sl + 8 when n_par > 8)
@@ -1054,7 +1065,114 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 					}
 				}
 			};
-			if (n <= 8)
+			// A model with a handful of parameters, their number known at compile time (apps/normal.c
+			// has one): every lane of the chain's group forms the WHOLE proposal redundantly (same
+			// instructions on the same inputs: same bits), so the point never leaves the registers --
+			// no shared-memory round trip and no group barrier between proposal and terms -- and every
+			// warp runs the same trips (a group without a chain shadows the last chain and writes
+			// nothing), which makes the butterfly's shuffles full-mask ones.
+			auto decide_small = [&]() {
+				constexpr int NP = M::NPAR > 0 ? M::NPAR : 1;
+				const size_t step_stride = (size_t) NE * nb, ring_stride = (size_t) RW * nb;
+				const double * mc = L.model_const;
+				for (int k0 = 0; k0 < nb; k0 += n_slots) {
+					const bool writer = k0 + slot < nb && sl == 0;
+					const int k = k0 + slot < nb ? k0 + slot : nb - 1;
+					double x[NP], st[NP], lo[NP], hi[NP], v[NP];
+#pragma unroll
+					for (int i = 0; i < NP; i++) {
+						x[i] = L.params[(size_t) k * NP + i];
+						st[i] = L.steps[(size_t) k * NP + i];
+						lo[i] = L.pmin[i];
+						hi[i] = L.pmax[i];
+					}
+					double prob = L.prob[k], prior = L.prior[k], best = L.prob_best[k];
+					const double beta = L.beta[k];
+					const double * z = buf + k;   // this step's draws of chain k, strided by nb
+					double * e = rb + k;          // this step's outcome
+					u64 ctr = ctr0[k] + (u64) s0;
+					for (int j = 0; j < ns; j++, z += step_stride, e += ring_stride, ctr++) {
+						const double logu = z[(size_t) (NE - 1) * nb];
+#pragma unroll
+						for (int i = 0; i < NP; i++) {
+							// do_step_for (reference src/markov_chain.c:226-270), the first FREE_ATT attempts at hand
+							const double * zi = z + (size_t) (i * FREE_ATT) * nb;
+							double w = x[i] + jump_apply(proposal, st[i], zi[0]);
+							if (w > hi[i] || w < lo[i]) {
+								bool inside = false;
+								const bool wraps = (circular >> i) & 1u;
+								if (!wraps) {
+#pragma unroll
+									for (int t = 1; t < FREE_ATT; t++)
+										if (!inside) {
+											w = x[i] + jump_apply(proposal, st[i], zi[(size_t) t * nb]);
+											inside = !(w > hi[i] || w < lo[i]);
+										}
+								}
+								if (!inside) // a circular parameter's wrap, or more redraws than were drawn ahead
+									w = propose_coordinate(L, k, ctr, i, x[i], st[i], wraps ? 0u : (unsigned) FREE_ATT);
+							}
+							v[i] = w;
+						}
+						double prior_new = prior;
+						if (M::HAS_PRIOR)
+							prior_new = M::prior(v, NP, mc);
+						double r = M::reduce_init();
+#pragma unroll
+						for (int t0 = 0; t0 < TERMS; t0 += LPC) {
+							const int t = t0 + sl;
+							const double term = M::term(t < TERMS ? t : TERMS - 1, v, mc);
+							r = t < TERMS ? M::reduce(r, term) : r;
+						}
+						__syncwarp();
+#pragma unroll
+						for (int o = LPC / 2; o > 0; o >>= 1)
+							r = M::reduce(r, __shfl_xor_sync(0xffffffffu, r, o));
+						const double prob_new = M::finish_reduced(beta, r);
+						// check_accept (reference src/markov_chain.c:282-311), as in chain_finalize_value
+						bool accepted;
+						if (prob_new == prob)
+							accepted = true;
+						else if (prob_new > prob)
+							accepted = true;
+						else
+							accepted = logu < (prob_new - prob);
+						if (accepted) {
+#pragma unroll
+							for (int i = 0; i < NP; i++)
+								x[i] = v[i];
+							prob = prob_new;
+							prior = prior_new;
+						} else if (quirks & 2u) {
+							prior = prior_new; // revert() restores prob only
+						}
+						const bool better = prob > best; // mcmc_check_best (chain_book_step sees it done)
+						best = better ? prob : best;
+						if (writer) {
+							e[0] = accepted ? 1.0 : 0.0;
+							e[(size_t) nb] = prob;
+							e[(size_t) 2 * nb] = prior;
+#pragma unroll
+							for (int i = 0; i < NP; i++) {
+								e[(size_t) (3 + i) * nb] = x[i];
+								if (better)
+									L.params_best[(size_t) k * NP + i] = x[i];
+							}
+						}
+					}
+					if (writer) {
+#pragma unroll
+						for (int i = 0; i < NP; i++)
+							L.params[(size_t) k * NP + i] = x[i];
+						L.prob[k] = prob;
+						L.prior[k] = prior;
+						L.prob_best[k] = best;
+					}
+				}
+			};
+			if constexpr (M::NPAR > 0 && M::NPAR <= FREE_REG_NPAR)
+				decide_small();
+			else if (n <= 8)
 				decide(std::integral_constant<int, 1>());
 			else
 				decide(std::integral_constant<int, APM_MAX_PAR / 8>());
@@ -1105,7 +1223,7 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 			}
 		}
 		cooperative_groups::this_cluster().sync(); // batch b is decided, batch b + 1 is drawn (and visible in CTA 0), batch b - 1 is written down
-		if (rank == 0 && s_next % a.n_swap == 0) {
+		if (rank == 0 && pos_next == 0) {
 			// round end: adapt (if compiled in: it reads the counters, so the books are brought up
 			// to date first), tempering_interaction for this ensemble
 			if (L.adapt) {
@@ -1124,13 +1242,14 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 		s_prev = s0;
 		ns_prev = ns;
 		s0 = s_next;
+		pos = pos_next;
 		ns = ns_next;
 		cur = 1 - cur;
 	}
 	if (rank != 0)
 		return;
 	if (tid >= n_dec && tid < n_dec + n_book)
-		book(s_prev, ns_prev, ring + (size_t) (1 - cur) * nb * 64, tid - n_dec);
+		book(s_prev, ns_prev, ring + (size_t) (1 - cur) * nb * FREE_RING_SLOTS, tid - n_dec);
 	fused_writeback(S, L, ens);
 }
 
