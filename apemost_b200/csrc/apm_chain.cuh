@@ -752,17 +752,37 @@ APM_D void chain_adapt(const DevState & S, int g) {
 // pack_next = first rung of the next one, [n_ens][LADDER_PACK(n)] each.
 #define LADDER_PACK(n) (4 + 2 * (n))
 
+// The two draws of a round (which pair, and the logarithm the exchange is tested against) depend on
+// the ensemble's id and its round counter only: a caller with idle threads may take them ahead of
+// time (ensemble_swap_draws) and hand them over as `drawn`.
+APM_D void ensemble_swap_draws(const DevState & S, int ens, double * drawn) {
+	const uint32_t id = (uint32_t) (S.ensemble_id_offset + ens);
+	const u64 round = S.swap_round[ens];
+	double u_pick, u_test, dummy;
+	philox_uniforms(S.seed, id, round, PURPOSE_SWAP_PICK, 0, 0, u_pick, dummy);
+	philox_uniforms(S.seed, id, round, PURPOSE_SWAP_TEST, 0, 0, u_test, dummy);
+	drawn[0] = u_pick;
+	drawn[1] = log(u_test);
+}
+
 APM_D void ensemble_swap(const DevState & S, int ens, const double * pack_prev = nullptr,
-		const double * pack_next = nullptr) {
+		const double * pack_next = nullptr, const double * drawn = nullptr) {
 	const int n_beta = S.n_beta, n = S.n_par, total = S.n_beta_total;
 	if (total == 1)
 		return;
 	const int base = ens * n_beta;
 	const uint32_t id = (uint32_t) (S.ensemble_id_offset + ens);
 	const u64 round = S.swap_round[ens];
-	double u_pick, u_test, dummy;
-	philox_uniforms(S.seed, id, round, PURPOSE_SWAP_PICK, 0, 0, u_pick, dummy);
-	philox_uniforms(S.seed, id, round, PURPOSE_SWAP_TEST, 0, 0, u_test, dummy);
+	double u_pick, log_u_test;
+	if (drawn != nullptr) {
+		u_pick = drawn[0];
+		log_u_test = drawn[1];
+	} else {
+		double u_test, dummy;
+		philox_uniforms(S.seed, id, round, PURPOSE_SWAP_PICK, 0, 0, u_pick, dummy);
+		philox_uniforms(S.seed, id, round, PURPOSE_SWAP_TEST, 0, 0, u_test, dummy);
+		log_u_test = log(u_test);
+	}
 	S.swap_round[ens] = round + 1;
 	const int a = (int) (total * 1000 * u_pick) % (total - 1); // rung of the whole ladder
 	const int la = a - S.k_offset, lb = la + 1;                  // positions on this device
@@ -790,7 +810,7 @@ APM_D void ensemble_swap(const DevState & S, int ens, const double * pack_prev =
 		double lb_ = (b_prob - b_prior) / b_beta;
 		r = (a_beta - b_beta) * (lb_ - la_);
 	}
-	if (r > log(u_test)) {
+	if (r > log_u_test) {
 		for (int i = 0; i < n; i++) {
 			const double ta = a_params[i], tb = b_params[i];
 			if (own_a)

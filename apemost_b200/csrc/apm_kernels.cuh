@@ -819,7 +819,11 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_run_kernel(cons
 //   * BOOK-KEEPERS write batch b - 1 down from the ring (chain_book_step: counters, n_iter, trace
 //     rows, accumulators), a thread per chain.
 // Values and order of operations are those of chain_propose / chain_finalize / chain_record.
-constexpr int FREE_THREADS = 768, FREE_MAX_DECIDERS = 512, FREE_BOOK_WARPS = 2, FREE_CLUSTER = 2;
+#ifndef APM_FREE_THREADS
+#define APM_FREE_THREADS 512 /* (128 registers a thread: the deciders' loop keeps everything in registers) */
+#endif
+constexpr int FREE_THREADS = APM_FREE_THREADS, FREE_BOOK_WARPS = 2, FREE_CLUSTER = 2;
+constexpr int FREE_MAX_DECIDERS = (FREE_THREADS - 32 * FREE_BOOK_WARPS - 32) / 128 * 128; // (a warp is left for the swap's draws)
 
 template<class M, class = void> struct ModelLaneTerms { static constexpr int value = 0; };
 template<class M> struct ModelLaneTerms<M, std::void_t<decltype(M::LANE_TERMS)>> { static constexpr int value = M::LANE_TERMS; };
@@ -831,8 +835,13 @@ template<class M>
 __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevState S, const FusedArgs a) {
 	extern __shared__ __align__(128) unsigned char fused_smem[];
 	constexpr int TERMS = ModelLaneTerms<M>::value;
-	constexpr int LPC = TERMS > 0 ? 8 : 1;             // lanes per chain
+#ifndef APM_FREE_LPC_SMALL
+#define APM_FREE_LPC_SMALL 4
+#endif
+	constexpr bool SMALL = TERMS > 0 && M::NPAR > 0 && M::NPAR <= FREE_REG_NPAR;
+	constexpr int LPC = TERMS > 0 ? (SMALL ? APM_FREE_LPC_SMALL : 8) : 1; // lanes per chain
 	__shared__ DevState L_sh;
+	__shared__ double swap_drawn[2];
 	// a cluster of two CTAs (two SMs) per ensemble: CTA 0 plays the chains and keeps their books, CTA 1
 	// only draws, straight into CTA 0's shared memory (distributed shared memory) -- the draws are
 	// two thirds of a step's instructions and most of its fp64 work, and on one SM they competed
@@ -883,26 +892,35 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 		const int pc = t % cols, pr = t / cols;
 		if (pr >= rows)
 			return;
+		// a draw is one long chain of dependent instructions (Philox, logarithm, square root, cosine):
+		// a thread takes them two at a time, side by side
+		const int NJ = NE - 1, nj = ns * NJ; // jump draws of a chain in this batch: m = j NJ + e
 		for (int k = pc; k < nb; k += cols) {
 			const uint32_t id = chain_rng_id(L, k);
 			const u64 c0 = ctr0[k] + (u64) s0;
-			int j = 0, e = pr;
-			while (e >= NE) {
-				e -= NE;
-				j++;
+			for (int m = pr; m < nj; m += 2 * rows) {
+				const bool two = m + rows < nj;
+				const int ma = m, mb = two ? m + rows : m;
+				const int ja = ma / NJ, ea = ma - ja * NJ, jb = mb / NJ, eb = mb - jb * NJ;
+				const int da = ea / FREE_ATT, db = eb / FREE_ATT; // (a constant divisor)
+				double u0a, u1a, u0b, u1b, za, zb;
+				philox_uniforms(L.seed, id, c0 + (u64) ja, PURPOSE_JUMP, (uint32_t) da, (uint32_t) (ea - da * FREE_ATT), u0a, u1a);
+				philox_uniforms(L.seed, id, c0 + (u64) jb, PURPOSE_JUMP, (uint32_t) db, (uint32_t) (eb - db * FREE_ATT), u0b, u1b);
+				jump_unit2(proposal, u0a, u1a, u0b, u1b, za, zb);
+				buf[(size_t) (ja * NE + ea) * nb + k] = za;
+				if (two)
+					buf[(size_t) (jb * NE + eb) * nb + k] = zb;
 			}
-			while (j < ns) {
-				double u0, u1;
-				const bool is_jump = e < NE - 1;
-				const int d = e / FREE_ATT; // (a constant divisor)
-				philox_uniforms(L.seed, id, c0 + (u64) j, is_jump ? PURPOSE_JUMP : PURPOSE_ACCEPT,
-						is_jump ? (uint32_t) d : 0u, is_jump ? (uint32_t) (e - d * FREE_ATT) : 0u, u0, u1);
-				buf[(size_t) (j * NE + e) * nb + k] = is_jump ? jump_unit(proposal, u0, u1) : log(u0);
-				e += rows;
-				while (e >= NE) {
-					e -= NE;
-					j++;
-				}
+			for (int j = pr; j < ns; j += 2 * rows) {
+				const bool two = j + rows < ns;
+				const int jb = two ? j + rows : j;
+				double u0a, u0b, dummy;
+				philox_uniforms(L.seed, id, c0 + (u64) j, PURPOSE_ACCEPT, 0u, 0u, u0a, dummy);
+				philox_uniforms(L.seed, id, c0 + (u64) jb, PURPOSE_ACCEPT, 0u, 0u, u0b, dummy);
+				const double la = log(u0a), lb = log(u0b);
+				buf[(size_t) (j * NE + NE - 1) * nb + k] = la;
+				if (two)
+					buf[(size_t) (jb * NE + NE - 1) * nb + k] = lb;
 			}
 		}
 	};
@@ -938,6 +956,12 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 		produce(0, ns, dbuf_w, tid, blockDim.x);
 	cooperative_groups::this_cluster().sync();
 	int cur = 0;
+#ifdef APM_FREE_CLOCKS /* (timing experiments only: where a warp of each role spends its clocks) */
+	long long clk_work = 0, clk_bar = 0, clk_end = 0, clk_t = clock64();
+#define FREE_CLK(acc) { const long long t_ = clock64(); acc += t_ - clk_t; clk_t = t_; }
+#else
+#define FREE_CLK(acc)
+#endif
 	while (ns > 0) {
 		const long long s_next = s0 + ns;
 		const int pos_next = pos + ns == a.n_swap ? 0 : pos + ns;
@@ -947,7 +971,10 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 		if (rank == 1) {
 			produce(s_next, ns_next, dbuf_w + (size_t) (1 - cur) * nb * FREE_DRAW_SLOTS, tid, blockDim.x);
 		} else if (tid >= n_dec + n_book) {
-			// (nothing: the third of CTA 0 that neither decides nor keeps books)
+			// the rest of CTA 0 neither decides nor keeps books; one of its threads takes the draws of
+			// the swap that follows a round's last batch, so that they are not waited for at the round's end
+			if (tid == n_dec + n_book && pos_next == 0)
+				ensemble_swap_draws(L, 0, swap_drawn);
 		} else if (tid >= n_dec) {
 			book(s_prev, ns_prev, ring + (size_t) (1 - cur) * nb * FREE_RING_SLOTS, tid - n_dec);
 		} else if constexpr (TERMS > 0) {
@@ -1075,9 +1102,13 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 				constexpr int NP = M::NPAR > 0 ? M::NPAR : 1;
 				const size_t step_stride = (size_t) NE * nb, ring_stride = (size_t) RW * nb;
 				const double * mc = L.model_const;
+				// (the hot rungs redraw their proposals more often than the cold ones, and a warp waits for
+				// whichever of its chains does: warp w takes chains w, w + n_warps, ... -- a mix of rungs)
+				constexpr int SPW = 32 / LPC;
+				const int pslot = (slot % SPW) * (n_dec / 32) + slot / SPW;
 				for (int k0 = 0; k0 < nb; k0 += n_slots) {
-					const bool writer = k0 + slot < nb && sl == 0;
-					const int k = k0 + slot < nb ? k0 + slot : nb - 1;
+					const bool writer = k0 + pslot < nb && sl == 0;
+					const int k = k0 + pslot < nb ? k0 + pslot : nb - 1;
 					double x[NP], st[NP], lo[NP], hi[NP], v[NP];
 #pragma unroll
 					for (int i = 0; i < NP; i++) {
@@ -1170,7 +1201,7 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 					}
 				}
 			};
-			if constexpr (M::NPAR > 0 && M::NPAR <= FREE_REG_NPAR)
+			if constexpr (SMALL)
 				decide_small();
 			else if (n <= 8)
 				decide(std::integral_constant<int, 1>());
@@ -1222,7 +1253,9 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 				}
 			}
 		}
+		FREE_CLK(clk_work)
 		cooperative_groups::this_cluster().sync(); // batch b is decided, batch b + 1 is drawn (and visible in CTA 0), batch b - 1 is written down
+		FREE_CLK(clk_bar)
 		if (rank == 0 && pos_next == 0) {
 			// round end: adapt (if compiled in: it reads the counters, so the books are brought up
 			// to date first), tempering_interaction for this ensemble
@@ -1236,9 +1269,10 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 				__syncthreads();
 			}
 			if (tid == 0)
-				ensemble_swap(L, 0);
+				ensemble_swap(L, 0, nullptr, nullptr, swap_drawn);
 			__syncthreads();
 		}
+		FREE_CLK(clk_end)
 		s_prev = s0;
 		ns_prev = ns;
 		s0 = s_next;
@@ -1246,6 +1280,10 @@ __global__ void __launch_bounds__(FREE_THREADS, 1) free_run_kernel(const DevStat
 		ns = ns_next;
 		cur = 1 - cur;
 	}
+#ifdef APM_FREE_CLOCKS
+	if (blockIdx.x < 2 && ((tid < n_dec && tid % 32 == 0) || tid == n_dec || tid == n_dec + n_book))
+		printf("rank %u tid %d: work %lld barrier %lld round-end %lld clocks, %lld steps\n", rank, tid, clk_work, clk_bar, clk_end, total);
+#endif
 	if (rank != 0)
 		return;
 	if (tid >= n_dec && tid < n_dec + n_book)

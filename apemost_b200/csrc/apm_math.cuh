@@ -285,6 +285,23 @@ APM_HD double jump_unit(int proposal, double u0, double u1) {
 		return u0;
 	return sqrt(-2.0 * log(u0)) * cos(2.0 * 3.14159265358979323846 * u1);
 }
+// two at a time (the same operations on each: the same bits), written side by side so that the
+// two chains of dependent instructions overlap
+APM_HD void jump_unit2(int proposal, double u0a, double u1a, double u0b, double u1b, double & za, double & zb) {
+	if (proposal == 1) {
+		const double qa = u0a / (1 - u0a), qb = u0b / (1 - u0b);
+		za = log(qa);
+		zb = log(qb);
+	} else if (proposal == 2) {
+		za = u0a;
+		zb = u0b;
+	} else {
+		const double la = log(u0a), lb = log(u0b);
+		const double ca = cos(2.0 * 3.14159265358979323846 * u1a), cb = cos(2.0 * 3.14159265358979323846 * u1b);
+		za = sqrt(-2.0 * la) * ca;
+		zb = sqrt(-2.0 * lb) * cb;
+	}
+}
 APM_HD double jump_apply(int proposal, double sigma, double z) {
 	if (proposal == 2)
 		return (-sigma) * (1 - z) + sigma * z;
