@@ -472,6 +472,14 @@ def main():
 
     n_chains = eng.n_chains
     steps_per_round = n_chains * N_SWAP
+    per_rank = None
+    if world > 1:
+        # every rank's own time and SM clock: the job's value is the slowest rank's, and the ranks differ
+        # by the GPUs' own clocks under load, not by anything they wait for (no data-path collective)
+        mine = torch.tensor([total_ms / K, float(clocks.get("sm_mhz") or 0.0)], dtype=torch.float64, device="cuda")
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank = {"ms_per_step": [float(v[0]) for v in every], "sm_mhz": [float(v[1]) for v in every]}
     t = torch.tensor([total_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -544,6 +552,8 @@ def main():
             "cpu_baseline": cpu, "clocks": clocks, "wall_ms_per_step": wall_ms / K,
             "row_evals_per_s": value * N_ROWS,
         }
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         if parity is not None:
             line["multi_gpu_parity"] = parity
             line["extra"] = extra
