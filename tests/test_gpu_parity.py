@@ -245,6 +245,45 @@ def test_run_trajectory_equals_oracle(capi, name, kw, quirks, path):
     assert st_g["swapcount"].sum() > 0, "the test must exercise accepted swaps"
 
 
+@pytest.mark.parametrize("n_ens,n_beta,adapt,kw", [
+    pytest.param(1, 3, False, {}, id="1x3"),
+    pytest.param(2, 7, True, dict(proposal=1), id="2x7-logistic-adapt"),
+    pytest.param(5, 33, False, dict(proposal=2), id="5x33-uniform"),
+    pytest.param(2, 90, True, {}, id="2x90-adapt"),
+    pytest.param(3, 20, False, dict(circular_mask=1), id="3x20-circular"),
+    pytest.param(150, 8, False, {}, id="150x8-more-ensembles-than-sms")])
+def test_data_free_kernel_geometries(capi, n_ens, n_beta, adapt, kw):
+    """free_run_kernel (a cluster of two CTAs per ensemble: deciders with the chain's state in their
+    registers, drawers writing through distributed shared memory, book-keepers) on ladders that do
+    not fill the deciding warps, on more ensembles than SMs, with every proposal kind, a circular
+    parameter, adapt and wide step widths on the hot rungs (redraws beyond the attempts drawn
+    ahead): trajectories, traces and accumulators against the oracle's"""
+    rows = [(20.0, 0.0, 60.0, "x", 4.0)]
+    n = n_ens * n_beta
+    beta = np.tile(np.linspace(1.0, 0.02, n_beta), n_ens)
+    res = []
+    engines = _pair(capi, "normal", n_ens, n_beta, seed=11, path=2, **kw)
+    for eng in engines:
+        eng.set_data(np.zeros((2, 2)))
+        pt_flow.setup_chains(eng, rows)
+        eng.set_chains(0, n, beta=beta, steps=(4.0 * beta ** -0.75)[:, None])
+        eng.set_adapt(adapt, 0.5)
+        eng.reset_stats()
+        eng.run(4, 31, prob_every=1, params_chains=1)
+        tr = eng.read_trace()
+        eng.run(3, 7)
+        res.append((tr, eng.get_chains(), eng.get_stats()))
+    (tr_g, st_g, ac_g), (tr_c, st_c, ac_c) = res
+    assert engines[0].last_path() == 2
+    _compare_state(st_g, st_c)
+    for k in ("prob", "prob_minus_prior", "params"):
+        np.testing.assert_allclose(tr_g[k], tr_c[k], rtol=RTOL_TRAJ, atol=1e-300, err_msg=k)
+    np.testing.assert_array_equal(ac_g["n"], ac_c["n"])
+    for k in ("sum_dl", "sum_params", "sum_params_sq"):
+        np.testing.assert_allclose(ac_g[k], ac_c[k], rtol=RTOL_TRAJ)
+    assert st_g["accept"].sum() > 0 and st_g["reject"].sum() > 0
+
+
 @pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("name,which", [("c1_phases", 2), ("c4_phases", 1), ("c2_phases", 2)])
 def test_marginal_statistics_equal_oracle(capi, name, which, path):
