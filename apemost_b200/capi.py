@@ -297,7 +297,8 @@ class EngineBase:
 
 
 # ---- the product library -------------------------------------------------------
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libapemost_gpu.so")
+# (APEMOST_GPU_LIB: another build of the same library, e.g. a one-model build under build_variants/)
+LIB_PATH = os.environ.get("APEMOST_GPU_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libapemost_gpu.so")
 _lib = None
 
 
