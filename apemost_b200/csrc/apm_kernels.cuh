@@ -806,19 +806,22 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_run_kernel(cons
 // apps/normal.c never touches the data table: a step is Philox + log + sqrt + cos for the jump, the
 // model's closed form, Philox + log for the accept test, and the step's book-keeping -- one long
 // chain of dependent instructions per Metropolis step and nothing to stream, so what counts is
-// how little of it sits between one step's proposal and the next.  One CTA per ensemble, 1024
-// threads in three roles that work on consecutive batches of K = 32 / (n_par + 1) steps at the
-// same time (one CTA barrier per batch):
-//   * PRODUCERS draw batch b + 1: the draws depend on the chain's id and step counter only;
-//   * DECIDERS play batch b.  A model may split its evaluation into independent terms
+// how little of it sits between one step's proposal and the next.  A cluster of two CTAs (two SMs)
+// per ensemble, 512 threads each, in three roles that work on consecutive batches of K steps
+// (16 for one parameter) at the same time, one cluster barrier per batch:
+//   * DRAWERS (CTA 1) draw batch b + 1 straight into CTA 0's shared memory (distributed shared
+//     memory): the draws depend on the chain's id and step counter only, two at a time per thread;
+//   * DECIDERS (CTA 0) play batch b.  A model may split its evaluation into independent terms
 //     (M::LANE_TERMS, term / reduce / finish_reduced: the ten bumps of apps/normal.c): a chain then
-//     has 8 lanes instead of one thread, the terms are dealt out over them and reduced with
-//     shuffles.  Every lane of the group forms the proposal, the new prob and the accept decision
-//     redundantly (same instructions on the same inputs: same bits); the group's first lane moves
-//     the chain (params, prob, prior, best) and leaves the step's outcome in a ring;
-//   * BOOK-KEEPERS write batch b - 1 down from the ring (chain_book_step: counters, n_iter, trace
-//     rows, accumulators), a thread per chain.
+//     has a group of lanes instead of one thread (4 with the chain's whole state in every lane's
+//     registers when the model has a few compile-time parameters, else 8), the terms are dealt out
+//     over them and reduced with shuffles.  Every lane of the group forms the proposal, the new
+//     prob and the accept decision redundantly (same instructions on the same inputs: same bits);
+//     the group's first lane moves the chain and leaves the step's outcome in a ring;
+//   * BOOK-KEEPERS (CTA 0, two warps) write batch b - 1 down from the ring (chain_book_batch:
+//     counters, n_iter, trace rows, accumulators, marginal statistics), a thread per chain.
 // Values and order of operations are those of chain_propose / chain_finalize / chain_record.
+// -DAPM_FREE_CLOCKS prints where a warp of each role spends its clocks.
 #ifndef APM_FREE_THREADS
 #define APM_FREE_THREADS 512 /* (128 registers a thread: the deciders' loop keeps everything in registers) */
 #endif

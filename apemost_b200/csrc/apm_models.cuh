@@ -197,17 +197,20 @@ struct ModelNormal {
 	// passes `a > b`, so it is handed out as NaN without the division.  The divisions by 1 .. 9 are
 	// div_by_known (apm_math.cuh): the IEEE quotient in three instructions.
 	APM_D static double term(int i, const double * p, const double *) {
+		// (written for a short chain of dependent instructions, each step the reference's value bit
+		// for bit: pos - x is -(x - pos) exactly, so |x - pos| is one subtraction with the sign dropped;
+		// 1.0 * v is v; halving is exact, so (-sigma * q^2) / 2 is q^2 * (-sigma / 2))
 		const double x = p[0];
 		const double pos = NORMAL_EXP_I[i];
 		const double height = 10.0;
 		const double sigma = (double) i;
 		const bool even = i % 2 == 0;
-		const double d = x > pos ? x - pos : pos - x;
-		const double num = even ? x - pos : -height * d;
+		const double v0 = x - pos;
+		const double num = (even ? 1.0 : -height) * (even ? v0 : fabs(v0));
 		if (i == 0)
 			return __longlong_as_double(0x7ff8000000000000ll);
 		const double quo = div_by_known(num, sigma, NORMAL_INV_I[i]); // = num / sigma, bit for bit
-		return even ? -sigma * (quo * quo) / 2 + height : quo + height;
+		return (even ? (quo * quo) * (-0.5 * sigma) : quo) + height;
 	}
 	APM_D static double reduce_init() { return 0.0; }                           // b = 0 (:11)
 	APM_D static double reduce(double b, double a) { return a > b ? a : b; }    // if (a > b) b = a (:31-32)

@@ -245,6 +245,27 @@ def test_run_trajectory_equals_oracle(capi, name, kw, quirks, path):
     assert st_g["swapcount"].sum() > 0, "the test must exercise accepted swaps"
 
 
+def test_normal_model_value_is_the_oracles_bit_for_bit(capi):
+    """apps/normal.c on the device is written for a short chain of dependent instructions (|x - pos| as
+    a subtraction with the sign dropped, the divisions by 1..9 as div_by_known, -sigma q^2 / 2 as
+    q^2 (-sigma / 2)): every one of these is the reference's value exactly, so calc_model agrees with
+    the oracle's plain restatement in every bit, on a dense sweep of the range, at the bumps'
+    centres and next to them"""
+    rng = np.random.default_rng(5)
+    centres = np.exp(np.arange(10.0))
+    x = np.concatenate([rng.uniform(-10, 10000, 200_000), rng.uniform(0, 60, 200_000), centres,
+                        np.nextafter(centres, 0), np.nextafter(centres, 1e9), (centres + rng.normal(0, 1e-9, (50, 10))).ravel()])
+    beta = rng.uniform(0.01, 1.0, x.size)
+    e, o = _pair(capi, "normal", 1, 2)
+    out = []
+    for eng in (e, o):
+        eng.set_data(np.zeros((2, 2)))
+        eng.set_bounds([-10.0], [10000.0])
+        out.append(eng.eval(x[:, None], beta))
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+
+
 @pytest.mark.parametrize("n_ens,n_beta,adapt,kw", [
     pytest.param(1, 3, False, {}, id="1x3"),
     pytest.param(2, 7, True, dict(proposal=1), id="2x7-logistic-adapt"),
