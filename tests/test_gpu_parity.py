@@ -245,6 +245,59 @@ def test_run_trajectory_equals_oracle(capi, name, kw, quirks, path):
     assert st_g["swapcount"].sum() > 0, "the test must exercise accepted swaps"
 
 
+def test_error_codes_and_the_handle_stays_usable(capi):
+    """error behaviour across the C ABI (include/apemost_gpu.h: negative APM_E* codes, a message in
+    apm_gpu_last_error, nothing thrown, nothing exits): the reference asserts or exit(1)s in these
+    situations; the library reports them and the handle stays usable"""
+    E = capi.EngineError
+
+    def code(fn, *a, **kw):
+        with pytest.raises(E) as ei:
+            fn(*a, **kw)
+        assert str(ei.value), "a message must come with the code"
+        return ei.value.code
+
+    # create: geometry, parameter count, model id
+    assert code(capi.Engine, "simplesin", 0, 4) == -1
+    assert code(capi.Engine, "simplesin", 1, 4, n_par=3) == -1
+    assert code(capi.Engine, "pulse", 1, 4, n_par=5) == -1
+    assert code(capi.Engine, 99, 1, 4, n_par=2) == -1
+    e = capi.Engine("simplesin", 2, 5, seed=3)
+    data = lightcurve(700)
+    # call order: nothing runs before the table and the bounds are there
+    assert code(e.eval, np.zeros((1, 4))) == -5
+    assert code(e.run, 1, 3) == -5
+    assert code(e.calibrate) == -5
+    e._marg = (2, 20, 8)                                       # (what set_marginals would have remembered)
+    assert code(e.get_marginals) == -5
+    # arguments
+    assert code(e.set_data, np.zeros((10, 1))) == -1          # the model reads two columns
+    assert code(e.set_bounds, [0, 0, 0, 2.0], [1, 1, 1, 1.0]) == -1   # min > max
+    assert code(e.set_chains, 8, 5, beta=np.ones(5)) == -1     # chains [8, 13) of 10
+    assert code(e.get_chains, 9, 2) == -1
+    assert code(e.set_adapt, True, 1.5) == -1
+    assert code(e.set_marginals, 7, 20, 5, 8) == -1
+    # ... and the handle is as good as new
+    e.set_data(data)
+    pt_flow.setup_chains(e, [(1.3, 0.0, 3.0, "a", 0.01), (7.25, 4.0, 10.0, "f", 1e-4), (0.31, 0.0, 1.0, "p", 0.01),
+                             (0.2, -1.0, 1.0, "o", 0.01)])
+    assert code(e.run, 1, 3, prob_every=-1) == -1              # bad trace configuration
+    o = Oracle("simplesin", 2, 5, seed=3, rng=RNG_PHILOX)
+    o.set_data(data)
+    pt_flow.setup_chains(o, [(1.3, 0.0, 3.0, "a", 0.01), (7.25, 4.0, 10.0, "f", 1e-4), (0.31, 0.0, 1.0, "p", 0.01),
+                             (0.2, -1.0, 1.0, "o", 0.01)])
+    for eng in (e, o):
+        eng.set_chains(0, 10, beta=np.tile(np.linspace(1, 0.2, 5), 2))
+        eng.run(3, 7)
+    _compare_state(e.get_chains(), o.get_chains())
+    # a path that does not apply, asked for by name
+    f = capi.Engine("simplesin", 1, 4, seed=1, path=2)
+    f.set_data(lightcurve(60000))                              # 960 KB: more than an SM's shared memory
+    pt_flow.setup_chains(f, [(1.3, 0.0, 3.0, "a", 0.01), (7.25, 4.0, 10.0, "f", 1e-4), (0.31, 0.0, 1.0, "p", 0.01),
+                             (0.2, -1.0, 1.0, "o", 0.01)])
+    assert code(f.run, 1, 3) == -1
+
+
 def test_normal_model_value_is_the_oracles_bit_for_bit(capi):
     """apps/normal.c on the device is written for a short chain of dependent instructions (|x - pos| as
     a subtraction with the sign dropped, the divisions by 1..9 as div_by_known, -sigma q^2 / 2 as
