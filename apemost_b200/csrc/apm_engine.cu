@@ -381,10 +381,13 @@ extern "C" int apm_gpu_destroy(apm_gpu * h) {
 }
 
 // ------------------------------------------------------------------ launch plan
-// How many row splits for n_slots chains in tiles of `tile`: work items = chain tiles x
-// splits are dealt round-robin to the persistent grid, so pick the split count whose last
-// round is fullest (all items of a plan cost the same), charging a small per-item overhead
-// (parameter load + fold) so that items do not get needlessly small.
+// How many row splits for n_slots chains in tiles of `tile`.  Work items = chain tiles x splits
+// are dealt round-robin to the persistent grid, split-major, and a split has n_chunks / n_splits
+// chunks (the first n_chunks % n_splits one more): a CTA's items come from all over the table, so
+// its load is (its number of items) x (the mean split) but for the last, partly filled round,
+// whose items are from the last -- the smaller -- splits.  Pick the count with the shortest
+// makespan, charging a small per-item overhead (parameter load + fold) so that items do not get
+// needlessly small.
 static void make_plan(const apm_gpu * h, int n_slots, int tile, int & n_splits, int & cps) {
 	const int n_chunks = std::max(h->n_chunks, 1);
 	const long long grid = std::max(h->ll_grid, 1);
@@ -392,7 +395,6 @@ static void make_plan(const apm_gpu * h, int n_slots, int tile, int & n_splits, 
 	if (const char * t = getenv("APM_SPLITS")) { // kernel-sweep override
 		n_splits = std::max(1, std::min(atoi(t), n_chunks));
 		cps = (n_chunks + n_splits - 1) / n_splits;
-		n_splits = (n_chunks + cps - 1) / cps;
 		return;
 	}
 	const double item_overhead = 0.15; // in units of one chunk's compute time
@@ -400,17 +402,15 @@ static void make_plan(const apm_gpu * h, int n_slots, int tile, int & n_splits, 
 	n_splits = 1;
 	cps = n_chunks;
 	for (int s = 1; s <= std::min(n_chunks, 512); s++) {
-		const int c = (n_chunks + s - 1) / s;
-		const int s_eff = (n_chunks + c - 1) / c;
-		if (s_eff != s)
-			continue;
-		const long long items = n_ctiles * s_eff;
-		const long long rounds = (items + grid - 1) / grid;
-		const double makespan = rounds * (c + item_overhead);
+		const int base = n_chunks / s;
+		const double mean = (double) n_chunks / s;
+		const long long items = n_ctiles * s;
+		const long long full = items / grid, rest = items % grid;
+		const double makespan = full * (mean + item_overhead) + (rest ? base + item_overhead : 0.0);
 		if (makespan < best * (1 - 1e-9)) {
 			best = makespan;
-			n_splits = s_eff;
-			cps = c;
+			n_splits = s;
+			cps = (n_chunks + s - 1) / s;
 		}
 	}
 }

@@ -164,8 +164,8 @@ struct LLArgs {
 	const int * act_n;      // device-side length of act_idx (read only when act_idx != NULL)
 	int n_slots;
 	int n_par;
-	int n_splits;
-	int chunks_per_split;
+	int n_splits;           // the table's chunks are dealt over the splits as evenly as they go: split s has
+	int chunks_per_split;   // n_chunks / n_splits chunks, the first n_chunks % n_splits one more (this: the larger count)
 	int n_chunks;
 	const double * xabsmax; // device scalar: max |x| over the table (bound for the fast sine)
 	double * partial;       // [n_slots][n_splits]
@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(LL_LAUNCH_THREADS, 1) loglik_tiled_kernel(cons
 	const int n_items = n_ctiles * a.n_splits; // < 2^31, checked by the host
 	const double xub = *a.xabsmax;
 	constexpr uint32_t CHUNK_BYTES = CHUNK * sizeof(Row<M>);
+	const int sp_base = a.n_chunks / a.n_splits, sp_rem = a.n_chunks - sp_base * a.n_splits; // chunks of a split
 
 	// ---- producer warpgroup: gives its registers back; its first lane walks this CTA's items chunk by
 	// chunk, as far ahead as the ring allows (a stage is free again once every compute warp has
@@ -235,8 +236,9 @@ __global__ void __launch_bounds__(LL_LAUNCH_THREADS, 1) loglik_tiled_kernel(cons
 		if (warp == LL_WARPS && lane == 0) {
 			uint32_t p_st = 0, p_phase = 1, p_n = 0;
 			for (int p_item = blockIdx.x; p_item < n_items; p_item += gridDim.x) {
-				const int k0 = (p_item / n_ctiles) * a.chunks_per_split;
-				const int nk = min(a.chunks_per_split, a.n_chunks - k0);
+				const int p_split = p_item / n_ctiles;
+				const int k0 = p_split * sp_base + min(p_split, sp_rem);
+				const int nk = sp_base + (p_split < sp_rem ? 1 : 0);
 				const double * src = a.data + (size_t) k0 * CHUNK * M::ROW_W;
 				for (int p_k = 0; p_k < nk; p_k++, p_n++, src += (size_t) CHUNK * M::ROW_W) {
 					if (p_n >= LL_STAGES) // the chunk that was in this stage must have been read by every warp
@@ -259,8 +261,8 @@ __global__ void __launch_bounds__(LL_LAUNCH_THREADS, 1) loglik_tiled_kernel(cons
 		const int split = item / n_ctiles;
 		const int ctile = item - split * n_ctiles; // chain tile fastest: neighbours share rows in L2
 		const int c0 = ctile * C;
-		const int k0 = split * a.chunks_per_split;
-		const int nk = min(a.chunks_per_split, a.n_chunks - k0);
+		const int k0 = split * sp_base + min(split, sp_rem);
+		const int nk = sp_base + (split < sp_rem ? 1 : 0);
 
 		typename M::Prep q[C];
 		int gid[C];
