@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(FUSED_MAX_WARPS * 32, 1) fused_run_kernel(cons
 #define APM_FREE_THREADS 512 /* (128 registers a thread: the deciders' loop keeps everything in registers) */
 #endif
 constexpr int FREE_THREADS = APM_FREE_THREADS, FREE_BOOK_WARPS = 2, FREE_CLUSTER = 2;
-constexpr int FREE_MAX_DECIDERS = (FREE_THREADS - 32 * FREE_BOOK_WARPS - 32) / 128 * 128; // (a warp is left for the swap's draws)
+constexpr int FREE_MAX_DECIDERS = (FREE_THREADS - 32 * FREE_BOOK_WARPS - 32) / 128 * 128; static_assert(FREE_MAX_DECIDERS >= 128 && FREE_MAX_DECIDERS + 32 * FREE_BOOK_WARPS < FREE_THREADS, "a warp must be left for the swap's draws");
 
 template<class M, class = void> struct ModelLaneTerms { static constexpr int value = 0; };
 template<class M> struct ModelLaneTerms<M, std::void_t<decltype(M::LANE_TERMS)>> { static constexpr int value = M::LANE_TERMS; };
