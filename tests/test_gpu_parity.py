@@ -358,6 +358,46 @@ def test_data_free_kernel_geometries(capi, n_ens, n_beta, adapt, kw):
     assert st_g["accept"].sum() > 0 and st_g["reject"].sum() > 0
 
 
+def test_data_free_long_run_equals_oracle(capi):
+    """31 000 Metropolis steps of 2 x 64 chains of apps/normal.c in ONE launch of free_run_kernel
+    (2000 batches, 1000 swap rounds) with -DADAPT on and the counters started next to its
+    thresholds: ensemble 0 adapts from the first round and has its counters reset at 100 000,
+    ensemble 1 starts adapting at 20 000; the hot rungs' step widths grow to several times the
+    range, so most of their proposals need more redraws than are drawn ahead.  State, counters
+    and accumulators equal the oracle's at the end: every one of the 4 M accept decisions and
+    23 000 adapt decisions is the oracle's.  (Not longer: with a flat hot rung the reference's adapt rule grows
+    the step width without bound, and the redraw loop with it -- in the reference as here.)"""
+    rows = [(20.0, -10.0, 10000.0, "x", 4.0)]
+    n_ens, n_beta = 2, 64
+    n = n_ens * n_beta
+    beta = np.tile(np.linspace(1.0, 0.01, n_beta), n_ens)
+    start = 30.0 * beta ** -0.5
+    pa = np.full((n, 1), 52000, dtype=np.uint64)
+    pa[n_beta:] = 2000
+    res = []
+    engines = _pair(capi, "normal", n_ens, n_beta, seed=23, path=2)
+    for eng in engines:
+        eng.set_data(np.zeros((2, 2)))
+        pt_flow.setup_chains(eng, rows)
+        eng.set_chains(0, n, beta=beta, steps=start[:, None], params_accepts=pa,
+                       params_rejects=(pa * 0.9).astype(np.uint64))
+        eng.set_adapt(True, 0.5)
+        eng.reset_stats()
+        eng.run(1000, 31)
+        res.append((eng.get_chains(), eng.get_stats()))
+    (st_g, ac_g), (st_c, ac_c) = res
+    assert engines[0].last_path() == 2
+    _compare_state(st_g, st_c)   # counters equal; values to 1e-9 (the jumps' log / sqrt / cos are the device library's)
+    np.testing.assert_array_equal(st_g["steps"], st_c["steps"])
+    np.testing.assert_array_equal(ac_g["n"], ac_c["n"])
+    for k in ("sum_dl", "sum_params", "sum_params_sq"):
+        np.testing.assert_allclose(ac_g[k], ac_c[k], rtol=RTOL_TRAJ)
+    assert (st_g["n_iter"] == 31000).all()
+    assert (st_g["params_accepts"] + st_g["params_rejects"] < 100000).all(), "adapt must have reset ensemble 0's counters"
+    ratio = st_g["steps"][:, 0] / start
+    assert ratio.max() > 50 and ratio.min() < 0.05, "adapt must have moved the step widths a long way"
+
+
 @pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("name,which", [("c1_phases", 2), ("c4_phases", 1), ("c2_phases", 2)])
 def test_marginal_statistics_equal_oracle(capi, name, which, path):
